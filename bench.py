@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the dynamic attentive graph block on B200.
+
+Contract (see task brief):  python bench.py --gpus N --steps K --warmup W
+prints ONE JSON line on rank 0.  A "step" is one graph-block forward
+(``CE.forward``, DN_Gray/model/dagl.py:207-275) on one 64-channel 256x256
+feature map per GPU — the shape BASELINE.json's metric is quoted on
+("patches/sec + ms/graph-block fwd, 64ch 256x256").
+
+  value        query patches/s (B*Nq / t) with the input resident in HBM, all GPUs
+  e2e          the same through the host-buffer C-ABI entry (pinned host input,
+               H2D + forward + D2H of the result inside the timed region)
+  roofline     dominant fused graph kernel: algorithmic FLOPs / measured kernel
+               time against the measured bf16 tensor peak (the path is a dense
+               contraction pair) + algorithmic HBM GB/s for context
+  cpu_baseline the CPU oracle port of the reference timed on this box's cores
+
+``--impl reference`` times the oracle port (reference op order, torch CPU,
+all host threads) on the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 256
+C_IN = 64
+B_PER_GPU = 1
+NQ = ((H + 3) // 4) * ((W + 3) // 4)
+NK = H * W
+FLOPS_ALG = 2.0 * NQ * NK * (196 + 784)                       # 526.1 GFLOP / image
+BYTES_ALG = 4.0 * (NQ * 196 + NK * 196 + 196 + 2 * NQ + 32 * NK)  # 63.0 MB / image
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained"), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def workload_tensors(seed: int):
+    """Synthetic, seeded: random-init head (torch default init statistics) and a randn feature map."""
+    from oracle import ce_oracle as O     # only for the shared seeded parameter generator
+    params = O.init_ce_params(1000 + seed, in_channels=C_IN)
+    gen = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(B_PER_GPU, C_IN, H, W, generator=gen)
+    return params, x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle port, reference op order)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ce_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params, x = workload_tensors(0)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.ce_forward(params, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.ce_forward(params, x)
+        dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = B_PER_GPU * NQ / (ms * 1e-3)
+    out = {
+        "impl": "reference", "metric": "graph-block query patches/s (64ch 256x256)", "value": value,
+        "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} (one graph block, direct/no-chop), random-init head",
+                   "Nq": NQ, "Nk": NK},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"full workload, {args.steps} steps after {args.warmup} warm-up, oracle.ce_forward (reference op order, torch CPU)"},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_sample():
+    from oracle import ce_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params, x = workload_tensors(0)
+    with torch.no_grad():
+        O.ce_forward(params, x)                       # warm-up
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.ce_forward(params, x)
+            ts.append(time.perf_counter() - t0)
+    best = min(ts)
+    return {"value": B_PER_GPU * NQ / best, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"full workload (1x{C_IN}x{H}x{W}), 1 warm-up + best of 3, oracle.ce_forward (reference op order, torch CPU); {best*1e3:.0f} ms",
+            "ms_per_step": best * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="auto", choices=["auto", "simt", "tc", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import dagl_b200
+    from dagl_b200 import _lib, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = _lib.lib()
+    params, x_host = workload_tensors(rank)
+    ce = dagl_b200.CE(in_channels=C_IN, impl=args.impl)
+    ce.load_state_dict(params)
+    ce = ce.to(dev).eval()
+    x_dev = x_host.to(dev)
+    x_pin = x_host.pin_memory()
+    y_pin = torch.empty(B_PER_GPU, 16, H, W).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value) --------------------------------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            ce(x_dev)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        L.dagl_profile_enable(1)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        launches = 0
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                              # L2 flush between timed iterations (untimed)
+            starts[i].record()
+            ce(x_dev)
+            stops[i].record()
+            launches += ce.last_launches
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        kbuf = (ctypes.c_float * 256)()
+        nk = L.dagl_profile_read(kbuf, 256)
+        L.dagl_profile_enable(0)
+        clocks = sampler.stop() if rank == 0 else None
+        step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+        total_ms = sum(step_ms)
+        impl_used = ce.last_impl
+
+        # ---- end-to-end through the host-buffer entry (e2e) -----------------------
+        for _ in range(2):
+            ce.forward_host(x_pin, y_pin, device=dev)
+        barrier()
+        e_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        e_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.zero_()
+            e_starts[i].record()
+            ce.forward_host(x_pin, y_pin, device=dev, sync=False)
+            e_stops[i].record()
+        barrier()
+        e2e_total_ms = sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))
+        checksum = float(y_pin.double().abs().sum())
+
+    total_ms = parallel.max_over_ranks(total_ms, dev)
+    e2e_total_ms = parallel.max_over_ranks(e2e_total_ms, dev)
+    launches_all = int(parallel.sum_over_ranks(launches, dev))
+    ms_per_step = total_ms / args.steps
+    patches_per_step = world * B_PER_GPU * NQ
+    value = patches_per_step / (ms_per_step * 1e-3)
+    e2e_value = patches_per_step / (e2e_total_ms / args.steps * 1e-3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        kern_ms = [kbuf[i] for i in range(nk)]
+        k_avg = sum(kern_ms) / len(kern_ms) if kern_ms else float("nan")
+        achieved_tflops = B_PER_GPU * FLOPS_ALG / (k_avg * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(impl_used, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": traffic,
+            "peak_source": f"{peaks['source']} bf16 dense burst (MEASURED_PEAKS.json)",
+            "kernel": f"attend_{impl_used}", "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
+            "flops_per_launch": B_PER_GPU * FLOPS_ALG, "bytes_per_launch": B_PER_GPU * BYTES_ALG,
+            "hbm_gbs_algorithmic": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9,
+            "hbm_frac_of_measured": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        }
+        out = {
+            "metric": "graph-block query patches/s (64ch 256x256)", "value": value, "unit": "patches/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} per GPU (one graph block, direct/no-chop), random-init head",
+                       "Nq": NQ, "Nk": NK, "impl": impl_used, "l2": "flushed between timed iterations (256 MiB memset)",
+                       "timing": "CUDA events per step, summed; max over ranks"},
+            "ms_per_graph_block": ms_per_step, "pairs_per_s": world * B_PER_GPU * NQ * NK / (ms_per_step * 1e-3),
+            "wall_s_timed_region": t_wall,
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": B_PER_GPU * C_IN * H * W * 4,
+                    "d2h_bytes_per_step": B_PER_GPU * 16 * H * W * 4, "ms_per_step": e2e_total_ms / args.steps,
+                    "api": "CE.forward_host -> dagl_ce_forward_host_f32 (pinned host buffers)", "checksum": checksum},
+            "gpu_launches": launches_all, "roofline": roofline, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

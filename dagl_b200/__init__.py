@@ -1,0 +1,12 @@
+"""dagl_b200 — B200-native (sm_100a) implementation of DAGL's dynamic attentive
+graph block (reference: jianzhangcs/DAGL, */model/dagl.py classes CE / CES).
+
+Public surface:
+    CE, CES            drop-in nn.Modules (reference constructor / state_dict)
+    patch_reference    swap reference CE instances inside a built network
+    install            rebind model.dagl.CE before make_model(args)
+"""
+from .ce import CE, CES, install, patch_reference  # noqa: F401
+from . import _lib  # noqa: F401
+
+__all__ = ["CE", "CES", "install", "patch_reference"]

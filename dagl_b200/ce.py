@@ -1,0 +1,271 @@
+"""Drop-in ``CE`` / ``CES`` modules backed by the sm_100a C-ABI library.
+
+``CE`` mirrors the reference module (DN_Gray/model/dagl.py:174-277): same
+constructor signature and defaults, same parameter names and shapes (so a
+reference ``state_dict`` / checkpoint loads unchanged, including the unused
+``W`` conv), same ``forward(b) -> [B, inter_channels, H, W]``.  The body of
+``forward`` is one call through ``dagl_ce_forward_f32`` (include/dagl_b200.h);
+there is no PyTorch/CPU fallback — CPU tensors, non-fp32 input, unsupported
+configurations or a missing library raise.
+
+``CES`` mirrors dagl.py:74-119 (3 stages x 4 heads, 1x1 merge convs, two
+groups of 4 ResBlocks) so the caller row can be exercised without the
+reference being importable; its convolutions are plain ``torch.nn`` layers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_WS_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Caller-owned workspace, allocated through torch's caching allocator so the
+    usual stream semantics hold.  One buffer per device, grown on demand."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+class CE(nn.Module):
+    """Dynamic attentive graph head.  Constructor mirrors dagl.py:175-176."""
+
+    def __init__(self, ksize=7, stride_1=4, stride_2=1, softmax_scale=10, shape=64, p_len=64, in_channels=64,
+                 inter_channels=16, use_multiple_size=False, use_topk=False, add_SE=False, num_edge=50,
+                 impl: str = "auto"):
+        super().__init__()
+        self.ksize = ksize
+        self.shape = shape
+        self.p_len = p_len
+        self.stride_1 = stride_1
+        self.stride_2 = stride_2
+        self.softmax_scale = softmax_scale
+        self.inter_channels = inter_channels
+        self.in_channels = in_channels
+        self.use_multiple_size = use_multiple_size
+        self.use_topk = use_topk          # stored, never read (as in the reference, dagl.py:187)
+        self.add_SE = add_SE
+        self.num_edge = num_edge
+        self.impl = impl
+        # Parameter containers only: the convolutions/linears below are never
+        # *called*; the CUDA kernels read their weights directly.
+        self.g = nn.Conv2d(in_channels, inter_channels, kernel_size=3, stride=1, padding=1)
+        self.W = nn.Conv2d(inter_channels, in_channels, kernel_size=1, stride=1, padding=0)   # dead in forward
+        self.theta = nn.Conv2d(in_channels, inter_channels, kernel_size=1, stride=1, padding=0)
+        d = ksize ** 2 * inter_channels
+        self.fc1 = nn.Sequential(nn.Linear(d, d // 4), nn.ReLU())
+        self.fc2 = nn.Sequential(nn.Linear(d, d // 4), nn.ReLU())
+        self.thr_conv = nn.Conv2d(in_channels, 1, kernel_size=ksize, stride=stride_1, padding=0)
+        self.bias_conv = nn.Conv2d(in_channels, 1, kernel_size=ksize, stride=stride_1, padding=0)
+        self.last_impl: Optional[str] = None
+        self.last_launches: int = 0
+
+    # -- C-ABI plumbing -------------------------------------------------------
+    def _weights(self, device: torch.device) -> Tuple[_lib.DaglCEWeights, list]:
+        keep = []
+
+        def ptr(t: torch.Tensor) -> int:
+            if t.device != device or t.dtype != torch.float32:
+                raise RuntimeError("CE parameters must be fp32 on the input's CUDA device")
+            t = t.detach().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.DaglCEWeights(
+            g_w=ptr(self.g.weight), g_b=ptr(self.g.bias),
+            theta_w=ptr(self.theta.weight), theta_b=ptr(self.theta.bias),
+            fc1_w=ptr(self.fc1[0].weight), fc1_b=ptr(self.fc1[0].bias),
+            fc2_w=ptr(self.fc2[0].weight), fc2_b=ptr(self.fc2[0].bias),
+            thr_w=ptr(self.thr_conv.weight), thr_b=ptr(self.thr_conv.bias),
+            bias_w=ptr(self.bias_conv.weight), bias_b=ptr(self.bias_conv.bias),
+            in_channels=self.in_channels, inter_channels=self.inter_channels, ksize=self.ksize,
+            stride_q=self.stride_1, stride_k=self.stride_2, softmax_scale=float(self.softmax_scale))
+        return w, keep
+
+    def _check_input(self, b: torch.Tensor) -> None:
+        if not isinstance(b, torch.Tensor) or b.dim() != 4:
+            raise RuntimeError("CE.forward expects a [B, C, H, W] tensor")
+        if b.dtype != torch.float32:
+            raise RuntimeError("CE.forward: fp32 only (the reference default precision)")
+        if b.shape[1] != self.in_channels:
+            raise RuntimeError(f"CE.forward: expected {self.in_channels} channels, got {b.shape[1]}")
+        if torch.is_grad_enabled() and (b.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "dagl_b200.CE is forward-only; call it under torch.no_grad() (training/backward is a "
+                "'next' row, SURVEY.md §8f)")
+
+    def forward(self, b: torch.Tensor) -> torch.Tensor:
+        self._check_input(b)
+        if not b.is_cuda:
+            raise RuntimeError("dagl_b200.CE has no CPU path: input must be a CUDA tensor "
+                               "(use forward_host for pinned host buffers)")
+        L = _lib.lib()
+        b = b.contiguous()
+        B, Cc, H, W = b.shape
+        with torch.cuda.device(b.device):
+            y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
+            nbytes = L.dagl_ce_workspace_bytes(B, Cc, H, W)
+            ws = _workspace(b.device, nbytes)
+            w, keep = self._weights(b.device)
+            stream = torch.cuda.current_stream(b.device).cuda_stream
+            rc = L.dagl_ce_forward_f32(C.byref(w), b.data_ptr(), y.data_ptr(), B, H, W, ws.data_ptr(),
+                                       ws.numel(), _lib.IMPL_BY_NAME[self.impl], stream)
+            _lib.check(rc, "dagl_ce_forward_f32")
+            self.last_impl = L.dagl_last_impl().decode()
+            self.last_launches = L.dagl_last_launch_count()
+        return y
+
+    def forward_debug(self, b: torch.Tensor):
+        """forward + the neighbour selection of dagl.py:256-257.
+        Returns (y, mask_bits int32 [B,Nq,ceil(Nk/32)], nnz int32 [B,Nq])."""
+        self._check_input(b)
+        if not b.is_cuda:
+            raise RuntimeError("dagl_b200.CE has no CPU path")
+        L = _lib.lib()
+        b = b.contiguous()
+        B, Cc, H, W = b.shape
+        nq = ((H + 3) // 4) * ((W + 3) // 4)
+        nw = (H * W + 31) // 32
+        with torch.cuda.device(b.device):
+            y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
+            bits = torch.empty(B, nq, nw, dtype=torch.int32, device=b.device)
+            nnz = torch.empty(B, nq, dtype=torch.int32, device=b.device)
+            ws = _workspace(b.device, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+            w, keep = self._weights(b.device)
+            stream = torch.cuda.current_stream(b.device).cuda_stream
+            rc = L.dagl_ce_forward_debug_f32(C.byref(w), b.data_ptr(), y.data_ptr(), B, H, W, ws.data_ptr(),
+                                             ws.numel(), _lib.IMPL_BY_NAME[self.impl], stream,
+                                             bits.data_ptr(), nnz.data_ptr())
+            _lib.check(rc, "dagl_ce_forward_debug_f32")
+            self.last_impl = L.dagl_last_impl().decode()
+            self.last_launches = L.dagl_last_launch_count()
+        return y, bits, nnz
+
+    def intermediates(self, b_shape) -> Dict[str, torch.Tensor]:
+        """Copies of the prologue results left in the workspace by the last
+        forward on this device (parity tests): G, theta, gamma, beta, Q, K, Kbar."""
+        L = _lib.lib()
+        B, Cc, H, W = b_shape
+        dev = self.g.weight.device
+        ws = _workspace(dev, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+        nq = ((H + 3) // 4) * ((W + 3) // 4)
+        nk = H * W
+        shapes = {"G": (0, (B, 16, H, W)), "theta": (1, (B, 16, H, W)), "gamma": (2, (B, nq)),
+                  "beta": (3, (B, nq)), "Q": (4, (B, nq, 196)), "K": (5, (B, nk, 196)), "Kbar": (6, (B, 196))}
+        out = {}
+        for name, (which, shp) in shapes.items():
+            p = L.dagl_ce_workspace_view(ws.data_ptr(), which, B, Cc, H, W)
+            off = (p - ws.data_ptr())
+            n = 1
+            for d in shp:
+                n *= d
+            out[name] = ws[off:off + 4 * n].view(torch.float32).view(*shp).clone()
+        return out
+
+    def forward_host(self, b_host: torch.Tensor, y_host: Optional[torch.Tensor] = None,
+                     device: Optional[torch.device] = None, sync: bool = True) -> torch.Tensor:
+        """Host-buffer entry (``dagl_ce_forward_host_f32``): ``b_host`` is a CPU
+        tensor (pinned for async copies); returns a pinned CPU tensor.  The H2D
+        copy, the kernels and the D2H copy are enqueued on the current stream."""
+        self._check_input(b_host)
+        if b_host.is_cuda:
+            raise RuntimeError("forward_host expects a host tensor")
+        L = _lib.lib()
+        device = device or self.g.weight.device
+        b_host = b_host.contiguous()
+        B, Cc, H, W = b_host.shape
+        if y_host is None:
+            y_host = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32).pin_memory()
+        with torch.cuda.device(device):
+            nbytes = L.dagl_ce_workspace_bytes(B, Cc, H, W) + L.dagl_ce_host_staging_bytes(B, Cc, H, W)
+            ws = _workspace(device, nbytes)
+            w, keep = self._weights(device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            rc = L.dagl_ce_forward_host_f32(C.byref(w), b_host.data_ptr(), y_host.data_ptr(), B, H, W,
+                                            ws.data_ptr(), ws.numel(), _lib.IMPL_BY_NAME[self.impl], stream)
+            _lib.check(rc, "dagl_ce_forward_host_f32")
+            self.last_impl = L.dagl_last_impl().decode()
+            self.last_launches = L.dagl_last_launch_count()
+            if sync:
+                torch.cuda.current_stream(device).synchronize()
+        return y_host
+
+
+class _ResBlock(nn.Module):
+    """conv3x3 - PReLU - conv3x3, + x  (reference common.ResBlock, common.py:59-79,
+    same parameter names: body.0 / body.1 / body.2)."""
+
+    def __init__(self, n_feats: int):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(n_feats, n_feats, 3, padding=1), nn.PReLU(),
+                                  nn.Conv2d(n_feats, n_feats, 3, padding=1))
+
+    def forward(self, x):
+        return self.body(x) + x
+
+
+class CES(nn.Module):
+    """3 stages x 4 CE heads (dagl.py:74-119); state_dict-compatible with the reference CES."""
+
+    def __init__(self, in_channels: int, num: int = 4, impl: str = "auto"):
+        super().__init__()
+        self.RBS1 = nn.Sequential(*[_ResBlock(in_channels) for _ in range(num)])
+        self.RBS2 = nn.Sequential(*[_ResBlock(in_channels) for _ in range(num)])
+        for s in (1, 2, 3):
+            for h in (1, 2, 3, 4):
+                setattr(self, f"c{s}_{h}", CE(in_channels=in_channels, impl=impl))
+            setattr(self, f"c{s}_c", nn.Conv2d(in_channels, in_channels, 1, 1, 0))
+
+    def _stage(self, s: int, x: torch.Tensor) -> torch.Tensor:
+        heads = [getattr(self, f"c{s}_{h}")(x) for h in (1, 2, 3, 4)]
+        return getattr(self, f"c{s}_c")(torch.cat(heads, dim=1)) + x
+
+    def forward(self, x):
+        out = self._stage(1, x)
+        out = self.RBS1(out)
+        out = self._stage(2, out)
+        out = self.RBS2(out)
+        return self._stage(3, out)
+
+
+def patch_reference(module: nn.Module, impl: str = "auto") -> int:
+    """Replace every reference ``CE`` instance inside ``module`` (e.g. an ``RR``
+    or ``CES`` built by the unmodified reference code) with a ``dagl_b200.CE``
+    that *shares* the same Parameters.  Returns the number of heads swapped."""
+    n = 0
+    for parent in module.modules():
+        for name, child in list(parent.named_children()):
+            if type(child).__name__ == "CE" and not isinstance(child, CE) and hasattr(child, "thr_conv"):
+                new = CE(ksize=child.ksize, stride_1=child.stride_1, stride_2=child.stride_2,
+                         softmax_scale=child.softmax_scale, shape=child.shape, p_len=child.p_len,
+                         in_channels=child.in_channels, inter_channels=child.inter_channels,
+                         use_multiple_size=child.use_multiple_size, use_topk=child.use_topk,
+                         add_SE=child.add_SE, num_edge=child.num_edge, impl=impl)
+                for sub in ("g", "W", "theta", "fc1", "fc2", "thr_conv", "bias_conv"):
+                    setattr(new, sub, getattr(child, sub))
+                setattr(parent, name, new)
+                n += 1
+    return n
+
+
+def install(ref_dagl_module, impl: str = "auto") -> None:
+    """Rebind ``model.dagl.CE`` so that ``make_model(args)`` of the unmodified
+    reference (model/__init__.py:92-93) builds networks on the CUDA head."""
+    default_impl = impl
+
+    class _CE(CE):
+        def __init__(self, *a, **k):
+            k.setdefault("impl", default_impl)
+            super().__init__(*a, **k)
+
+    _CE.__name__ = "CE"
+    ref_dagl_module.CE = _CE

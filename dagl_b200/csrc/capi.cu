@@ -1,0 +1,263 @@
+// C-ABI of dagl_b200 (see include/dagl_b200.h).  Thin dispatch only: validates
+// arguments, carves the caller-owned workspace and enqueues the kernels on the
+// caller's stream.  No allocation, no synchronisation, no CPU fallback.
+#include "../../include/dagl_b200.h"
+#include "common.cuh"
+
+namespace dagl {
+CallState& call_state() {
+  static thread_local CallState s;
+  return s;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int prof_begin(cudaStream_t st) {
+  CallState& s = call_state();
+  if (!s.prof_on || s.prof_n >= PROF_RING) return 0;
+  DAGL_CUDA_OK(cudaEventRecord(s.prof_start[s.prof_n], st));
+  return 0;
+}
+int prof_end(cudaStream_t st) {
+  CallState& s = call_state();
+  if (!s.prof_on || s.prof_n >= PROF_RING) return 0;
+  DAGL_CUDA_OK(cudaEventRecord(s.prof_stop[s.prof_n], st));
+  s.prof_n++;
+  return 0;
+}
+
+// Workspace carve-up shared by workspace_bytes / forward / workspace_view.
+struct WsLayout {
+  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, attend, total;
+  int kblocks;
+};
+
+static WsLayout ws_layout(const Geom& g) {
+  WsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t f = sizeof(float);
+  L.kblocks = embed_num_blocks(g.Nk);
+  L.G = take((size_t)g.B * CI * g.Nk * f);
+  L.Th = take((size_t)g.B * CI * g.Nk * f);
+  L.gamma = take((size_t)g.B * g.Nq * f);
+  L.beta = take((size_t)g.B * g.Nq * f);
+  L.Q = take((size_t)g.B * g.Nq * ED * f);
+  L.K = take((size_t)g.B * g.Nk * ED * f);
+  L.kpart = take((size_t)g.B * L.kblocks * ED * f);
+  L.Kbar = take((size_t)g.B * ED * f);
+  L.attend = off;
+  off += align_up(attend_simt_workspace_bytes(g));
+  L.total = off;
+  return L;
+}
+
+static int check_weights(const DaglCEWeights* w) {
+  if (!w || !w->g_w || !w->g_b || !w->theta_w || !w->theta_b || !w->fc1_w || !w->fc1_b || !w->fc2_w ||
+      !w->fc2_b || !w->thr_w || !w->thr_b || !w->bias_w || !w->bias_b) {
+    call_state().err = "null weight pointer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  if (w->inter_channels != CI || w->ksize != KS || w->stride_q != SQ || w->stride_k != 1) {
+    call_state().err = "unsupported CE configuration: kernels are built for ksize=7, stride_1=4, stride_2=1, inter_channels=16";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  if (w->in_channels <= 0 || w->in_channels > 256 || (w->in_channels % 4) != 0) {
+    call_state().err = "unsupported in_channels (need a multiple of 4 in [4,256])";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+static int check_shape(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) {
+    call_state().err = "non-positive shape";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  if ((long long)H * W > (1 << 22) || (long long)B * H * W * CI > (1ll << 30)) {
+    call_state().err = "shape too large";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+static int run_attend(const Geom& g, const AttendArgs& a, int impl, cudaStream_t st) {
+  if (impl == DAGL_IMPL_TC) {
+    call_state().err = "tensor-core graph kernel not available in this build";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  call_state().impl = "simt";
+  return launch_attend_simt(g, a, st);
+}
+
+static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B, int H, int W, void* ws,
+                        size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz) {
+  call_state().launches = 0;
+  call_state().impl = "none";
+  int rc = check_weights(w);
+  if (rc) return rc;
+  rc = check_shape(B, H, W);
+  if (rc) return rc;
+  if (!b || !y || !ws) {
+    call_state().err = "null buffer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  const Geom g = make_geom(B, w->in_channels, H, W);
+  const WsLayout L = ws_layout(g);
+  if (ws_bytes < L.total) {
+    call_state().err = "workspace too small";
+    return DAGL_ERR_WORKSPACE;
+  }
+  char* base = static_cast<char*>(ws);
+  float* G = reinterpret_cast<float*>(base + L.G);
+  float* Th = reinterpret_cast<float*>(base + L.Th);
+  float* gamma = reinterpret_cast<float*>(base + L.gamma);
+  float* beta = reinterpret_cast<float*>(base + L.beta);
+  float* Q = reinterpret_cast<float*>(base + L.Q);
+  float* K = reinterpret_cast<float*>(base + L.K);
+  float* kpart = reinterpret_cast<float*>(base + L.kpart);
+  float* Kbar = reinterpret_cast<float*>(base + L.Kbar);
+
+  if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, st))) return rc;
+  if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
+  if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, st))) return rc;
+  if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, st))) return rc;
+  if ((rc = launch_kbar(g, kpart, L.kblocks, Kbar, st))) return rc;
+
+  AttendArgs a;
+  a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
+  a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
+  a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
+  return run_attend(g, a, impl, st);
+}
+}  // namespace dagl
+
+using namespace dagl;
+
+extern "C" {
+
+int32_t dagl_abi_version(void) { return DAGL_ABI_VERSION; }
+
+const char* dagl_last_error(void) { return call_state().err.c_str(); }
+const char* dagl_last_impl(void) { return call_state().impl; }
+int32_t dagl_last_launch_count(void) { return call_state().launches; }
+
+size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return ws_layout(make_geom(B, C, H, W)).total;
+}
+
+int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y, int32_t B, int32_t H, int32_t W,
+                            void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
+  return forward_impl(w, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int32_t dagl_ce_forward_debug_f32(const DaglCEWeights* w, const float* b, float* y, int32_t B, int32_t H, int32_t W,
+                                  void* workspace, size_t workspace_bytes, int32_t impl, void* stream,
+                                  uint32_t* mask_bits, int32_t* nnz) {
+  return forward_impl(w, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), mask_bits, nnz);
+}
+
+size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return align_up((size_t)B * C * H * W * sizeof(float)) + align_up((size_t)B * CI * H * W * sizeof(float));
+}
+
+int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, float* y_host, int32_t B, int32_t H,
+                                 int32_t W, void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
+  int rc = check_weights(w);
+  if (rc) return rc;
+  rc = check_shape(B, H, W);
+  if (rc) return rc;
+  if (!b_host || !y_host || !workspace) {
+    call_state().err = "null buffer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  const int C = w->in_channels;
+  const size_t need = dagl_ce_workspace_bytes(B, C, H, W);
+  const size_t stage = dagl_ce_host_staging_bytes(B, C, H, W);
+  if (workspace_bytes < need + stage) {
+    call_state().err = "workspace too small for host entry (need workspace_bytes + host_staging_bytes)";
+    return DAGL_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(workspace);
+  float* b_dev = reinterpret_cast<float*>(base + need);
+  const size_t b_bytes = (size_t)B * C * H * W * sizeof(float);
+  const size_t y_bytes = (size_t)B * CI * H * W * sizeof(float);
+  float* y_dev = reinterpret_cast<float*>(base + need + align_up(b_bytes));
+  DAGL_CUDA_OK(cudaMemcpyAsync(b_dev, b_host, b_bytes, cudaMemcpyHostToDevice, st));
+  rc = forward_impl(w, b_dev, y_dev, B, H, W, workspace, need, impl, st, nullptr, nullptr);
+  if (rc) return rc;
+  DAGL_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, y_bytes, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+size_t dagl_graph_attend_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return attend_simt_workspace_bytes(make_geom(B, 64, H, W));
+}
+
+int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar, const float* gamma,
+                              const float* beta, const float* theta, float* y, int32_t B, int32_t H, int32_t W,
+                              float softmax_scale, void* workspace, size_t workspace_bytes, int32_t impl,
+                              void* stream, uint32_t* mask_bits, int32_t* nnz) {
+  call_state().launches = 0;
+  call_state().impl = "none";
+  int rc = check_shape(B, H, W);
+  if (rc) return rc;
+  if (!Q || !K || !Kbar || !gamma || !beta || !theta || !y || !workspace) {
+    call_state().err = "null buffer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  const Geom g = make_geom(B, 64, H, W);
+  AttendArgs a;
+  a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = theta; a.y = y;
+  a.scale = softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
+  a.ws = workspace; a.ws_bytes = workspace_bytes;
+  return run_attend(g, a, impl, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dagl_profile_enable(int32_t on) {
+  CallState& s = call_state();
+  if (on && !s.prof_created) {
+    for (int i = 0; i < PROF_RING; ++i) {
+      DAGL_CUDA_OK(cudaEventCreate(&s.prof_start[i]));
+      DAGL_CUDA_OK(cudaEventCreate(&s.prof_stop[i]));
+    }
+    s.prof_created = true;
+  }
+  s.prof_on = on != 0;
+  s.prof_n = 0;
+  return 0;
+}
+
+int32_t dagl_profile_read(float* ms, int32_t max) {
+  CallState& s = call_state();
+  if (!ms || max < 0) { s.err = "bad profile buffer"; return DAGL_ERR_INVALID_ARG; }
+  int n = s.prof_n < max ? s.prof_n : max;
+  for (int i = 0; i < n; ++i) {
+    DAGL_CUDA_OK(cudaEventSynchronize(s.prof_stop[i]));
+    DAGL_CUDA_OK(cudaEventElapsedTime(&ms[i], s.prof_start[i], s.prof_stop[i]));
+  }
+  s.prof_n = 0;
+  return n;
+}
+
+const float* dagl_ce_workspace_view(void* workspace, int32_t which, int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (!workspace || B <= 0 || C <= 0 || H <= 0 || W <= 0) return nullptr;
+  const WsLayout L = ws_layout(make_geom(B, C, H, W));
+  const char* base = static_cast<const char*>(workspace);
+  switch (which) {
+    case 0: return reinterpret_cast<const float*>(base + L.G);
+    case 1: return reinterpret_cast<const float*>(base + L.Th);
+    case 2: return reinterpret_cast<const float*>(base + L.gamma);
+    case 3: return reinterpret_cast<const float*>(base + L.beta);
+    case 4: return reinterpret_cast<const float*>(base + L.Q);
+    case 5: return reinterpret_cast<const float*>(base + L.K);
+    case 6: return reinterpret_cast<const float*>(base + L.Kbar);
+    default: return nullptr;
+  }
+}
+
+}  // extern "C"

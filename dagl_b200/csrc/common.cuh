@@ -1,0 +1,100 @@
+// Shared definitions for the dagl_b200 CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace dagl {
+
+constexpr int KS = 7;            // patch size        (CE ksize,   dagl.py:175)
+constexpr int KK = KS * KS;      // 49 taps
+constexpr int CI = 16;           // inter_channels    (dagl.py:176)
+constexpr int ED = 196;          // embedding width   = KK*CI/4  (dagl.py:196-203)
+constexpr int VD = KK * CI;      // 784 value-patch width
+constexpr int SQ = 4;            // query stride      (stride_1)
+constexpr int PADK = 3;          // SAME pad of the stride-1 unfold, also the fold padding (dagl.py:243,267)
+
+struct Geom {
+  int B, C, H, W;
+  int nqy, nqx, Nq, Nk;
+  int qpad_top, qpad_left;       // SAME pad of the stride-4 unfold (dagl.py:126-136)
+};
+
+__host__ __device__ inline int same_pad_before(int n, int k, int s) {
+  int out = (n + s - 1) / s;
+  int total = (out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+inline Geom make_geom(int B, int C, int H, int W) {
+  Geom g;
+  g.B = B; g.C = C; g.H = H; g.W = W;
+  g.nqy = (H + SQ - 1) / SQ; g.nqx = (W + SQ - 1) / SQ;
+  g.Nq = g.nqy * g.nqx; g.Nk = H * W;
+  g.qpad_top = same_pad_before(H, KS, SQ);
+  g.qpad_left = same_pad_before(W, KS, SQ);
+  return g;
+}
+
+// thread-local call state (error text, launch counter, impl name)
+constexpr int PROF_RING = 256;
+struct CallState {
+  std::string err;
+  int launches = 0;
+  const char* impl = "none";
+  // optional event ring around the dominant kernel (dagl_profile_*)
+  bool prof_on = false;
+  int prof_n = 0;
+  cudaEvent_t prof_start[PROF_RING];
+  cudaEvent_t prof_stop[PROF_RING];
+  bool prof_created = false;
+};
+// record helpers: no-ops unless profiling is enabled on this thread
+int prof_begin(cudaStream_t st);
+int prof_end(cudaStream_t st);
+CallState& call_state();
+
+#define DAGL_CUDA_OK(expr)                                                           \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::dagl::call_state().err = std::string(#expr) + ": " + cudaGetErrorString(_e); \
+      return -4;                                                                     \
+    }                                                                                \
+  } while (0)
+
+#define DAGL_LAUNCH_CHECK()                   \
+  do {                                        \
+    ::dagl::call_state().launches++;          \
+    DAGL_CUDA_OK(cudaGetLastError());         \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- launchers implemented in the .cu files ------------------------------
+int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const float* g_b,
+                        const float* th_w, const float* th_b, float* G, float* Th, cudaStream_t st);
+int launch_gamma_beta(const Geom& g, const float* b, const float* thr_w, const float* thr_b,
+                      const float* bias_w, const float* bias_b, float* gamma, float* beta, cudaStream_t st);
+// positions = ny*nx outputs at stride s, window origin (oy*s - off_y, ox*s - off_x)
+int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* fc_b, float* out,
+                 int ny, int nx, int s, int off_y, int off_x,
+                 float* colsum_partial /*nullable [B][nblk][196]*/, cudaStream_t st);
+int embed_num_blocks(int npos);
+int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st);
+
+struct AttendArgs {
+  const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
+  const float* theta; float* y; float scale;
+  uint32_t* mask_bits; int32_t* nnz;
+  void* ws; size_t ws_bytes;
+};
+size_t attend_simt_workspace_bytes(const Geom& g);
+int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st);
+
+}  // namespace dagl

@@ -1,0 +1,139 @@
+/* dagl_b200 — C-ABI of the B200-native dynamic attentive graph block.
+ *
+ * The reference (jianzhangcs/DAGL) has no FFI: the hot path is the Python
+ * nn.Module `CE` (DN_Gray/model/dagl.py:174-277) called from `CES.forward`
+ * (dagl.py:112-119).  This header is the boundary a maintainer would bind
+ * instead of the body of `CE.forward` (dagl.py:207-275); each entry point
+ * names the reference lines it replaces.  Plain pointers and sizes only; no
+ * torch / C++ types; no exceptions cross it; nothing is allocated or kept by
+ * the library between calls (caller owns every buffer incl. the workspace).
+ *
+ * All device pointers are fp32, contiguous, on the current CUDA device.
+ * All calls are asynchronous on `stream` (a cudaStream_t passed as void*).
+ * Return value: 0 on success, <0 on error (message via dagl_last_error()).
+ */
+#ifndef DAGL_B200_H_
+#define DAGL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAGL_ABI_VERSION 1
+
+enum {
+  DAGL_OK = 0,
+  DAGL_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size */
+  DAGL_ERR_UNSUPPORTED = -2,   /* ksize/stride/channels the kernels are not built for */
+  DAGL_ERR_WORKSPACE = -3,     /* workspace too small */
+  DAGL_ERR_CUDA = -4           /* a CUDA runtime call failed; see dagl_last_error() */
+};
+
+/* Which fused graph kernel to run. */
+enum {
+  DAGL_IMPL_AUTO = 0,   /* best available for the shape */
+  DAGL_IMPL_SIMT = 1,   /* fp32 CUDA-core kernel (bit-faithful neighbour mask) */
+  DAGL_IMPL_TC = 2      /* tcgen05 tensor-core kernel (split-fp16 scores, fp16 P.V) */
+};
+
+/* Borrowed device pointers to one CE head's parameters, in the reference's
+ * state_dict layout (CE.__init__, dagl.py:175-205):
+ *   g      Conv2d(C,16,3,pad 1)   weight [16][C][3][3]   bias [16]
+ *   theta  Conv2d(C,16,1)         weight [16][C]         bias [16]
+ *   fc1    Linear(784,196)        weight [196][784]      bias [196]   (query embedding)
+ *   fc2    Linear(784,196)        weight [196][784]      bias [196]   (key embedding)
+ *   thr    Conv2d(C,1,7,stride 4) weight [C][7][7]       bias [1]
+ *   bias   Conv2d(C,1,7,stride 4) weight [C][7][7]       bias [1]
+ * `W` (dagl.py:193) is dead in forward and is not passed.                   */
+typedef struct DaglCEWeights {
+  const float* g_w;     const float* g_b;
+  const float* theta_w; const float* theta_b;
+  const float* fc1_w;   const float* fc1_b;
+  const float* fc2_w;   const float* fc2_b;
+  const float* thr_w;   const float* thr_b;
+  const float* bias_w;  const float* bias_b;
+  int32_t in_channels;      /* C; kernels are built for C % 4 == 0, C <= 256 */
+  int32_t inter_channels;   /* must be 16 */
+  int32_t ksize;            /* must be 7  */
+  int32_t stride_q;         /* must be 4  (stride_1)  */
+  int32_t stride_k;         /* must be 1  (stride_2)  */
+  float softmax_scale;      /* reference default 10   */
+} DaglCEWeights;
+
+int32_t dagl_abi_version(void);
+
+/* Thread-local description of the last error returned on this thread. */
+const char* dagl_last_error(void);
+
+/* Bytes of device workspace dagl_ce_forward_* needs for a [B,C,H,W] input. */
+size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+
+/* y[B,16,H,W] = CE.forward(b[B,C,H,W])          — replaces dagl.py:207-275. */
+int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y,
+                            int32_t B, int32_t H, int32_t W,
+                            void* workspace, size_t workspace_bytes,
+                            int32_t impl, void* stream);
+
+/* Same, and also reports the neighbour selection of dagl.py:256-257:
+ *   mask_bits [B][Nq][ceil(Nk/32)] : bit j of word w set <=> key 32w+j is a
+ *                                    neighbour of the query (mask_b != 0)
+ *   nnz       [B][Nq]              : neighbours per query
+ * either may be NULL.  Nq = ceil(H/4)*ceil(W/4), Nk = H*W (row-major).       */
+int32_t dagl_ce_forward_debug_f32(const DaglCEWeights* w, const float* b, float* y,
+                                  int32_t B, int32_t H, int32_t W,
+                                  void* workspace, size_t workspace_bytes,
+                                  int32_t impl, void* stream,
+                                  uint32_t* mask_bits, int32_t* nnz);
+
+/* Host-buffer entry: b_host / y_host are HOST pointers (pinned for async
+ * copies); the H2D copy of b, the forward and the D2H copy of y are all
+ * enqueued on `stream`.  Needs dagl_ce_workspace_bytes() +
+ * dagl_ce_host_staging_bytes() of device workspace.                          */
+size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, float* y_host,
+                                 int32_t B, int32_t H, int32_t W,
+                                 void* workspace, size_t workspace_bytes,
+                                 int32_t impl, void* stream);
+
+/* Split entry for the fused graph stage alone (dagl.py:250-272), taking the
+ * embeddings as inputs:
+ *   Q [B][Nq][196], K [B][Nk][196] (post-ReLU), Kbar [B][196] = mean_k K,
+ *   gamma, beta [B][Nq], theta [B][16][H][W]  ->  y [B][16][H][W].           */
+size_t dagl_graph_attend_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar,
+                              const float* gamma, const float* beta, const float* theta,
+                              float* y, int32_t B, int32_t H, int32_t W, float softmax_scale,
+                              void* workspace, size_t workspace_bytes,
+                              int32_t impl, void* stream,
+                              uint32_t* mask_bits, int32_t* nnz);
+
+/* Intermediate views inside the workspace after dagl_ce_forward_* (device
+ * pointers, valid until the workspace is reused): which = 0 G [B,16,H,W],
+ * 1 theta [B,16,H,W], 2 gamma [B,Nq], 3 beta [B,Nq], 4 Q [B,Nq,196],
+ * 5 K [B,Nk,196], 6 Kbar [B,196].  Used by the parity tests.                 */
+const float* dagl_ce_workspace_view(void* workspace, int32_t which,
+                                    int32_t B, int32_t C, int32_t H, int32_t W);
+
+/* Name of the kernel family actually used by the last forward on this thread
+ * ("simt" or "tc"); lets callers assert that no fallback happened.           */
+const char* dagl_last_impl(void);
+
+/* Number of kernel launches issued by the last forward on this thread.      */
+int32_t dagl_last_launch_count(void);
+
+/* Profiling aid for bench.py (not used on the product path).  When enabled on
+ * this thread the library brackets the dominant fused graph kernel of every
+ * forward with a pair of CUDA events recorded on the caller's stream (a ring
+ * of 256 pairs).  dagl_profile_read() synchronises on the recorded events and
+ * returns up to `max` kernel durations in milliseconds, oldest first, and
+ * resets the ring.  Returns the number written, <0 on error.                 */
+int32_t dagl_profile_enable(int32_t on);
+int32_t dagl_profile_read(float* ms, int32_t max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAGL_B200_H_ */

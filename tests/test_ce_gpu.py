@@ -1,0 +1,278 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (dagl_b200.CE ->
+dagl_ce_forward_f32), against the CPU oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): output within 1e-3 relative fp32 of the
+reference forward; neighbour mask identical — flips are tolerated only for
+entries whose margin |S - mu*gamma + beta| is within a few fp32 ulps of the
+operands (threshold ties under a different summation order).
+"""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import load_npz
+from oracle import ce_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3          # north_star: <= 1e-3 relative fp32
+IMPLS = ["simt"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def make_ce(params, dev, impl="simt"):
+    import dagl_b200
+    ce = dagl_b200.CE(in_channels=params["g.weight"].shape[1], impl=impl)
+    ce.load_state_dict(params, strict=True)
+    return ce.to(dev).eval()
+
+
+def rel_err(y, yref):
+    denom = yref.abs().max().item()
+    err = (y - yref).abs().max().item()
+    return err / denom if denom > 0 else err
+
+
+def assert_mask_parity(bits_gpu, aux, max_flips_frac=2e-6):
+    """Exact neighbour-mask parity up to threshold ties."""
+    Nk = aux["mask"].shape[-1]
+    m_gpu = O.unpack_mask_bits(bits_gpu.cpu(), Nk)
+    flips = m_gpu != aux["mask"]
+    nflip = int(flips.sum())
+    if nflip == 0:
+        return 0
+    S = aux["S"]
+    t = aux["mu"].unsqueeze(-1) * aux["gamma"].unsqueeze(-1)
+    beta = aux["beta"].unsqueeze(-1)
+    margin = ((S - t) + beta).abs()
+    scale = S.abs() + t.abs() + beta.abs()
+    ulp = torch.finfo(torch.float32).eps * scale
+    bad = flips & (margin > 16 * ulp)
+    assert int(bad.sum()) == 0, f"{int(bad.sum())} mask flips are not threshold ties (of {nflip} flips)"
+    assert nflip <= max(2, max_flips_frac * flips.numel()), f"too many tie flips: {nflip}"
+    return nflip
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_cfg1_golden(dev, rand_weights, impl):
+    """BASELINE config 1: 1x64x64x64, reference-made weights/input/output."""
+    g = load_npz("ce_cfg1_64x64.npz")
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(g["x"].to(dev))
+    assert ce.last_impl == impl and ce.last_launches >= 3
+    assert rel_err(y.cpu(), g["y"]) <= REL_TOL
+    _, aux = O.ce_forward(rand_weights, g["x"], return_aux=True)
+    nflip = assert_mask_parity(bits, aux)
+    if impl == "simt":
+        assert nflip == 0, "fp32 kernel must reproduce the 64x64 mask bit-exactly"
+        assert torch.equal(nnz.cpu(), g["nnz"])
+    with torch.no_grad():
+        y2 = ce(g["x"].to(dev))
+    assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_ragged_golden(dev, rand_weights, impl):
+    """H, W not multiples of 4, non-square, batch 2, tiny (7x9), chop-leaf 72x72."""
+    g = load_npz("ce_ragged.npz")
+    ce = make_ce(rand_weights, dev, impl)
+    for i in range(4):
+        x = g[f"x{i}"]
+        with torch.no_grad():
+            y, bits, nnz = ce.forward_debug(x.to(dev))
+        assert rel_err(y.cpu(), g[f"y{i}"]) <= REL_TOL, tuple(x.shape)
+        _, aux = O.ce_forward(rand_weights, x, return_aux=True)
+        nflip = assert_mask_parity(bits, aux)
+        assert (nnz.cpu() - g[f"nnz{i}"]).abs().sum().item() <= nflip
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_reference_smoke_shape(dev, rand_weights, impl):
+    g = load_npz("ce_demo_smoke.npz")      # the reference's own __main__ smoke (2,64,16,16)
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y = ce(g["x"].to(dev))
+    assert y.shape == (2, 16, 16, 16)
+    assert rel_err(y.cpu(), g["y"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("head", ["c1_2", "c2_1", "c3_1", "c3_3"])
+def test_trained_heads(dev, head, impl):
+    """Heads of the shipped DN_Gray checkpoint on their real inputs: dense, medium,
+    very sparse (10 neighbours/row) and fully masked."""
+    g = load_npz(f"ce_trained_{head}.npz")
+    p = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    ce = make_ce(p, dev, impl)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(g["x"].to(dev))
+    _, aux = O.ce_forward(p, g["x"], return_aux=True)
+    nflip = assert_mask_parity(bits, aux)
+    if head == "c3_3":
+        assert int(nnz.sum()) == 0 and float(y.abs().max()) == 0.0
+    else:
+        # one flipped neighbour in a sparse row moves it by ~1/nnz; only assert the
+        # tolerance on rows without flips
+        if nflip == 0:
+            assert rel_err(y.cpu(), g["y"]) <= REL_TOL
+        else:
+            assert rel_err(y.cpu(), g["y"]) <= 2e-2
+
+
+def test_prologue_intermediates(dev, rand_weights):
+    g = load_npz("ce_ragged.npz")
+    x = g["x0"]                                  # (2,64,30,41)
+    ce = make_ce(rand_weights, dev)
+    with torch.no_grad():
+        ce(x.to(dev))
+    torch.cuda.synchronize()
+    inter = {k: v.cpu() for k, v in ce.intermediates(tuple(x.shape)).items()}
+    _, aux = O.ce_forward(rand_weights, x, return_aux=True)
+    for name, ref in [("G", aux["G"]), ("theta", aux["theta"]), ("gamma", aux["gamma"]),
+                      ("beta", aux["beta"]), ("Q", aux["Q"]), ("K", aux["K"])]:
+        assert rel_err(inter[name], ref) <= 2e-5, name
+    assert rel_err(inter["Kbar"], aux["K"].mean(dim=1)) <= 2e-5
+    assert (inter["Q"] >= 0).all() and (inter["K"] >= 0).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_batch_independence_and_determinism(dev, rand_weights, impl):
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 64, 24, 20, generator=gen).to(dev)
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y = ce(x)
+        y_again = ce(x)
+        ys = torch.cat([ce(x[i:i + 1]) for i in range(3)], dim=0)
+    assert torch.equal(y, y_again)
+    assert rel_err(ys, y) <= 1e-6
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_all_masked_gives_exact_zero(dev, rand_weights, impl):
+    """Rows with no neighbour output exactly 0 (softmax uniform, times mask_b)."""
+    p = {k: v.clone() for k, v in rand_weights.items()}
+    p["bias_conv.weight"].zero_(); p["bias_conv.bias"].fill_(-1e6)
+    ce = make_ce(p, dev, impl)
+    gen = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(torch.randn(1, 64, 20, 28, generator=gen).to(dev))
+    assert int(nnz.sum()) == 0 and int((bits != 0).sum()) == 0
+    assert float(y.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_all_selected_is_plain_softmax_attention(dev, rand_weights, impl):
+    """gamma = 0, beta = +1 selects every key with mask = S + 1: checks the unmasked limit
+    against the oracle and that nnz == Nk for every query."""
+    p = {k: v.clone() for k, v in rand_weights.items()}
+    p["thr_conv.weight"].zero_(); p["thr_conv.bias"].zero_()
+    p["bias_conv.weight"].zero_(); p["bias_conv.bias"].fill_(1.0)
+    ce = make_ce(p, dev, impl)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 64, 21, 19, generator=gen)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(x.to(dev))
+    assert int((nnz != 21 * 19).sum()) == 0
+    assert rel_err(y.cpu(), O.ce_forward(p, x)) <= REL_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_linearity_in_values(dev, rand_weights, impl):
+    """y is linear in the value map theta(b): scaling theta's weights by 2 doubles y."""
+    gen = torch.Generator().manual_seed(10)
+    x = torch.randn(1, 64, 32, 36, generator=gen).to(dev)
+    ce = make_ce(rand_weights, dev, impl)
+    p2 = {k: v.clone() for k, v in rand_weights.items()}
+    p2["theta.weight"] *= 2.0; p2["theta.bias"] *= 2.0
+    ce2 = make_ce(p2, dev, impl)
+    with torch.no_grad():
+        y1, y2 = ce(x), ce2(x)
+    assert rel_err(y2, 2.0 * y1) <= 1e-5
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_host_entry_matches_device_entry(dev, rand_weights, impl):
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 64, 28, 24, generator=gen).pin_memory()
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y_host = ce.forward_host(x)
+        y_dev = ce(x.to(dev))
+    assert not y_host.is_cuda and y_host.shape == (2, 16, 28, 24)
+    assert torch.equal(y_host, y_dev.cpu())
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_256(dev, rand_weights, impl):
+    """The north-star shape (64ch 256x256, Nq=4096, Nk=65536) against the query-chunked oracle."""
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(1, 64, 256, 256, generator=gen)
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(x.to(dev))
+    yref, nnz_ref = O.ce_forward_chunked(rand_weights, x, chunk=256, return_nnz=True)
+    assert rel_err(y.cpu(), yref) <= REL_TOL
+    # 268M pairs: allow a handful of threshold ties (O(1) per 1e7 pairs)
+    assert (nnz.cpu().long() - nnz_ref).abs().sum().item() <= 64
+    # popcount of the packed mask equals nnz
+    pc = torch.zeros_like(nnz, dtype=torch.int64)
+    b64 = bits.long() & 0xFFFFFFFF
+    for s in range(32):
+        pc += ((b64 >> s) & 1).sum(dim=-1)
+    assert torch.equal(pc, nnz.long())
+
+
+def test_split_entry_graph_attend(dev, rand_weights):
+    """dagl_graph_attend_f32 on oracle-made embeddings isolates the fused graph stage."""
+    from dagl_b200 import _lib
+    L = _lib.lib()
+    gen = torch.Generator().manual_seed(14)
+    x = torch.randn(1, 64, 26, 30, generator=gen)
+    yref, aux = O.ce_forward(rand_weights, x, return_aux=True)
+    B, H, W = 1, 26, 30
+    t = lambda a: a.contiguous().to(dev)
+    Q, K, gamma, beta, theta = t(aux["Q"]), t(aux["K"]), t(aux["gamma"]), t(aux["beta"]), t(aux["theta"])
+    Kbar = t(aux["K"].double().mean(dim=1).float())
+    y = torch.empty(B, 16, H, W, device=dev)
+    ws = torch.empty(L.dagl_graph_attend_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+    rc = L.dagl_graph_attend_f32(Q.data_ptr(), K.data_ptr(), Kbar.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                 theta.data_ptr(), y.data_ptr(), B, H, W, ctypes.c_float(10.0), ws.data_ptr(),
+                                 ws.numel(), _lib.IMPL_SIMT, torch.cuda.current_stream().cuda_stream, None, None)
+    _lib.check(rc, "dagl_graph_attend_f32")
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), yref) <= 1e-4
+
+
+def test_ces_caller_row(dev):
+    """CES (3 stages x 4 heads + ResBlocks) against the oracle's CES on the same state_dict."""
+    import dagl_b200
+    torch.manual_seed(21)
+    ces = dagl_b200.CES(in_channels=64, impl="simt").eval()
+    state = {k: v.detach().clone() for k, v in ces.state_dict().items()}
+    x = torch.randn(1, 64, 20, 24)
+    yref = O.ces_forward(state, x)
+    ces = ces.to(dev)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y = ces(x.to(dev))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert rel_err(y.cpu(), yref) <= REL_TOL
+
+
+def test_unsupported_configuration_raises(dev):
+    import dagl_b200
+    ce = dagl_b200.CE(ksize=5, in_channels=64).to(dev)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="unsupported"):
+        ce(torch.zeros(1, 64, 16, 16, device=dev))

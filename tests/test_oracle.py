@@ -1,0 +1,158 @@
+"""CPU tests: pin the oracle (oracle/ce_oracle.py) to the golden fixtures that
+oracle/make_golden.py produced by running the UNMODIFIED reference, and — when
+the reference is mounted (build container only) — to the live reference."""
+import pytest
+import torch
+
+from conftest import have_reference, import_reference, load_npz
+from oracle import ce_oracle as O
+
+
+def test_same_pad_rule():
+    # dagl.py:126-136; SURVEY §8 a1 table
+    assert O.same_pad_amounts(64, 7, 4) == (1, 2)      # n % 4 == 0
+    assert O.same_pad_amounts(65, 7, 4) == (3, 3)      # n % 4 == 1
+    assert O.same_pad_amounts(66, 7, 4) == (2, 3)      # n % 4 == 2
+    assert O.same_pad_amounts(67, 7, 4) == (2, 2)      # n % 4 == 3
+    for n in (1, 7, 30, 41, 256):
+        assert O.same_pad_amounts(n, 7, 1) == (3, 3)
+    assert O.num_queries(256, 256) == (64, 64)
+    assert O.num_queries(30, 41) == (8, 11)
+
+
+def test_cfg1_bit_exact(rand_weights):
+    g = load_npz("ce_cfg1_64x64.npz")
+    y, aux = O.ce_forward(rand_weights, g["x"], return_aux=True)
+    assert torch.equal(y, g["y"])
+    assert torch.equal(O.pack_mask_bits(aux["mask"]), g["mask_bits"])
+    assert torch.equal(aux["mask"].sum(-1).to(torch.int32), g["nnz"])
+    assert torch.equal(aux["gamma"], g["gamma"]) and torch.equal(aux["beta"], g["beta"])
+    assert torch.equal(aux["mu"], g["mu"])
+    assert torch.equal(aux["Q"][0, :8], g["Q_head"]) and torch.equal(aux["K"][0, :8], g["K_head"])
+    assert torch.equal(aux["S"][0, :8, :64], g["S_head"])
+
+
+def test_ragged_shapes(rand_weights):
+    g = load_npz("ce_ragged.npz")
+    for i in range(4):
+        x, yref = g[f"x{i}"], g[f"y{i}"]
+        y, aux = O.ce_forward(rand_weights, x, return_aux=True)
+        assert torch.equal(y, yref), f"shape {tuple(x.shape)}"
+        assert torch.equal(aux["mask"].sum(-1).to(torch.int32), g[f"nnz{i}"])
+        if f"mask_bits{i}" in g:
+            assert torch.equal(O.pack_mask_bits(aux["mask"]), g[f"mask_bits{i}"])
+
+
+def test_reference_smoke_shape(rand_weights):
+    g = load_npz("ce_demo_smoke.npz")                    # Demosaic/model/dagl.py:280-284
+    y = O.ce_forward(rand_weights, g["x"])
+    assert y.shape == (2, 16, 16, 16)
+    assert torch.equal(y, g["y"])
+
+
+@pytest.mark.parametrize("head", ["c1_2", "c2_1", "c3_1", "c3_3"])
+def test_trained_heads(head):
+    g = load_npz(f"ce_trained_{head}.npz")
+    p = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
+    y, aux = O.ce_forward(p, g["x"], return_aux=True)
+    assert torch.equal(y, g["y"])
+    assert torch.equal(O.pack_mask_bits(aux["mask"]), g["mask_bits"])
+    if head == "c3_3":                                   # whole head masked out -> exactly zero
+        assert g["nnz"].sum() == 0 and y.abs().max() == 0
+
+
+def test_chunked_matches_reference_order(rand_weights):
+    g = load_npz("ce_cfg1_64x64.npz")
+    y, nnz = O.ce_forward_chunked(rand_weights, g["x"], chunk=37, return_nnz=True)
+    assert (y - g["y"]).abs().max() <= 2e-6 * g["y"].abs().max()
+    assert torch.equal(nnz.to(torch.int32), g["nnz"])
+
+
+def test_fp64_arbitration(rand_weights):
+    """fp64 evaluation of the same restatement: the fp32 reference sits within 1e-4 of it
+    and the neighbour masks agree (0 flips at 64^2)."""
+    g = load_npz("ce_cfg1_64x64.npz")
+    p64 = {k: v.double() for k, v in rand_weights.items()}
+    y64, aux64 = O.ce_forward(p64, g["x"].double(), return_aux=True)
+    assert (y64.float() - g["y"]).abs().max() <= 1e-4 * g["y"].abs().max()
+    flips = (O.pack_mask_bits(aux64["mask"]) != g["mask_bits"]).sum().item()
+    assert flips == 0
+
+
+def test_mask_bit_packing_roundtrip():
+    gen = torch.Generator().manual_seed(3)
+    m = torch.rand(2, 5, 77, generator=gen) > 0.5
+    w = O.pack_mask_bits(m)
+    assert w.shape == (2, 5, 3) and w.dtype == torch.int32
+    assert torch.equal(O.unpack_mask_bits(w, 77), m)
+
+
+def test_algorithmic_work_figures():
+    # SURVEY §8(d) / Appendix D
+    assert abs(O.algorithmic_flops(1, 256, 256) / 1e9 - 526.1) < 0.1
+    assert abs(O.algorithmic_bytes(1, 256, 256) / 1e6 - 63.0) < 0.1
+    assert abs(O.algorithmic_flops(1, 64, 64) / 1e9 - 2.055) < 0.001
+
+
+# ---------------------------------------------------------------------------
+# live reference (build container only; /root/reference is absent on the GPU box)
+# ---------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not have_reference(), reason="/root/reference not mounted")
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(1, 64, 20, 24), (2, 64, 17, 13), (1, 64, 9, 33)])
+def test_live_reference_ce(shape):
+    ref = import_reference()
+    torch.manual_seed(11)
+    ce = ref.CE(in_channels=64).eval()
+    x = torch.randn(*shape)
+    with torch.no_grad():
+        yref = ce(x)
+    y = O.ce_forward(dict(ce.state_dict()), x)
+    assert torch.equal(y, yref)
+
+
+@needs_ref
+def test_live_reference_ces():
+    ref = import_reference()
+    torch.manual_seed(5)
+    ces = ref.CES(in_channels=64).eval()
+    x = torch.randn(1, 64, 16, 20)
+    with torch.no_grad():
+        yref = ces(x)
+    y = O.ces_forward(dict(ces.state_dict()), x)
+    assert (y - yref).abs().max() <= 1e-5 * yref.abs().max()
+
+
+@needs_ref
+def test_state_dict_compat_with_reference():
+    """dagl_b200.CE / CES carry the reference's parameter names and shapes, so reference
+    checkpoints load unchanged (SURVEY §5 checkpoint row, §8b)."""
+    import dagl_b200
+    ref = import_reference()
+    rce, mce = ref.CE(in_channels=64), dagl_b200.CE(in_channels=64)
+    assert {k: tuple(v.shape) for k, v in rce.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in mce.state_dict().items()}
+    mce.load_state_dict(rce.state_dict(), strict=True)
+    rces, mces = ref.CES(in_channels=64), dagl_b200.CES(in_channels=64)
+    assert {k: tuple(v.shape) for k, v in rces.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in mces.state_dict().items()}
+    mces.load_state_dict(rces.state_dict(), strict=True)
+
+
+@needs_ref
+def test_patch_reference_swaps_all_heads_and_shares_parameters():
+    import types
+    import dagl_b200
+    ref = import_reference()
+    args = types.SimpleNamespace(n_resblocks=16, n_feats=64, n_colors=1, res_scale=1, rgb_range=1.0)
+    net = ref.RR(args)
+    before = dict(net.named_parameters())
+    keys_before = list(net.state_dict().keys())
+    n = dagl_b200.patch_reference(net)
+    assert n == 12
+    assert list(net.state_dict().keys()) == keys_before
+    after = dict(net.named_parameters())
+    assert all(after[k] is before[k] for k in before)
+    assert all(isinstance(getattr(net.body[8], f"c{s}_{h}"), dagl_b200.CE) for s in (1, 2, 3) for h in (1, 2, 3, 4))
