@@ -65,7 +65,7 @@ def workload_tensors(seed: int):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -79,12 +79,21 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts: str):
+        import datetime
+        try:
+            return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0: float = None, t1: float = None):
+        """Summarise the samples taken between wall-clock t0 and t1 (time.time())."""
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -97,6 +106,9 @@ class ClockSampler:
             for line in open(self.path):
                 f = [s.strip() for s in line.split(",")]
                 if len(f) < 9:
+                    continue
+                ts = self._epoch(f[0])
+                if t0 is not None and ts is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
                     continue
                 try:
                     sm.append(float(f[1])); mx.append(float(f[2]))
@@ -209,18 +221,19 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing (value) --------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(args.warmup):
             ce(x_dev)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         L.dagl_profile_enable(1)
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         launches = 0
         barrier()
+        t_epoch0 = time.time()
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()                              # L2 flush between timed iterations (untimed)
@@ -230,10 +243,11 @@ def main():
             launches += ce.last_launches
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        t_epoch1 = time.time()
         kbuf = (ctypes.c_float * 256)()
         nk = L.dagl_profile_read(kbuf, 256)
         L.dagl_profile_enable(0)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(t_epoch0, t_epoch1) if rank == 0 else None
         step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
         total_ms = sum(step_ms)
         impl_used = ce.last_impl
