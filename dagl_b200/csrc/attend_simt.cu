@@ -264,52 +264,6 @@ attend_simt_kernel(Geom g, const float* __restrict__ Q, const float* __restrict_
   }
 }
 
-// coef[s][q] = exp(m_s - M) / sum_s exp(m_s - M) l_s      (log-sum-exp merge of the key splits)
-__global__ void merge_coef_kernel(int B, int Nq, int nsplit, const float* __restrict__ mpart,
-                                  const float* __restrict__ lpart, float* __restrict__ coef) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * Nq) return;
-  const int img = i / Nq, q = i % Nq;
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mpart[((size_t)img * nsplit + s) * Nq + q]);
-  float L = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const size_t j = ((size_t)img * nsplit + s) * Nq + q;
-    L += expf(mpart[j] - M) * lpart[j];
-  }
-  const float inv = 1.f / L;
-  for (int s = 0; s < nsplit; ++s) {
-    const size_t j = ((size_t)img * nsplit + s) * Nq + q;
-    coef[j] = expf(mpart[j] - M) * inv;
-  }
-}
-
-// y[c][py][px] = (1/cnt) * sum over the <=2x2 queries whose folded 7x7 patch covers the pixel
-// (F.fold with kernel 7, padding 3, stride 4, then / coverage count: dagl.py:265-272).
-__global__ void fold_kernel(Geom g, int nsplit, const float* __restrict__ Opart,
-                            const float* __restrict__ coef, float* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = g.B * CI * g.Nk;
-  if (i >= total) return;
-  const int px = i % g.W, py = (i / g.W) % g.H, c = (i / g.Nk) % CI, img = i / (CI * g.Nk);
-  const int qy_lo = py >> 2, qy_hi = min(g.nqy - 1, (py + PADK) >> 2);
-  const int qx_lo = px >> 2, qx_hi = min(g.nqx - 1, (px + PADK) >> 2);
-  float sum = 0.f;
-  for (int qy = qy_lo; qy <= qy_hi; ++qy)
-    for (int qx = qx_lo; qx <= qx_hi; ++qx) {
-      const int q = qy * g.nqx + qx;
-      const int d = c * KK + (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
-      float v = 0.f;
-      for (int s = 0; s < nsplit; ++s) {
-        const size_t j = ((size_t)img * nsplit + s) * g.Nq + q;
-        v = fmaf(coef[j], Opart[j * VD + d], v);
-      }
-      sum += v;
-    }
-  const float cntf = (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
-  y[i] = sum / cntf;
-}
-
 // ---- host side ---------------------------------------------------------------
 static void simt_tiling(const Geom& g, int* nsplit, int* ntx, int* tw) {
   *ntx = (g.W + AT_BN - 1) / AT_BN;
@@ -363,13 +317,7 @@ int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st) {
                                                      ns, ntx, tw, Opart, mpart, lpart, a.mask_bits, a.nnz);
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
-  const int nq_total = g.B * g.Nq;
-  merge_coef_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, ns, mpart, lpart, coef);
-  DAGL_LAUNCH_CHECK();
-  const int total = g.B * CI * g.Nk;
-  fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, ns, Opart, coef, a.y);
-  DAGL_LAUNCH_CHECK();
-  return 0;
+  return launch_merge_fold(g, ns, Opart, mpart, lpart, coef, a.y, /*log2_units=*/0, /*shift_major=*/0, 1.f, st);
 }
 
 }  // namespace dagl

@@ -1,0 +1,599 @@
+// Fused graph stage on the Blackwell tensor cores (tcgen05 + TMEM + bulk-TMA), sm_100a.
+// Reference math: CE.forward, DN_Gray/model/dagl.py:250-272 (scores, adaptive neighbour mask,
+// un-renormalised masked softmax, weighted aggregation of 7x7x16 value patches, fold).
+//
+// Design (see DESIGN.md §4 for the derivation and the measured MMA cost model):
+//  * CTA = 128 queries x one half of the 784 value columns (TMEM holds 512 fp32 columns, so the
+//    128x784 accumulator is split over two CTAs) x one slice of the keys (split-K; partials are
+//    merged by merge_fold.cu).
+//  * Keys are enumerated over the zero-padded width Wp = W+6 ("padded-flat" order).  Then the value
+//    patch of key k' at shift (dy,dx) is theta_pad_flat[k' + dy*Wp + dx]: the whole N_k x 784 value
+//    operand is a Toeplitz view of the 16-channel theta map and is never materialised.  In smem a
+//    7-row halo of theta lies as [pixel][16 ch] (32 B per pixel, SWIZZLE_32B, MN-major); one
+//    tcgen05.mma with N = 16*G whose N-group stride is one pixel covers G dx-shifts x 16 channels.
+//  * Scores need fp32 accuracy: Q and K are split into fp16 hi + lo parts after a
+//    power-of-two rescale, S = Qh.Kh + Qh.Kl + Ql.Kh (three kind::f16 MMAs, fp32 accumulate).
+//  * P (fp16) is written back into the S columns of TMEM and used as the A operand of P.V.
+//  * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax/epilogue (one query row
+//    per thread, no cross-thread reductions), mbarrier pipelines between them; S is double buffered
+//    so the scores of tile j+1 are computed while tile j goes through the softmax.
+#include <cuda_fp16.h>
+#include <math.h>
+#include "common.cuh"
+#include "tc_utils.cuh"
+
+namespace dagl {
+using namespace tc;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 48;
+constexpr int TC_EP = 208;                        // 196 padded to 13 k-steps of 16
+constexpr int TC_KSTEPS = TC_EP / 16;
+constexpr int TC_ECH = TC_EP / 8;                 // 26 16-byte chunks per row
+constexpr int Q_HALF_BYTES = TC_BM * TC_EP * 2;   // 53248
+constexpr int Q_TILE_BYTES = 2 * Q_HALF_BYTES;    // hi | lo
+constexpr int K_HALF_BYTES = TC_BN * TC_EP * 2;   // 19968
+constexpr int K_TILE_BYTES = 2 * K_HALF_BYTES;    // 39936
+constexpr int TH_SEG_PIX = 64;
+constexpr int TH_SEG_BYTES = TH_SEG_PIX * 32;     // 2048
+constexpr int TH_SLOTS = 4;                       // dy rows per half
+constexpr int TH_STAGE_BYTES = TH_SLOTS * TH_SEG_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_S_COL0 = 400;                    // S/P buffers at columns 400 and 448
+constexpr float TC_RESCALE_LOG2 = 10.f;           // lazy rescale threshold of the softmax reference
+
+constexpr int SM_Q = 0;
+constexpr int SM_K = SM_Q + Q_TILE_BYTES;                 // 2 stages
+constexpr int SM_T = SM_K + 2 * K_TILE_BYTES;             // 2 stages
+constexpr int SM_BAR = SM_T + 2 * TH_STAGE_BYTES;
+constexpr int SM_TOTAL = SM_BAR + 256;
+static_assert(SM_K % 1024 == 0 && SM_T % 1024 == 0 && K_TILE_BYTES % 1024 == 0, "smem carve-up alignment");
+
+struct TcGeom {
+  int Wp;        // padded width W + 6
+  int NkP;       // number of padded-flat key slots = (H-1)*Wp + W
+  int NT;        // key tiles of 48
+  int NP;        // pixels in the packed theta array
+  int nqt;       // query tiles of 128
+};
+
+static TcGeom tc_geom(const Geom& g) {
+  TcGeom t;
+  t.Wp = g.W + 2 * PADK;
+  t.NkP = (g.H - 1) * t.Wp + g.W;
+  t.NT = (t.NkP + TC_BN - 1) / TC_BN;
+  int np = (g.H + 2 * PADK) * t.Wp;
+  int need = TC_BN * t.NT + 2 * PADK * t.Wp + TH_SEG_PIX + 8;
+  t.NP = ((np > need ? np : need) + 7) & ~7;
+  t.nqt = (g.Nq + TC_BM - 1) / TC_BM;
+  return t;
+}
+
+// power-of-two scale that brings absmax just below 2^target
+__device__ __forceinline__ float pow2_scale(unsigned absmax_bits, int target) {
+  const float a = __uint_as_float(absmax_bits);
+  if (!(a > 0.f) || !isfinite(a)) return 1.f;
+  int e;
+  frexpf(a, &e);                      // a = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, target - e);
+}
+
+// byte offset of the 16-byte chunk (row, chunk kc) inside a K-major no-swizzle tile half of `rows` rows
+__device__ __forceinline__ uint32_t tile_chunk_off(int row, int kc, int rows) {
+  return (uint32_t)(kc * (rows / 8) * 128 + (row / 8) * 128 + (row % 8) * 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// absmax reduction for the split entry (when the embeddings come from the caller)
+// ---------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n_per_img, unsigned* __restrict__ absmax, int slot) {
+  const int img = blockIdx.y;
+  const float* xi = x + (size_t)img * n_per_img;
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(xi[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(absmax + img * 3 + slot, __float_as_uint(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: fp32 rows [*,196] -> fp16 hi/lo UMMA tiles.  One CTA per tile; rows staged through smem so
+// both the global reads and the tile writes are coalesced.
+//   MODE 0: queries, ROWS=128, row r of tile t <- Q[t*128 + r]; also emits tA = mu*gamma, tB = beta
+//   MODE 1: keys, ROWS=48, padded-flat slot k' = t*48 + r <- K[y*W + x] if x < W (y = k'/Wp, x = k'%Wp)
+// ---------------------------------------------------------------------------------------------
+template <int ROWS, int MODE>
+__global__ void __launch_bounds__(256)
+pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsigned* __restrict__ absmax,
+                  uint8_t* __restrict__ tiles, unsigned long long* __restrict__ tilemask,
+                  const float* __restrict__ Kbar, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ thrA, float* __restrict__ thrB) {
+  extern __shared__ __align__(16) float rows_s[];            // [ROWS][196]
+  const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  const int nrows_src = MODE == 0 ? g.Nq : g.Nk;
+  const float* si = src + (size_t)img * nrows_src * ED;
+  const float scale = pow2_scale(absmax[img * 3 + MODE], 14);
+
+  for (int i = tid; i < ROWS * (ED / 4); i += 256) {
+    const int r = i / (ED / 4), e4 = i % (ED / 4);
+    int srow = -1;
+    if (MODE == 0) {
+      const int q = t * ROWS + r;
+      if (q < g.Nq) srow = q;
+    } else {
+      const int kp = t * ROWS + r;
+      const int y = kp / tg.Wp, x = kp % tg.Wp;
+      if (kp < tg.NkP && x < g.W) srow = y * g.W + x;
+    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (srow >= 0) v = __ldg(reinterpret_cast<const float4*>(si + (size_t)srow * ED) + e4);
+    reinterpret_cast<float4*>(rows_s)[i] = v;
+  }
+  __syncthreads();
+
+  uint8_t* tile = tiles + ((size_t)img * gridDim.x + t) * (size_t)(2 * ROWS * TC_EP * 2);
+  constexpr int HALF = ROWS * TC_EP * 2;
+  // one thread per 16-byte output chunk, in output order (coalesced stores)
+  for (int o = tid; o < HALF / 16; o += 256) {
+    const int kc = o / ROWS, r = o % ROWS;          // chunk order inside a half: [kc][row-group][row%8] == [kc][row]
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = 0.f, x1 = 0.f;
+      const int e = kc * 8 + 2 * j;
+      if (e < ED) { x0 = rows_s[r * ED + e] * scale; x1 = rows_s[r * ED + e + 1] * scale; }
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const uint32_t off = tile_chunk_off(r, kc, ROWS);   // == 16 * o
+    *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile + HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (MODE == 1) {
+    if (tid == 0) {                                  // validity bits of the 48 key slots of this tile
+      unsigned long long m = 0ull;
+      for (int r = 0; r < ROWS; ++r) {
+        const int kp = t * ROWS + r;
+        if (kp < tg.NkP && (kp % tg.Wp) < g.W) m |= 1ull << r;
+      }
+      tilemask[(size_t)img * gridDim.x + t] = m;
+    }
+  } else {
+    // per-query threshold terms: mu = Q[q,:] . Kbar (fp64 accumulate), tA = mu*gamma, tB = beta  (dagl.py:256)
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < ROWS; r += 8) {
+      const int q = t * ROWS + r;
+      double s = 0.0;
+      for (int e = lane; e < ED; e += 32) s += (double)rows_s[r * ED + e] * (double)__ldg(Kbar + (size_t)img * ED + e);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        const size_t idx = ((size_t)img * gridDim.x + t) * ROWS + r;
+        const float mu = (float)s;
+        thrA[idx] = (q < g.Nq) ? mu * __ldg(gamma + (size_t)img * g.Nq + q) : 0.f;
+        thrB[idx] = (q < g.Nq) ? __ldg(beta + (size_t)img * g.Nq + q) : -1.f;
+      }
+    }
+  }
+}
+
+// theta [16][H][W] fp32 -> zero-padded flat [NP pixels][16 ch] fp16 (scaled), SWIZZLE_32B pre-applied:
+// the two 16-byte halves of a pixel are swapped when (pixel & 4), which is address bit 7 once a
+// segment that starts at a multiple of 8 pixels lands on a 256-byte aligned smem address.
+__global__ void __launch_bounds__(256)
+pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsigned* __restrict__ absmax,
+                  uint8_t* __restrict__ thp) {
+  const int img = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= tg.NP) return;
+  const float scale = pow2_scale(absmax[img * 3 + 2], 12);
+  const int r = pix / tg.Wp, cc = pix % tg.Wp;
+  const int y = r - PADK, x = cc - PADK;
+  const bool inb = (y >= 0 && y < g.H && x >= 0 && x < g.W);
+  uint32_t w[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = 0.f, b = 0.f;
+    if (inb) {
+      a = __ldg(theta + (((size_t)img * CI + 2 * j) * g.H + y) * g.W + x) * scale;
+      b = __ldg(theta + (((size_t)img * CI + 2 * j + 1) * g.H + y) * g.W + x) * scale;
+    }
+    w[j] = pack_half2(a, b);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(thp + ((size_t)img * tg.NP + pix) * 32);
+  const int sw = (pix >> 2) & 1;
+  dst[sw] = make_uint4(w[0], w[1], w[2], w[3]);
+  dst[sw ^ 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------
+struct PvGroup { int dy, dx0, n, col0; };
+// half 0: dy 0,1,2 full (3 x 112 cols) + dy 3 dx 0..3 (64)      = 400 columns
+// half 1: dy 3 dx 4..6 (48) + dy 4,5,6 full (3 x 112)            = 384 columns
+__constant__ PvGroup c_groups[2][4] = {
+    {{0, 0, 112, 0}, {1, 0, 112, 112}, {2, 0, 112, 224}, {3, 0, 64, 336}},
+    {{3, 4, 48, 0}, {4, 0, 112, 48}, {5, 0, 112, 160}, {6, 0, 112, 272}}};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
+                 const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
+                 const float* __restrict__ thrA, const float* __restrict__ thrB,
+                 const unsigned* __restrict__ absmax, float sm_scale_log2, int nsplit,
+                 float* __restrict__ Opart, float* __restrict__ mpart, float* __restrict__ lpart,
+                 uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* t_full = bars + 5;    // [2]
+  uint64_t* t_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* pv_done = bars + 13;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int img = blockIdx.z, split = blockIdx.y;
+  const int qt = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int ntiles = t_end - t_begin;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
+      mbar_init(s_full + i, 1); mbar_init(p_full + i, 128);
+      mbar_init(pv_done + i, 1);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
+      mbar_arrive_expect_tx(q_full, Q_TILE_BYTES);
+      bulk_g2s(smem + SM_Q, qsrc, Q_HALF_BYTES, q_full);
+      bulk_g2s(smem + SM_Q + Q_HALF_BYTES, qsrc + Q_HALF_BYTES, Q_HALF_BYTES, q_full);
+      const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
+      for (int j = 0; j < ntiles; ++j) {
+        const int t = t_begin + j, s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(k_empty + s, ph ^ 1u);
+        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
+        bulk_g2s(smem + SM_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t) * K_TILE_BYTES, K_TILE_BYTES, k_full + s);
+        mbar_wait(t_empty + s, ph ^ 1u);
+        mbar_arrive_expect_tx(t_full + s, TH_STAGE_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < TH_SLOTS; ++sl) {
+          const int dy = c_groups[half][sl].dy;
+          const int first = (t * TC_BN + dy * tg.Wp) & ~7;
+          bulk_g2s(smem + SM_T + s * TH_STAGE_BYTES + sl * TH_SEG_BYTES, thp + (size_t)first * 32, TH_SEG_BYTES, t_full + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
+      const uint32_t q_hi = smem_u32(smem + SM_Q), q_lo = q_hi + Q_HALF_BYTES;
+      const uint64_t dq_hi = smem_desc(q_hi, (TC_BM / 8) * 128, 128);
+      const uint64_t dq_lo = smem_desc(q_lo, (TC_BM / 8) * 128, 128);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+
+      auto issue_S = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(k_full + s, (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(smem + SM_K + s * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
+        const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
+        const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
+        const uint32_t d = tbase + TC_S_COL0 + s * TC_BN;
+#pragma unroll
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);   // advance start address (16-byte units)
+          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+          mma_f16_ss(d, dq_hi + qo, dk_hi + ko, idS, ks > 0);
+          mma_f16_ss(d, dq_hi + qo, dk_lo + ko, idS, 1);
+          mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, 1);
+        }
+        mma_commit(s_full + s);
+        mma_commit(k_empty + s);
+      };
+
+      if (ntiles > 0) issue_S(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        if (j + 1 < ntiles) issue_S(j + 1);
+        mbar_wait(p_full + s, ph);
+        mbar_wait(t_full + s, ph);
+        tc_fence_after();
+        const int t = t_begin + j;
+        const uint32_t tstage = smem_u32(smem + SM_T + s * TH_STAGE_BYTES);
+        const uint32_t p_tmem = tbase + TC_S_COL0 + s * TC_BN;
+#pragma unroll
+        for (int ks = 0; ks < TC_BN / 16; ++ks) {
+#pragma unroll
+          for (int sl = 0; sl < TH_SLOTS; ++sl) {
+            const PvGroup gp = c_groups[half][sl];
+            const int off = ((t * TC_BN + gp.dy * tg.Wp) & 7) + gp.dx0 + ks * 16;
+            const uint32_t start = tstage + sl * TH_SEG_BYTES + off * 32;
+            // MN-major, SWIZZLE_32B: LBO = 32 B (next 16-channel N group = next pixel), SBO = 256 B (next 8 keys)
+            uint64_t bd = (uint64_t)((start >> 4) & 0x3FFF) | ((uint64_t)(32 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+                          ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+            const uint32_t idP = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
+            mma_f16_ts(tbase + gp.col0, p_tmem + ks * 8, bd, idP, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(t_empty + s);
+        mma_commit(pv_done + s);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps (one query row per thread) =====================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + (tid & 31);
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
+    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
+    const float inv_s = 1.f / (pow2_scale(absmax[img * 3 + 0], 14) * pow2_scale(absmax[img * 3 + 1], 14));
+    const int q = qt * TC_BM + row;
+    const bool qvalid = q < g.Nq;
+    float m_ref = -INFINITY, l_run = 0.f;
+    int cnt = 0;
+    const int nwords = (g.Nk + 31) / 32;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      const int t = t_begin + j;
+      const unsigned long long vm = __ldg(tilemask + (size_t)img * tg.NT + t);
+      mbar_wait(s_full + s, ph);
+      tc_fence_after();
+      float sv[TC_BN];
+      {
+        uint32_t r0[16], r1[16], r2[16];
+        const uint32_t a = trow + TC_S_COL0 + s * TC_BN;
+        tmem_ld16(a, r0); tmem_ld16(a + 16, r1); tmem_ld16(a + 32, r2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          sv[i] = __uint_as_float(r0[i]); sv[16 + i] = __uint_as_float(r1[i]); sv[32 + i] = __uint_as_float(r2[i]);
+        }
+      }
+      // neighbour mask + exponent (dagl.py:256-260), log2 domain
+      float tmax = -INFINITY;
+      unsigned long long mk = 0ull;
+#pragma unroll
+      for (int i = 0; i < TC_BN; ++i) {
+        const bool valid = (vm >> i) & 1ull;
+        const float sc = sv[i] * inv_s;                     // exact: inv_s is a power of two
+        const float rl = fmaxf((sc - tA) + tB, 0.f);
+        if (valid && rl != 0.f) mk |= 1ull << i;
+        const float e2 = (sc * rl) * sm_scale_log2;
+        sv[i] = valid ? e2 : -INFINITY;
+        tmax = fmaxf(tmax, sv[i]);
+      }
+      // lazy reference update
+      float factor = 1.f;
+      if (tmax > m_ref + TC_RESCALE_LOG2) {
+        factor = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - tmax);
+        m_ref = tmax;
+        l_run *= factor;
+      }
+      const bool need = (j > 0) && (factor != 1.f);
+      if (__any_sync(0xffffffffu, need)) {
+        // the accumulator must be idle: P.V of the previous tile has to be complete
+        mbar_wait(pv_done + ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+        tc_fence_after();
+        const int ncol = half == 0 ? 400 : 384;
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+          tmem_st16(trow + c0, v);
+        }
+        tmem_wait_st();
+      }
+      // probabilities: denominator over every valid key, numerator only neighbours
+      uint32_t pk[TC_BN / 2];
+      float psum = 0.f;
+      const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
+#pragma unroll
+      for (int i = 0; i < TC_BN; i += 2) {
+        const float p0 = exp2f(sv[i] - mr), p1 = exp2f(sv[i + 1] - mr);   // exp2(-inf) = 0 for dummy key slots
+        psum += p0 + p1;
+        pk[i / 2] = pack_half2(((mk >> i) & 1ull) ? p0 : 0.f, ((mk >> (i + 1)) & 1ull) ? p1 : 0.f);
+      }
+      l_run += psum;
+      cnt += __popcll(mk);
+      {
+        const uint32_t a = trow + TC_S_COL0 + s * TC_BN;
+        uint32_t v16[16], v8[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v16[i] = pk[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = pk[16 + i];
+        tmem_st16(a, v16);
+        tmem_st8(a + 16, v8);
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(p_full + s);
+
+      if (mask_bits != nullptr && qvalid && mk != 0ull) {      // debug path only
+        uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
+        unsigned long long rem = mk;
+        while (rem) {
+          const int i = __ffsll((long long)rem) - 1;
+          rem &= rem - 1;
+          const int kp = t * TC_BN + i;
+          const int kk = (kp / tg.Wp) * g.W + (kp % tg.Wp);
+          atomicOr(mrow + (kk >> 5), 1u << (kk & 31));
+        }
+      }
+    }
+
+    // ---- epilogue: partial accumulator -> global ----
+    if (ntiles > 0) {
+      mbar_wait(pv_done + ((ntiles - 1) & 1), (uint32_t)((ntiles - 1) >> 1) & 1u);
+      tc_fence_after();
+    }
+    const float inv_t = 1.f / pow2_scale(absmax[img * 3 + 2], 12);
+    const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
+    float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
+#pragma unroll 1
+    for (int sl = 0; sl < TH_SLOTS; ++sl) {
+      const PvGroup gp = c_groups[half][sl];
+      for (int gdx = 0; gdx < gp.n / 16; ++gdx) {
+        uint32_t v[16];
+        tmem_ld16(trow + gp.col0 + gdx * 16, v);
+        tmem_wait_ld();
+        if (qvalid) {
+          float4* dst = reinterpret_cast<float4*>(orow + (gp.dy * KS + gp.dx0 + gdx) * CI);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_float4(__uint_as_float(v[4 * i]) * inv_t, __uint_as_float(v[4 * i + 1]) * inv_t,
+                                 __uint_as_float(v[4 * i + 2]) * inv_t, __uint_as_float(v[4 * i + 3]) * inv_t);
+        }
+      }
+    }
+    if (qvalid && half == 0) {
+      mpart[prow + q] = m_ref;
+      lpart[prow + q] = l_run;
+      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, cnt);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int tc_splits(const Geom& g, const TcGeom& tg) {
+  const long long base = (long long)g.B * tg.nqt * 2;
+  const int smax = tg.NT < 32 ? tg.NT : 32;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= smax; ++s) {
+    const double waves = (double)((base * s + 147) / 148);
+    // time ~ waves * (tiles per CTA + fixed per-CTA overhead of ~6 tiles), plus partial traffic
+    const double cost = waves * ((double)tg.NT / s + 6.0) + 0.5 * s;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+struct TcWs {
+  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, total;
+  int nsplit;
+};
+
+static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
+  TcWs w;
+  w.nsplit = tc_splits(g, tg);
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
+  w.absmax = take((size_t)g.B * 3 * sizeof(unsigned));
+  w.Qp = take((size_t)g.B * tg.nqt * Q_TILE_BYTES);
+  w.Kp = take((size_t)g.B * tg.NT * K_TILE_BYTES);
+  w.Thp = take((size_t)g.B * tg.NP * 32);
+  w.tilemask = take((size_t)g.B * tg.NT * 8);
+  w.thrA = take((size_t)g.B * tg.nqt * TC_BM * 4);
+  w.thrB = take((size_t)g.B * tg.nqt * TC_BM * 4);
+  const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
+  w.Opart = take(rows * VD * 4);
+  w.mpart = take(rows * 4);
+  w.lpart = take(rows * 4);
+  w.coef = take(rows * 4);
+  w.total = off;
+  return w;
+}
+
+size_t attend_tc_workspace_bytes(const Geom& g) { return tc_ws(g, tc_geom(g)).total; }
+
+int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, cudaStream_t st) {
+  const TcGeom tg = tc_geom(g);
+  const TcWs w = tc_ws(g, tg);
+  if (a.ws_bytes < w.total) {
+    call_state().err = "attend (tc) workspace too small";
+    return -3;
+  }
+  char* base = static_cast<char*>(a.ws);
+  unsigned* absmax = reinterpret_cast<unsigned*>(base + w.absmax);
+  uint8_t* Qp = reinterpret_cast<uint8_t*>(base + w.Qp);
+  uint8_t* Kp = reinterpret_cast<uint8_t*>(base + w.Kp);
+  uint8_t* Thp = reinterpret_cast<uint8_t*>(base + w.Thp);
+  unsigned long long* tilemask = reinterpret_cast<unsigned long long*>(base + w.tilemask);
+  float* thrA = reinterpret_cast<float*>(base + w.thrA);
+  float* thrB = reinterpret_cast<float*>(base + w.thrB);
+  float* Opart = reinterpret_cast<float*>(base + w.Opart);
+  float* mpart = reinterpret_cast<float*>(base + w.mpart);
+  float* lpart = reinterpret_cast<float*>(base + w.lpart);
+  float* coef = reinterpret_cast<float*>(base + w.coef);
+
+  if (absmax_in != nullptr) {
+    absmax = const_cast<unsigned*>(absmax_in);      // filled by the prologue kernels of the same forward
+  } else {
+    DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * 3 * sizeof(unsigned), st));
+    absmax_kernel<<<dim3(64, g.B), 256, 0, st>>>(a.Q, (size_t)g.Nq * ED, absmax, 0);
+    DAGL_LAUNCH_CHECK();
+    absmax_kernel<<<dim3(256, g.B), 256, 0, st>>>(a.K, (size_t)g.Nk * ED, absmax, 1);
+    DAGL_LAUNCH_CHECK();
+    absmax_kernel<<<dim3(64, g.B), 256, 0, st>>>(a.theta, (size_t)CI * g.Nk, absmax, 2);
+    DAGL_LAUNCH_CHECK();
+  }
+  const int nwords = (g.Nk + 31) / 32;
+  if (a.mask_bits) DAGL_CUDA_OK(cudaMemsetAsync(a.mask_bits, 0, (size_t)g.B * g.Nq * nwords * sizeof(uint32_t), st));
+  if (a.nnz) DAGL_CUDA_OK(cudaMemsetAsync(a.nnz, 0, (size_t)g.B * g.Nq * sizeof(int32_t), st));
+
+  {
+    auto kq = pack_tiles_kernel<TC_BM, 0>;
+    const size_t smem = (size_t)TC_BM * ED * 4;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kq<<<dim3(tg.nqt, g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, a.Kbar, a.gamma, a.beta, thrA, thrB);
+    DAGL_LAUNCH_CHECK();
+    auto kk = pack_tiles_kernel<TC_BN, 1>;
+    const size_t smem_k = (size_t)TC_BN * ED * 4;
+    kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr);
+    DAGL_LAUNCH_CHECK();
+    pack_theta_kernel<<<dim3((tg.NP + 255) / 256, g.B), 256, 0, st>>>(g, tg, a.theta, absmax, Thp);
+    DAGL_LAUNCH_CHECK();
+  }
+
+  DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+  const float sm_scale_log2 = a.scale * 1.4426950408889634f;
+  dim3 grid(tg.nqt * 2, w.nsplit, g.B);
+  if (int rc = prof_begin(st)) return rc;
+  attend_tc_kernel<<<grid, TC_THREADS, SM_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, sm_scale_log2,
+                                                       w.nsplit, Opart, mpart, lpart, a.mask_bits, a.nnz);
+  DAGL_LAUNCH_CHECK();
+  if (int rc = prof_end(st)) return rc;
+  return launch_merge_fold(g, w.nsplit, Opart, mpart, lpart, coef, a.y, /*log2_units=*/1, /*shift_major=*/1, 1.f, st);
+}
+
+}  // namespace dagl

@@ -28,7 +28,7 @@ int prof_end(cudaStream_t st) {
 
 // Workspace carve-up shared by workspace_bytes / forward / workspace_view.
 struct WsLayout {
-  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, attend, total;
+  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, attend, total;
   int kblocks;
 };
 
@@ -46,8 +46,10 @@ static WsLayout ws_layout(const Geom& g) {
   L.K = take((size_t)g.B * g.Nk * ED * f);
   L.kpart = take((size_t)g.B * L.kblocks * ED * f);
   L.Kbar = take((size_t)g.B * ED * f);
+  L.absmax = take((size_t)g.B * 3 * sizeof(unsigned));
   L.attend = off;
-  off += align_up(attend_simt_workspace_bytes(g));
+  const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g);
+  off += align_up(a_simt > a_tc ? a_simt : a_tc);
   L.total = off;
   return L;
 }
@@ -81,10 +83,15 @@ static int check_shape(int B, int H, int W) {
   return 0;
 }
 
-static int run_attend(const Geom& g, const AttendArgs& a, int impl, cudaStream_t st) {
+static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsigned* absmax, cudaStream_t st) {
+  if (impl == DAGL_IMPL_AUTO) impl = DAGL_IMPL_TC;
   if (impl == DAGL_IMPL_TC) {
-    call_state().err = "tensor-core graph kernel not available in this build";
-    return DAGL_ERR_UNSUPPORTED;
+    call_state().impl = "tc";
+    return launch_attend_tc(g, a, absmax, st);
+  }
+  if (impl != DAGL_IMPL_SIMT) {
+    call_state().err = "unknown impl";
+    return DAGL_ERR_INVALID_ARG;
   }
   call_state().impl = "simt";
   return launch_attend_simt(g, a, st);
@@ -117,18 +124,20 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   float* K = reinterpret_cast<float*>(base + L.K);
   float* kpart = reinterpret_cast<float*>(base + L.kpart);
   float* Kbar = reinterpret_cast<float*>(base + L.Kbar);
+  unsigned* absmax = reinterpret_cast<unsigned*>(base + L.absmax);
 
-  if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, st))) return rc;
+  DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * 3 * sizeof(unsigned), st));
+  if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
   if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
-  if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, st))) return rc;
-  if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, st))) return rc;
+  if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax + 0, st))) return rc;
+  if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax + 1, st))) return rc;
   if ((rc = launch_kbar(g, kpart, L.kblocks, Kbar, st))) return rc;
 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
-  return run_attend(g, a, impl, st);
+  return run_attend(g, a, impl, absmax, st);
 }
 }  // namespace dagl
 
@@ -195,7 +204,9 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
 
 size_t dagl_graph_attend_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return attend_simt_workspace_bytes(make_geom(B, 64, H, W));
+  const Geom g = make_geom(B, 64, H, W);
+  const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g);
+  return a_simt > a_tc ? a_simt : a_tc;
 }
 
 int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar, const float* gamma,
@@ -215,7 +226,7 @@ int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar,
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = theta; a.y = y;
   a.scale = softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = workspace; a.ws_bytes = workspace_bytes;
-  return run_attend(g, a, impl, static_cast<cudaStream_t>(stream));
+  return run_attend(g, a, impl, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int32_t dagl_profile_enable(int32_t on) {

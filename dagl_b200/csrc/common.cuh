@@ -78,13 +78,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- launchers implemented in the .cu files ------------------------------
 int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const float* g_b,
-                        const float* th_w, const float* th_b, float* G, float* Th, cudaStream_t st);
+                        const float* th_w, const float* th_b, float* G, float* Th, unsigned* absmax, cudaStream_t st);
 int launch_gamma_beta(const Geom& g, const float* b, const float* thr_w, const float* thr_b,
                       const float* bias_w, const float* bias_b, float* gamma, float* beta, cudaStream_t st);
 // positions = ny*nx outputs at stride s, window origin (oy*s - off_y, ox*s - off_x)
 int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* fc_b, float* out,
                  int ny, int nx, int s, int off_y, int off_x,
-                 float* colsum_partial /*nullable [B][nblk][196]*/, cudaStream_t st);
+                 float* colsum_partial /*nullable [B][nblk][196]*/,
+                 unsigned* absmax /*nullable: slot of image 0 in a [B][3] array (0 Q, 1 K, 2 theta)*/, cudaStream_t st);
 int embed_num_blocks(int npos);
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st);
 
@@ -94,7 +95,14 @@ struct AttendArgs {
   uint32_t* mask_bits; int32_t* nnz;
   void* ws; size_t ws_bytes;
 };
+int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
+                      float* coef, float* y, int log2_units, int shift_major, float out_scale, cudaStream_t st);
 size_t attend_simt_workspace_bytes(const Geom& g);
 int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st);
+
+// tensor-core path (attend_tc.cu).  `absmax` [B][3] holds max Q, max K, max|theta| as float bits;
+// when null the launcher computes it with a reduction kernel (split entry).
+size_t attend_tc_workspace_bytes(const Geom& g);
+int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, cudaStream_t st);
 
 }  // namespace dagl

@@ -1,0 +1,71 @@
+// Merge of the key-split partial results and the fold epilogue, shared by the fp32 and the
+// tensor-core graph kernels (reference: dagl.py:265-272).
+#include <math.h>
+#include "common.cuh"
+
+namespace dagl {
+
+// coef[s][q] = w_s / sum_s w_s l_s with w_s = exp(m_s - max_s m_s): log-sum-exp merge of the key splits.
+// `log2_units`: the running maxima are in log2 units (tensor-core kernel) instead of natural log.
+__global__ void merge_coef_kernel(int B, int Nq, int nsplit, int log2_units, float out_scale,
+                                  const float* __restrict__ mpart, const float* __restrict__ lpart,
+                                  float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Nq) return;
+  const int img = i / Nq, q = i % Nq;
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, mpart[((size_t)img * nsplit + s) * Nq + q]);
+  float L = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const size_t j = ((size_t)img * nsplit + s) * Nq + q;
+    const float w = log2_units ? exp2f(mpart[j] - M) : expf(mpart[j] - M);
+    L += w * lpart[j];
+  }
+  const float inv = out_scale / L;
+  for (int s = 0; s < nsplit; ++s) {
+    const size_t j = ((size_t)img * nsplit + s) * Nq + q;
+    const float w = log2_units ? exp2f(mpart[j] - M) : expf(mpart[j] - M);
+    coef[j] = w * inv;
+  }
+}
+
+// y[c][py][px] = (1/cnt) * sum over the <=2x2 queries whose folded 7x7 patch covers the pixel
+// (F.fold with kernel 7, padding 3, stride 4, then / coverage count: dagl.py:265-272).
+// Partial layout per query row: shift_major=0 -> [c][dy][dx] (reference order), 1 -> [dy*7+dx][c].
+__global__ void fold_kernel(Geom g, int nsplit, int shift_major, const float* __restrict__ Opart,
+                            const float* __restrict__ coef, float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = g.B * CI * g.Nk;
+  if (i >= total) return;
+  const int px = i % g.W, py = (i / g.W) % g.H, c = (i / g.Nk) % CI, img = i / (CI * g.Nk);
+  const int qy_lo = py >> 2, qy_hi = min(g.nqy - 1, (py + PADK) >> 2);
+  const int qx_lo = px >> 2, qx_hi = min(g.nqx - 1, (px + PADK) >> 2);
+  float sum = 0.f;
+  for (int qy = qy_lo; qy <= qy_hi; ++qy)
+    for (int qx = qx_lo; qx <= qx_hi; ++qx) {
+      const int q = qy * g.nqx + qx;
+      const int sh = (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
+      const int d = shift_major ? sh * CI + c : c * KK + sh;
+      float v = 0.f;
+      for (int s = 0; s < nsplit; ++s) {
+        const size_t j = ((size_t)img * nsplit + s) * g.Nq + q;
+        v = fmaf(coef[j], Opart[j * VD + d], v);
+      }
+      sum += v;
+    }
+  const float cntf = (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
+  y[i] = sum / cntf;
+}
+
+int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
+                      float* coef, float* y, int log2_units, int shift_major, float out_scale, cudaStream_t st) {
+  const int nq_total = g.B * g.Nq;
+  merge_coef_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, nsplit, log2_units, out_scale, mpart, lpart, coef);
+  DAGL_LAUNCH_CHECK();
+  const int total = g.B * CI * g.Nk;
+  fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, nsplit, shift_major, Opart, coef, y);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dagl

@@ -18,7 +18,8 @@ constexpr int FM_THREADS = 128;
 __global__ void __launch_bounds__(FM_THREADS)
 feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict__ g_w,
                     const float* __restrict__ g_b, const float* __restrict__ th_w,
-                    const float* __restrict__ th_b, float* __restrict__ G, float* __restrict__ Th) {
+                    const float* __restrict__ th_b, float* __restrict__ G, float* __restrict__ Th,
+                    unsigned* __restrict__ absmax /*nullable: [B][3], slot 2 = max|theta|*/) {
   extern __shared__ float smem[];
   float* gw_s = smem;                       // [C][9][16]
   float* tw_s = smem + g.C * 9 * CI;        // [C][16]
@@ -35,7 +36,7 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
 
   const int img = blockIdx.y;
   const int p = blockIdx.x * FM_THREADS + threadIdx.x;
-  if (p >= g.Nk) return;
+  const bool live = p < g.Nk;
   const int y = p / g.W, x = p % g.W;
   const float* bi = b + (size_t)img * C * g.Nk;
 
@@ -43,7 +44,7 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
 #pragma unroll
   for (int c = 0; c < CI; ++c) { ag[c] = g_b[c]; at[c] = th_b[c]; }
 
-  for (int ci = 0; ci < C; ++ci) {
+  for (int ci = 0; live && ci < C; ++ci) {
     const float* bc = bi + (size_t)ci * g.Nk;
     float v[9];
 #pragma unroll
@@ -73,19 +74,31 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
       at[4 * j + 3] = fmaf(v[4], w.w, at[4 * j + 3]);
     }
   }
-  float* Go = G + (size_t)img * CI * g.Nk + p;
-  float* To = Th + (size_t)img * CI * g.Nk + p;
+  float tmax = 0.f;
+  if (live) {
+    float* Go = G + (size_t)img * CI * g.Nk + p;
+    float* To = Th + (size_t)img * CI * g.Nk + p;
 #pragma unroll
-  for (int c = 0; c < CI; ++c) { Go[(size_t)c * g.Nk] = ag[c]; To[(size_t)c * g.Nk] = at[c]; }
+    for (int c = 0; c < CI; ++c) {
+      Go[(size_t)c * g.Nk] = ag[c];
+      To[(size_t)c * g.Nk] = at[c];
+      tmax = fmaxf(tmax, fabsf(at[c]));
+    }
+  }
+  if (absmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(absmax + img * 3 + 2, __float_as_uint(tmax));
+  }
 }
 
 int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const float* g_b,
-                        const float* th_w, const float* th_b, float* G, float* Th, cudaStream_t st) {
+                        const float* th_w, const float* th_b, float* G, float* Th, unsigned* absmax, cudaStream_t st) {
   size_t smem = (size_t)(g.C * 9 * CI + g.C * CI) * sizeof(float);
   if (smem > 48 * 1024)
     DAGL_CUDA_OK(cudaFuncSetAttribute(feature_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.Nk + FM_THREADS - 1) / FM_THREADS, g.B);
-  feature_maps_kernel<<<grid, FM_THREADS, smem, st>>>(g, b, g_w, g_b, th_w, th_b, G, Th);
+  feature_maps_kernel<<<grid, FM_THREADS, smem, st>>>(g, b, g_w, g_b, th_w, th_b, G, Th, absmax);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
@@ -145,7 +158,8 @@ constexpr int EM_WS_FLOATS = (KK * EM_WS_STRIDE + 3) & ~3;   // keep As 16-byte 
 __global__ void __launch_bounds__(EM_THREADS, 2)
 embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w,
              const float* __restrict__ fc_b, float* __restrict__ out,
-             int ny, int nx, int s, int off_y, int off_x, float* __restrict__ colsum_partial) {
+             int ny, int nx, int s, int off_y, int off_x, float* __restrict__ colsum_partial,
+             unsigned* __restrict__ absmax /*nullable: this tensor's slot of image 0; stride 3 per image*/) {
   extern __shared__ float smem[];
   float* Ws = smem;                              // [49][225]
   float* As = smem + EM_WS_FLOATS;               // [49][64]
@@ -202,6 +216,7 @@ embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w
 
   // epilogue: bias + ReLU, store, optional column sums
   float csum[7];
+  float vmax = 0.f;
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     const int e = lane + 32 * i;
@@ -215,9 +230,15 @@ embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w
           float v = fmaxf(acc[j][i] + bias, 0.f);
           out[((size_t)img * npos + p) * ED + e] = v;
           csum[i] += v;
+          vmax = fmaxf(vmax, v);
         }
       }
     }
+  }
+  if (absmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) atomicMax(absmax + img * 3, __float_as_uint(vmax));   // values are >= 0: uint order == float order
   }
   if (colsum_partial != nullptr) {
     __syncthreads();
@@ -237,11 +258,12 @@ embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w
 int embed_num_blocks(int npos) { return (npos + EM_POS - 1) / EM_POS; }
 
 int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* fc_b, float* out,
-                 int ny, int nx, int s, int off_y, int off_x, float* colsum_partial, cudaStream_t st) {
+                 int ny, int nx, int s, int off_y, int off_x, float* colsum_partial, unsigned* absmax,
+                 cudaStream_t st) {
   size_t smem = (size_t)(EM_WS_FLOATS + KK * EM_POS) * sizeof(float);
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(embed_num_blocks(ny * nx), g.B);
-  embed_kernel<<<grid, EM_THREADS, smem, st>>>(g, G, fc_w, fc_b, out, ny, nx, s, off_y, off_x, colsum_partial);
+  embed_kernel<<<grid, EM_THREADS, smem, st>>>(g, G, fc_w, fc_b, out, ny, nx, s, off_y, off_x, colsum_partial, absmax);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
