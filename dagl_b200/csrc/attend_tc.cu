@@ -14,9 +14,10 @@
 //  * Scores need fp32 accuracy: Q and K are split into fp16 hi + lo parts after a
 //    power-of-two rescale, S = Qh.Kh + Qh.Kl + Ql.Kh (three kind::f16 MMAs, fp32 accumulate).
 //  * P (fp16) is written back into the S columns of TMEM and used as the A operand of P.V.
-//  * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax/epilogue (one query row
-//    per thread, no cross-thread reductions), mbarrier pipelines between them; S is double buffered
-//    so the scores of tile j+1 are computed while tile j goes through the softmax.
+//  * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-13 softmax/epilogue (a thread owns
+//    one query row x 16 key columns; three warps share a TMEM lane quadrant), mbarrier pipelines
+//    between them; S is double buffered so the scores of tile j+1 are computed while tile j goes
+//    through the softmax.
 #include <cuda_fp16.h>
 #include <math.h>
 #include "common.cuh"
@@ -38,7 +39,7 @@ constexpr int TH_SEG_PIX = 64;
 constexpr int TH_SEG_BYTES = TH_SEG_PIX * 32;     // 2048
 constexpr int TH_SLOTS = 4;                       // dy rows per half
 constexpr int TH_STAGE_BYTES = TH_SLOTS * TH_SEG_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 448;                 // 1 TMA + 1 MMA + 12 softmax warps
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_S_COL0 = 400;                    // S/P buffers at columns 400 and 448
 constexpr float TC_RESCALE_LOG2 = 10.f;           // lazy rescale threshold of the softmax reference
@@ -47,7 +48,8 @@ constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + Q_TILE_BYTES;                 // 2 stages
 constexpr int SM_T = SM_K + 2 * K_TILE_BYTES;             // 2 stages
 constexpr int SM_BAR = SM_T + 2 * TH_STAGE_BYTES;
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_XCH = SM_BAR + 256;                      // softmax exchange: [2][4][3][32] floats
+constexpr int SM_TOTAL = SM_XCH + 2 * 4 * 3 * 32 * 4;
 static_assert(SM_K % 1024 == 0 && SM_T % 1024 == 0 && K_TILE_BYTES % 1024 == 0, "smem carve-up alignment");
 
 struct TcGeom {
@@ -77,6 +79,12 @@ __device__ __forceinline__ float pow2_scale(unsigned absmax_bits, int target) {
   int e;
   frexpf(a, &e);                      // a = m * 2^e, m in [0.5, 1)
   return ldexpf(1.f, target - e);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // byte offset of the 16-byte chunk (row, chunk kc) inside a K-major no-swizzle tile half of `rows` rows
@@ -213,6 +221,17 @@ pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsi
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef DAGL_TC_TRACE
+// development aid (tools/tc_trace.py): per-CTA cycle counters of the pipeline roles
+__device__ long long g_tc_trace[1024][16];
+__device__ int g_tc_dbg_mode = 0;      // bit0: skip the S MMAs, bit1: skip the P.V MMAs (timing experiments only)
+#define TRACE_T0() long long _t0 = clock64()
+#define TRACE_ADD(var) (var) += clock64() - _t0
+#else
+#define TRACE_T0()
+#define TRACE_ADD(var)
+#endif
+
 struct PvGroup { int dy, dx0, n, col0; };
 // half 0: dy 0,1,2 full (3 x 112 cols) + dy 3 dx 0..3 (64)      = 400 columns
 // half 1: dy 3 dx 4..6 (48) + dy 4,5,6 full (3 x 112)            = 384 columns
@@ -246,13 +265,18 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int ntiles = t_end - t_begin;
+#ifdef DAGL_TC_TRACE
+  long long tr_a = 0, tr_b = 0, tr_c = 0;
+  const long long tr_start = clock64();
+  const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#endif
 
   if (tid == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
       mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
-      mbar_init(s_full + i, 1); mbar_init(p_full + i, 128);
+      mbar_init(s_full + i, 1); mbar_init(p_full + i, 384);
       mbar_init(pv_done + i, 1);
     }
     mbar_init_fence();
@@ -274,10 +298,10 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
       for (int j = 0; j < ntiles; ++j) {
         const int t = t_begin + j, s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(k_empty + s, ph ^ 1u);
+        { TRACE_T0(); mbar_wait(k_empty + s, ph ^ 1u); TRACE_ADD(tr_a); }
         mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
         bulk_g2s(smem + SM_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t) * K_TILE_BYTES, K_TILE_BYTES, k_full + s);
-        mbar_wait(t_empty + s, ph ^ 1u);
+        { TRACE_T0(); mbar_wait(t_empty + s, ph ^ 1u); TRACE_ADD(tr_b); }
         mbar_arrive_expect_tx(t_full + s, TH_STAGE_BYTES);
 #pragma unroll
         for (int sl = 0; sl < TH_SLOTS; ++sl) {
@@ -299,19 +323,22 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
 
       auto issue_S = [&](int j) {
         const int s = j & 1;
-        mbar_wait(k_full + s, (uint32_t)(j >> 1) & 1u);
+        { TRACE_T0(); mbar_wait(k_full + s, (uint32_t)(j >> 1) & 1u); TRACE_ADD(tr_a); }
         tc_fence_after();
         const uint32_t k_hi = smem_u32(smem + SM_K + s * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
         const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
         const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
         const uint32_t d = tbase + TC_S_COL0 + s * TC_BN;
+#ifdef DAGL_TC_TRACE
+        if (!(g_tc_dbg_mode & 1))
+#endif
 #pragma unroll
         for (int ks = 0; ks < TC_KSTEPS; ++ks) {
           const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);   // advance start address (16-byte units)
           const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-          mma_f16_ss(d, dq_hi + qo, dk_hi + ko, idS, ks > 0);
-          mma_f16_ss(d, dq_hi + qo, dk_lo + ko, idS, 1);
-          mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, 1);
+          mma_f16_ss_a_fill(d, dq_hi + qo, dk_hi + ko, idS, ks > 0);      // Qh.Kh, keep Qh in the A collector
+          mma_f16_ss_a_lastuse(d, dq_hi + qo, dk_lo + ko, idS, 1);       // Qh.Kl, A re-used (no smem read)
+          mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, 1);                 // Ql.Kh
         }
         mma_commit(s_full + s);
         mma_commit(k_empty + s);
@@ -322,12 +349,15 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
         const int s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         if (j + 1 < ntiles) issue_S(j + 1);
-        mbar_wait(p_full + s, ph);
-        mbar_wait(t_full + s, ph);
+        { TRACE_T0(); mbar_wait(p_full + s, ph); TRACE_ADD(tr_b); }
+        { TRACE_T0(); mbar_wait(t_full + s, ph); TRACE_ADD(tr_c); }
         tc_fence_after();
         const int t = t_begin + j;
         const uint32_t tstage = smem_u32(smem + SM_T + s * TH_STAGE_BYTES);
         const uint32_t p_tmem = tbase + TC_S_COL0 + s * TC_BN;
+#ifdef DAGL_TC_TRACE
+        if (!(g_tc_dbg_mode & 2))
+#endif
 #pragma unroll
         for (int ks = 0; ks < TC_BN / 16; ++ks) {
 #pragma unroll
@@ -347,10 +377,17 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
       }
     }
   } else {
-    // ===================== softmax / epilogue warps (one query row per thread) =====================
-    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + (tid & 31);
+    // ===================== softmax / epilogue warps =====================
+    // 12 warps: TMEM lane quadrant = warp % 4 (hardware rule), `sub` = which 16 of the 48 key columns.
+    // The three warps of a quadrant own the same 32 query rows; they exchange the per-row tile maximum
+    // through smem + a 96-thread named barrier, which also orders "everyone has read S" before anyone
+    // overwrites the S columns with P.
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int lane = tid & 31;
+    const int row = quad * 32 + lane;
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    float* xch = reinterpret_cast<float*>(smem + SM_XCH);       // [2 parity][4 quad][3 sub][32]
     const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
     const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
     const float inv_s = 1.f / (pow2_scale(absmax[img * 3 + 0], 14) * pow2_scale(absmax[img * 3 + 1], 14));
@@ -359,42 +396,55 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
     float m_ref = -INFINITY, l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
+    const int ncol = half == 0 ? 400 : 384;
 
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
       const int t = t_begin + j;
-      const unsigned long long vm = __ldg(tilemask + (size_t)img * tg.NT + t);
-      mbar_wait(s_full + s, ph);
+      const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
+      { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
       tc_fence_after();
-      float sv[TC_BN];
+      float sv[16];
       {
-        uint32_t r0[16], r1[16], r2[16];
-        const uint32_t a = trow + TC_S_COL0 + s * TC_BN;
-        tmem_ld16(a, r0); tmem_ld16(a + 16, r1); tmem_ld16(a + 32, r2);
+        uint32_t r0[16];
+        tmem_ld16(trow + TC_S_COL0 + s * TC_BN + 16 * sub, r0);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          sv[i] = __uint_as_float(r0[i]); sv[16 + i] = __uint_as_float(r1[i]); sv[32 + i] = __uint_as_float(r2[i]);
-        }
+        for (int i = 0; i < 16; ++i) sv[i] = __uint_as_float(r0[i]);
       }
       // neighbour mask + exponent (dagl.py:256-260), log2 domain
       float tmax = -INFINITY;
-      unsigned long long mk = 0ull;
+      unsigned mk = 0u;
+      if (vbits == 0xffffu) {
 #pragma unroll
-      for (int i = 0; i < TC_BN; ++i) {
-        const bool valid = (vm >> i) & 1ull;
-        const float sc = sv[i] * inv_s;                     // exact: inv_s is a power of two
-        const float rl = fmaxf((sc - tA) + tB, 0.f);
-        if (valid && rl != 0.f) mk |= 1ull << i;
-        const float e2 = (sc * rl) * sm_scale_log2;
-        sv[i] = valid ? e2 : -INFINITY;
-        tmax = fmaxf(tmax, sv[i]);
+        for (int i = 0; i < 16; ++i) {
+          const float sc = sv[i] * inv_s;                     // exact: inv_s is a power of two
+          const float rl = fmaxf((sc - tA) + tB, 0.f);
+          if (rl != 0.f) mk |= 1u << i;
+          sv[i] = (sc * rl) * sm_scale_log2;
+          tmax = fmaxf(tmax, sv[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool valid = (vbits >> i) & 1u;
+          const float sc = sv[i] * inv_s;
+          const float rl = fmaxf((sc - tA) + tB, 0.f);
+          if (valid && rl != 0.f) mk |= 1u << i;
+          sv[i] = valid ? (sc * rl) * sm_scale_log2 : -INFINITY;   // dummy key slots contribute nothing
+          tmax = fmaxf(tmax, sv[i]);
+        }
       }
-      // lazy reference update
+      // row maximum over the three column groups
+      float* xq = xch + ((s * 4 + quad) * 3) * 32;
+      xq[sub * 32 + lane] = tmax;
+      { TRACE_T0(); asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory"); TRACE_ADD(tr_b); }
+      tmax = fmaxf(fmaxf(xq[lane], xq[32 + lane]), xq[64 + lane]);
+      // lazy reference update (identical in the three warps: same inputs)
       float factor = 1.f;
       if (tmax > m_ref + TC_RESCALE_LOG2) {
-        factor = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - tmax);
+        factor = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - tmax);
         m_ref = tmax;
         l_run *= factor;
       }
@@ -403,8 +453,7 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
         // the accumulator must be idle: P.V of the previous tile has to be complete
         mbar_wait(pv_done + ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
         tc_fence_after();
-        const int ncol = half == 0 ? 400 : 384;
-        for (int c0 = 0; c0 < ncol; c0 += 16) {
+        for (int c0 = 16 * sub; c0 < ncol; c0 += 48) {
           uint32_t v[16];
           tmem_ld16(trow + c0, v);
           tmem_wait_ld();
@@ -415,38 +464,29 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
         tmem_wait_st();
       }
       // probabilities: denominator over every valid key, numerator only neighbours
-      uint32_t pk[TC_BN / 2];
+      uint32_t pk[8];
       float psum = 0.f;
       const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
 #pragma unroll
-      for (int i = 0; i < TC_BN; i += 2) {
-        const float p0 = exp2f(sv[i] - mr), p1 = exp2f(sv[i + 1] - mr);   // exp2(-inf) = 0 for dummy key slots
+      for (int i = 0; i < 16; i += 2) {
+        const float p0 = ex2_approx(sv[i] - mr), p1 = ex2_approx(sv[i + 1] - mr);   // ex2(-inf) = 0
         psum += p0 + p1;
-        pk[i / 2] = pack_half2(((mk >> i) & 1ull) ? p0 : 0.f, ((mk >> (i + 1)) & 1ull) ? p1 : 0.f);
+        pk[i / 2] = pack_half2(((mk >> i) & 1u) ? p0 : 0.f, ((mk >> (i + 1)) & 1u) ? p1 : 0.f);
       }
       l_run += psum;
-      cnt += __popcll(mk);
-      {
-        const uint32_t a = trow + TC_S_COL0 + s * TC_BN;
-        uint32_t v16[16], v8[8];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v16[i] = pk[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v8[i] = pk[16 + i];
-        tmem_st16(a, v16);
-        tmem_st8(a + 16, v8);
-        tmem_wait_st();
-      }
+      cnt += __popc(mk);
+      tmem_st8(trow + TC_S_COL0 + s * TC_BN + 8 * sub, pk);
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(p_full + s);
 
-      if (mask_bits != nullptr && qvalid && mk != 0ull) {      // debug path only
+      if (mask_bits != nullptr && qvalid && mk != 0u) {      // debug path only
         uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
-        unsigned long long rem = mk;
+        unsigned rem = mk;
         while (rem) {
-          const int i = __ffsll((long long)rem) - 1;
+          const int i = __ffs((int)rem) - 1;
           rem &= rem - 1;
-          const int kp = t * TC_BN + i;
+          const int kp = t * TC_BN + 16 * sub + i;
           const int kk = (kp / tg.Wp) * g.W + (kp % tg.Wp);
           atomicOr(mrow + (kk >> 5), 1u << (kk & 31));
         }
@@ -461,10 +501,12 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
     const float inv_t = 1.f / pow2_scale(absmax[img * 3 + 2], 12);
     const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
     float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
+    int chunk = 0;
 #pragma unroll 1
     for (int sl = 0; sl < TH_SLOTS; ++sl) {
       const PvGroup gp = c_groups[half][sl];
-      for (int gdx = 0; gdx < gp.n / 16; ++gdx) {
+      for (int gdx = 0; gdx < gp.n / 16; ++gdx, ++chunk) {
+        if (chunk % 3 != sub) continue;                      // warp-uniform: the three warps share the columns
         uint32_t v[16];
         tmem_ld16(trow + gp.col0 + gdx * 16, v);
         tmem_wait_ld();
@@ -477,13 +519,27 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
         }
       }
     }
-    if (qvalid && half == 0) {
+    // row sums / neighbour counts of the three column groups
+    float* xl = xch + (quad * 3) * 32;                         // parity-0 slots are free again
+    int* xc = reinterpret_cast<int*>(xch + (4 + quad) * 3 * 32);
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
+    xl[sub * 32 + lane] = l_run;
+    xc[sub * 32 + lane] = cnt;
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
+    if (sub == 0 && qvalid && half == 0) {
       mpart[prow + q] = m_ref;
-      lpart[prow + q] = l_run;
-      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, cnt);
+      lpart[prow + q] = (xl[lane] + xl[32 + lane]) + xl[64 + lane];
+      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
     }
   }
 
+#ifdef DAGL_TC_TRACE
+  if (tr_cta < 1024 && (tid & 31) == 0 && warp <= 2) {
+    long long* o = g_tc_trace[tr_cta] + warp * 4;        // warp 0 producer, 1 mma, 2 softmax
+    o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
+    if (warp == 0) { g_tc_trace[tr_cta][12] = ntiles; unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); g_tc_trace[tr_cta][13] = sm; g_tc_trace[tr_cta][14] = tr_start; }
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
@@ -597,3 +653,12 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
 }
 
 }  // namespace dagl
+
+#ifdef DAGL_TC_TRACE
+extern "C" int dagl_debug_set_tc_mode(int mode) {
+  return (int)cudaMemcpyToSymbol(dagl::g_tc_dbg_mode, &mode, sizeof(int));
+}
+extern "C" int dagl_debug_read_tc_trace(long long* host_out /*[1024][16]*/) {
+  return (int)cudaMemcpyFromSymbol(host_out, dagl::g_tc_trace, sizeof(long long) * 1024 * 16);
+}
+#endif

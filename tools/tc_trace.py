@@ -1,0 +1,44 @@
+"""Build a -DDAGL_TC_TRACE variant of the library and print per-role wait-cycle counters of the
+tensor-core graph kernel for the bench shape (development aid; not part of the product)."""
+import ctypes, os, subprocess, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dagl_b200 import build as B
+lib_trace = os.path.join(ROOT, "dagl_b200", "libdagl_b200_trace.so")
+if "--build" in sys.argv or not os.path.exists(lib_trace):
+    cmd = ["nvcc"] + B.NVCC_FLAGS + ["-DDAGL_TC_TRACE", "-o", lib_trace] + B.sources()
+    subprocess.check_call(cmd)
+    if "--build" in sys.argv:
+        sys.exit(0)
+from dagl_b200 import _lib
+_lib.LIB_PATH = lib_trace
+import dagl_b200
+from oracle import ce_oracle as O
+dev = torch.device("cuda:0")
+H = W = int(os.environ.get("HW", "256"))
+params = O.init_ce_params(1000)
+x = torch.randn(1, 64, H, W, generator=torch.Generator().manual_seed(2000)).to(dev)
+ce = dagl_b200.CE(in_channels=64, impl="tc"); ce.load_state_dict(params); ce = ce.to(dev).eval()
+L = _lib.lib()
+for mode in (0, 1, 2, 3):
+  L.dagl_debug_set_tc_mode(mode)
+  print(f"=== dbg mode {mode} (bit0: no S MMAs, bit1: no P.V MMAs) ===")
+  with torch.no_grad():
+    for _ in range(3): ce(x)
+  torch.cuda.synchronize()
+  buf = np.zeros((1024, 16), dtype=np.int64)
+  rc = L.dagl_debug_read_tc_trace(buf.ctypes.data_as(ctypes.c_void_p))
+  assert rc == 0
+  n = int((buf[:, 12] > 0).sum())
+  b = buf[:n]
+  nt = b[:, 12].astype(float)
+  print(f"{n} CTAs, tiles/CTA mean {nt.mean():.1f}")
+  def per_tile(col): return (b[:, col] / nt)
+  print("per tile (cycles), mean over CTAs:")
+  print(f"  producer : wait k_empty {per_tile(0).mean():8.0f}  wait t_empty {per_tile(1).mean():8.0f}  total {per_tile(3).mean():8.0f}")
+  print(f"  mma      : wait k_full  {per_tile(4).mean():8.0f}  wait p_full  {per_tile(5).mean():8.0f}  wait t_full {per_tile(6).mean():8.0f}  total {per_tile(7).mean():8.0f}")
+  print(f"  softmax  : wait s_full  {per_tile(8).mean():8.0f}  named bar    {per_tile(9).mean():8.0f}  total {per_tile(11).mean():8.0f}")
+  t0 = b[:, 14].min(); 
+  print("kernel span cycles:", (b[:, 14] + b[:, 3]).max() - t0, " CTA total mean", b[:, 3].mean())
