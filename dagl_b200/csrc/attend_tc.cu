@@ -103,7 +103,7 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n_per_img, uns
     m = fmaxf(m, fabsf(xi[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(absmax + img * 3 + slot, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) atomicMax(absmax + img * AMAX_STRIDE + slot, __float_as_uint(m));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,7 +122,7 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
   const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
   const int nrows_src = MODE == 0 ? g.Nq : g.Nk;
   const float* si = src + (size_t)img * nrows_src * ED;
-  const float scale = pow2_scale(absmax[img * 3 + MODE], 14);
+  const float scale = pow2_scale(absmax[img * AMAX_STRIDE + MODE], 14);
 
   for (int i = tid; i < ROWS * (ED / 4); i += 256) {
     const int r = i / (ED / 4), e4 = i % (ED / 4);
@@ -198,7 +198,7 @@ pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsi
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   if (pix >= tg.NP) return;
-  const float scale = pow2_scale(absmax[img * 3 + 2], 12);
+  const float scale = pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
   const int r = pix / tg.Wp, cc = pix % tg.Wp;
   const int y = r - PADK, x = cc - PADK;
   const bool inb = (y >= 0 && y < g.H && x >= 0 && x < g.W);
@@ -329,16 +329,26 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
         const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
         const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
         const uint32_t d = tbase + TC_S_COL0 + s * TC_BN;
+        // Tensor-core fp32 accumulation truncates; its error is relative to the running sum.  The two
+        // cross terms are ~2^-11 of the result, so the 13 Ql.Kh steps go first (while the
+        // accumulator is small); Qh.Kl is paired with Qh.Kh to share the A operand through the collector.
 #ifdef DAGL_TC_TRACE
         if (!(g_tc_dbg_mode & 1))
 #endif
+        {
 #pragma unroll
-        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);   // advance start address (16-byte units)
-          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-          mma_f16_ss_a_fill(d, dq_hi + qo, dk_hi + ko, idS, ks > 0);      // Qh.Kh, keep Qh in the A collector
-          mma_f16_ss_a_lastuse(d, dq_hi + qo, dk_lo + ko, idS, 1);       // Qh.Kl, A re-used (no smem read)
-          mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, 1);                 // Ql.Kh
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);   // advance start address (16-byte units)
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, ks > 0);             // Ql.Kh
+          }
+#pragma unroll
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ss_a_fill(d, dq_hi + qo, dk_lo + ko, idS, 1);           // Qh.Kl, keep Qh in the A collector
+            mma_f16_ss_a_lastuse(d, dq_hi + qo, dk_hi + ko, idS, 1);        // Qh.Kh, A re-used (no smem read)
+          }
         }
         mma_commit(s_full + s);
         mma_commit(k_empty + s);
@@ -390,7 +400,7 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
     float* xch = reinterpret_cast<float*>(smem + SM_XCH);       // [2 parity][4 quad][3 sub][32]
     const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
     const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
-    const float inv_s = 1.f / (pow2_scale(absmax[img * 3 + 0], 14) * pow2_scale(absmax[img * 3 + 1], 14));
+    const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
     const bool qvalid = q < g.Nq;
     float m_ref = -INFINITY, l_run = 0.f;
@@ -498,7 +508,7 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
       mbar_wait(pv_done + ((ntiles - 1) & 1), (uint32_t)((ntiles - 1) >> 1) & 1u);
       tc_fence_after();
     }
-    const float inv_t = 1.f / pow2_scale(absmax[img * 3 + 2], 12);
+    const float inv_t = 1.f / pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
     const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
     float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
     int chunk = 0;
@@ -574,7 +584,7 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   w.nsplit = tc_splits(g, tg);
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
-  w.absmax = take((size_t)g.B * 3 * sizeof(unsigned));
+  w.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
   w.Qp = take((size_t)g.B * tg.nqt * Q_TILE_BYTES);
   w.Kp = take((size_t)g.B * tg.NT * K_TILE_BYTES);
   w.Thp = take((size_t)g.B * tg.NP * 32);
@@ -615,7 +625,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   if (absmax_in != nullptr) {
     absmax = const_cast<unsigned*>(absmax_in);      // filled by the prologue kernels of the same forward
   } else {
-    DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * 3 * sizeof(unsigned), st));
+    DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
     absmax_kernel<<<dim3(64, g.B), 256, 0, st>>>(a.Q, (size_t)g.Nq * ED, absmax, 0);
     DAGL_LAUNCH_CHECK();
     absmax_kernel<<<dim3(256, g.B), 256, 0, st>>>(a.K, (size_t)g.Nk * ED, absmax, 1);

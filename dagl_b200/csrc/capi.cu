@@ -28,8 +28,8 @@ int prof_end(cudaStream_t st) {
 
 // Workspace carve-up shared by workspace_bytes / forward / workspace_view.
 struct WsLayout {
-  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, attend, total;
-  int kblocks;
+  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, embed, attend, total;
+  int kblocks_simt, kblocks_tc;
 };
 
 static WsLayout ws_layout(const Geom& g) {
@@ -37,16 +37,19 @@ static WsLayout ws_layout(const Geom& g) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const size_t f = sizeof(float);
-  L.kblocks = embed_num_blocks(g.Nk);
+  L.kblocks_simt = embed_num_blocks(g.Nk);
+  L.kblocks_tc = embed_tc_num_tiles(g);
+  const int kblocks = L.kblocks_simt > L.kblocks_tc ? L.kblocks_simt : L.kblocks_tc;
   L.G = take((size_t)g.B * CI * g.Nk * f);
   L.Th = take((size_t)g.B * CI * g.Nk * f);
   L.gamma = take((size_t)g.B * g.Nq * f);
   L.beta = take((size_t)g.B * g.Nq * f);
   L.Q = take((size_t)g.B * g.Nq * ED * f);
   L.K = take((size_t)g.B * g.Nk * ED * f);
-  L.kpart = take((size_t)g.B * L.kblocks * ED * f);
+  L.kpart = take((size_t)g.B * kblocks * ED * f);
   L.Kbar = take((size_t)g.B * ED * f);
-  L.absmax = take((size_t)g.B * 3 * sizeof(unsigned));
+  L.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
+  L.embed = take(embed_tc_workspace_bytes(g));
   L.attend = off;
   const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g);
   off += align_up(a_simt > a_tc ? a_simt : a_tc);
@@ -126,12 +129,18 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   float* Kbar = reinterpret_cast<float*>(base + L.Kbar);
   unsigned* absmax = reinterpret_cast<unsigned*>(base + L.absmax);
 
-  DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * 3 * sizeof(unsigned), st));
+  DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
   if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
   if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
-  if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax + 0, st))) return rc;
-  if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax + 1, st))) return rc;
-  if ((rc = launch_kbar(g, kpart, L.kblocks, Kbar, st))) return rc;
+  if (impl == DAGL_IMPL_SIMT) {
+    if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax, AMAX_Q, st))) return rc;
+    if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax, AMAX_K, st))) return rc;
+    if ((rc = launch_kbar(g, kpart, L.kblocks_simt, Kbar, st))) return rc;
+  } else {
+    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, K, kpart, absmax, base + L.embed,
+                              L.attend - L.embed, st))) return rc;
+    if ((rc = launch_kbar(g, kpart, L.kblocks_tc, Kbar, st))) return rc;
+  }
 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;

@@ -14,6 +14,10 @@ constexpr int VD = KK * CI;      // 784 value-patch width
 constexpr int SQ = 4;            // query stride      (stride_1)
 constexpr int PADK = 3;          // SAME pad of the stride-1 unfold, also the fold padding (dagl.py:243,267)
 
+// absmax[B][AMAX_STRIDE]: float bits of max Q, max K, max|Theta|, max|G| per image
+constexpr int AMAX_STRIDE = 4;
+enum { AMAX_Q = 0, AMAX_K = 1, AMAX_THETA = 2, AMAX_G = 3 };
+
 struct Geom {
   int B, C, H, W;
   int nqy, nqx, Nq, Nk;
@@ -85,9 +89,16 @@ int launch_gamma_beta(const Geom& g, const float* b, const float* thr_w, const f
 int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* fc_b, float* out,
                  int ny, int nx, int s, int off_y, int off_x,
                  float* colsum_partial /*nullable [B][nblk][196]*/,
-                 unsigned* absmax /*nullable: slot of image 0 in a [B][3] array (0 Q, 1 K, 2 theta)*/, cudaStream_t st);
+                 unsigned* absmax /*nullable: [B][AMAX_STRIDE]*/, int absmax_slot, cudaStream_t st);
 int embed_num_blocks(int npos);
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st);
+
+// tensor-core embeddings (embed_tc.cu): Q, K fp32 + K column-sum partials [B][embed_tc_num_tiles][196]
+size_t embed_tc_workspace_bytes(const Geom& g);
+int embed_tc_num_tiles(const Geom& g);
+int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+                    const float* fc2_b, float* Q, float* K, float* colsum_partial, unsigned* absmax, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
@@ -100,7 +111,7 @@ int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float
 size_t attend_simt_workspace_bytes(const Geom& g);
 int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st);
 
-// tensor-core path (attend_tc.cu).  `absmax` [B][3] holds max Q, max K, max|theta| as float bits;
+// tensor-core path (attend_tc.cu).  `absmax` [B][AMAX_STRIDE] holds max Q, max K, max|theta| as float bits;
 // when null the launcher computes it with a reduction kernel (split entry).
 size_t attend_tc_workspace_bytes(const Geom& g);
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, cudaStream_t st);

@@ -1,0 +1,340 @@
+// Patch embeddings on the tensor cores (tcgen05), sm_100a.
+// Reference: fc1 / fc2 applied to unfolded 7x7x16 patches + ReLU, DN_Gray/model/dagl.py:216-221,233-239,248-249.
+//
+// out[p][e] = relu(b[e] + sum_{ky,kx,c} W[e][c,ky,kx] * Gpad[c][y+ky][x+kx])      (p = pixel (y,x))
+// is an implicit GEMM with M = pixels, N = 196 (padded 208), K = 49 taps x 16 channels.  With G stored
+// channel-last over the zero-padded image and pixels enumerated in padded-flat order (p' = y*Wp + x),
+// the A operand of tap (ky,kx) for 128 consecutive pixels is the contiguous slab
+// GpadFlat[p0 + ky*Wp + kx + (0..127)][0..15] — a pixel-shifted view of a 7-row halo held in smem
+// (K-major, SWIZZLE_32B, one k-step of 16 channels per tap).  Nothing is unfolded (the reference
+// writes 205 MB of key patches to HBM per image at 256^2).
+//
+// The embeddings feed the score threshold, so they need fp32 accuracy: G and W are rescaled by powers
+// of two and split into fp16 hi + lo; acc = Gh.Wh + Gh.Wl + Gl.Wh (fp32 accumulate in TMEM).
+//
+// Queries (stride 4, TF-SAME padding) are the same computation with fc1 at the pixels
+// (4qy - top + 3, 4qx - left + 3): the kernel runs over the image rows that contain query centres and
+// stores only those pixels.
+#include <cuda_fp16.h>
+#include <math.h>
+#include "common.cuh"
+#include "tc_utils.cuh"
+
+namespace dagl {
+using namespace tc;
+
+constexpr int EB_M = 128;                          // pixels per CTA
+constexpr int EB_N = 208;                          // 196 padded to 13 * 16
+constexpr int EB_SEG_PIX = 144;                    // 128 + 6 (kx) + 7 (alignment) rounded up to 8
+constexpr int EB_SEG_BYTES = EB_SEG_PIX * 32;      // 4608
+constexpr int EB_G_BYTES = 2 * KS * EB_SEG_BYTES;  // hi | lo, 7 rows each: 64512
+constexpr int EB_WPART_BYTES = EB_N * 16 * 2;      // one tap, one part: 6656
+constexpr int EB_WTAP_BYTES = 2 * EB_WPART_BYTES;  // hi | lo: 13312
+constexpr int EB_WSTAGES = 3;
+constexpr int EB_SM_G = 0;
+constexpr int EB_SM_W = EB_G_BYTES;                                  // 64512 = 63 * 1024
+constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WTAP_BYTES;      // 104448
+constexpr int EB_SM_RED = EB_SM_BAR + 128;                           // [4 warps][208] floats
+constexpr int EB_SM_TOTAL = EB_SM_RED + 4 * EB_N * 4;
+constexpr int EB_THREADS = 192;
+constexpr int EB_TMEM_COLS = 512;                  // main (hi.hi) accumulator at column 0, cross-term accumulator at 256
+static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
+
+struct EmbGeom {
+  int Wp, NkP, ntile, NPG;
+};
+static EmbGeom emb_geom(const Geom& g) {
+  EmbGeom e;
+  e.Wp = g.W + 2 * PADK;
+  e.NkP = (g.H - 1) * e.Wp + g.W;
+  e.ntile = (e.NkP + EB_M - 1) / EB_M;
+  int np = (g.H + 2 * PADK) * e.Wp;
+  int need = EB_M * e.ntile + 2 * PADK * e.Wp + EB_SEG_PIX + 8;
+  e.NPG = ((np > need ? np : need) + 7) & ~7;
+  return e;
+}
+
+__device__ __forceinline__ float pow2_scale_e(unsigned absmax_bits, int target) {
+  const float a = __uint_as_float(absmax_bits);
+  if (!(a > 0.f) || !isfinite(a)) return 1.f;
+  int e;
+  frexpf(a, &e);
+  return ldexpf(1.f, target - e);
+}
+
+// max |x| over a tensor (weights) -> absmax[slot]
+__global__ void absmax_flat_kernel(const float* __restrict__ x, int n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// fc weight [196][784] (e, (c,ky,kx)) -> per tap: [hi|lo][2 chunks][26 row groups][8 rows (e)][8 c] fp16
+__global__ void __launch_bounds__(256)
+pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, uint8_t* __restrict__ out) {
+  const int tap = blockIdx.x;
+  const float scale = pow2_scale_e(*wmax, 14);
+  for (int o = threadIdx.x; o < EB_WPART_BYTES / 16; o += 256) {      // one 16-byte chunk = 8 channels of one e
+    const int kc = o / EB_N, e = o % EB_N;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = 0.f, x1 = 0.f;
+      if (e < ED) {
+        const int c = kc * 8 + 2 * j;
+        x0 = __ldg(w + (size_t)e * VD + c * KK + tap) * scale;
+        x1 = __ldg(w + (size_t)e * VD + (c + 1) * KK + tap) * scale;
+      }
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    uint8_t* base = out + (size_t)tap * EB_WTAP_BYTES + (size_t)o * 16;      // [kc][e] chunk order == K-major no-swizzle
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + EB_WPART_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// G [16][H][W] fp32 -> zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
+__global__ void __launch_bounds__(256)
+pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* __restrict__ absmax,
+              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo) {
+  const int img = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= eg.NPG) return;
+  const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
+  const int r = pix / eg.Wp, cc = pix % eg.Wp;
+  const int y = r - PADK, x = cc - PADK;
+  const bool inb = (y >= 0 && y < g.H && x >= 0 && x < g.W);
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = 0.f, b = 0.f;
+    if (inb) {
+      a = __ldg(G + (((size_t)img * CI + 2 * j) * g.H + y) * g.W + x) * scale;
+      b = __ldg(G + (((size_t)img * CI + 2 * j + 1) * g.H + y) * g.W + x) * scale;
+    }
+    const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
+    const __half l0 = __float2half_rn(a - __half2float(h0)), l1 = __float2half_rn(b - __half2float(h1));
+    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  const int sw = (pix >> 2) & 1;
+  uint4* dh = reinterpret_cast<uint4*>(ghi + ((size_t)img * eg.NPG + pix) * 32);
+  uint4* dl = reinterpret_cast<uint4*>(glo + ((size_t)img * eg.NPG + pix) * 32);
+  dh[sw] = make_uint4(h[0], h[1], h[2], h[3]);
+  dh[sw ^ 1] = make_uint4(h[4], h[5], h[6], h[7]);
+  dl[sw] = make_uint4(l[0], l[1], l[2], l[3]);
+  dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// mode 0: keys (every pixel) -> out[y*W+x][196], column sums for Kbar, absmax slot 1
+// mode 1: queries (pixels (4qy+oy, 4qx+ox)) -> out[qy*nqx+qx][196], absmax slot 0
+__global__ void __launch_bounds__(EB_THREADS, 1)
+embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __restrict__ ghi,
+                const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
+                const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
+                float* __restrict__ out, float* __restrict__ colsum_partial, unsigned* __restrict__ absmax_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
+  uint64_t* g_full = bars + 0;
+  uint64_t* w_full = bars + 1;                 // [3]
+  uint64_t* w_empty = bars + 4;                // [3]
+  uint64_t* d_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* red = reinterpret_cast<float*>(smem + EB_SM_RED);
+
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int p0 = tile * EB_M;
+
+  // query mode: skip tiles whose rows hold no query centre
+  if (mode == 1) {
+    const int y_first = p0 / eg.Wp, y_last = min((p0 + EB_M - 1) / eg.Wp, g.H - 1);
+    bool any = false;
+    for (int y = y_first; y <= y_last; ++y) any |= (y >= oy) && (((y - oy) & 3) == 0);
+    if (!any) return;
+  }
+
+  if (tid == 0) {
+    mbar_init(g_full, 1);
+    for (int i = 0; i < EB_WSTAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    mbar_init(d_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<EB_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(g_full, EB_G_BYTES);
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* src = (part ? glo : ghi) + (size_t)img * eg.NPG * 32;
+        for (int ky = 0; ky < KS; ++ky) {
+          const int first = (p0 + ky * eg.Wp) & ~7;
+          bulk_g2s(smem + EB_SM_G + (part * KS + ky) * EB_SEG_BYTES, src + (size_t)first * 32, EB_SEG_BYTES, g_full);
+        }
+      }
+      for (int t = 0; t < KK; ++t) {
+        const int s = t % EB_WSTAGES;
+        const uint32_t ph = (uint32_t)(t / EB_WSTAGES) & 1u;
+        mbar_wait(w_empty + s, ph ^ 1u);
+        mbar_arrive_expect_tx(w_full + s, EB_WTAP_BYTES);
+        bulk_g2s(smem + EB_SM_W + s * EB_WTAP_BYTES, wp + (size_t)t * EB_WTAP_BYTES, EB_WTAP_BYTES, w_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = instr_desc(EB_M, EB_N, FMT_F16, FMT_F16, 0, 0);
+      mbar_wait(g_full, 0);
+      tc_fence_after();
+      const uint32_t gbase = smem_u32(smem + EB_SM_G);
+      for (int t = 0; t < KK; ++t) {
+        const int s = t % EB_WSTAGES;
+        mbar_wait(w_full + s, (uint32_t)(t / EB_WSTAGES) & 1u);
+        tc_fence_after();
+        const int ky = t / KS, kx = t % KS;
+        const int off = ((p0 + ky * eg.Wp) & 7) + kx;
+        // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
+        const uint32_t a_hi = gbase + ky * EB_SEG_BYTES + off * 32;
+        const uint32_t a_lo = a_hi + KS * EB_SEG_BYTES;
+        const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                               ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+        const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                               ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WTAP_BYTES);
+        const uint64_t db_hi = smem_desc(w_hi, (EB_N / 8) * 128, 128);
+        const uint64_t db_lo = smem_desc(w_hi + EB_WPART_BYTES, (EB_N / 8) * 128, 128);
+        // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
+        // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
+        // the epilogue adds the two in round-to-nearest fp32.
+        mma_f16_ss_a_fill(tbase, da_hi, db_hi, idesc, t > 0);                // Gh.Wh
+        mma_f16_ss_a_lastuse(tbase + 256, da_hi, db_lo, idesc, t > 0);       // Gh.Wl
+        mma_f16_ss(tbase + 256, da_lo, db_hi, idesc, 1);                     // Gl.Wh
+        mma_commit(w_empty + s);
+      }
+      mma_commit(d_full);
+    }
+  } else {
+    // epilogue: thread = pixel row
+    const int quad = warp & 3, lane = tid & 31;
+    const int r = quad * 32 + lane;
+    const int p = p0 + r;
+    const int y = p / eg.Wp, x = p % eg.Wp;
+    bool valid = (p < eg.NkP) && (x < g.W);
+    size_t orow = 0;
+    if (mode == 0) {
+      orow = (size_t)img * g.Nk + (size_t)y * g.W + x;
+    } else {
+      valid = valid && (y >= oy) && (x >= ox) && (((y - oy) & 3) == 0) && (((x - ox) & 3) == 0);
+      const int qy = (y - oy) >> 2, qx = (x - ox) >> 2;
+      valid = valid && (qy < g.nqy) && (qx < g.nqx);
+      orow = (size_t)img * g.Nq + (size_t)qy * g.nqx + qx;
+    }
+    const float inv = 1.f / (pow2_scale_e(absmax_in[img * 4 + 3], 14) * pow2_scale_e(*wmax, 14));
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    float vmax = 0.f;
+    mbar_wait(d_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c16 = 0; c16 < EB_N / 16; ++c16) {
+      uint32_t v[16], vc[16];
+      tmem_ld16(trow + c16 * 16, v);
+      tmem_ld16(trow + 256 + c16 * 16, vc);
+      tmem_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int e = c16 * 16 + i;
+        const float b = (e < ED) ? __ldg(bias + e) : 0.f;
+        f[i] = valid ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
+        vmax = fmaxf(vmax, f[i]);
+      }
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(out + orow * ED + c16 * 16);
+        const int n4 = (c16 == EB_N / 16 - 1) ? 1 : 4;          // 196 = 12*16 + 4
+        for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+      }
+      if (colsum_partial != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float sum = f[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == i) red[quad * EB_N + c16 * 16 + i] = sum;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
+    if (colsum_partial != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int e = tid - 64; e < ED; e += 128)
+        colsum_partial[((size_t)img * gridDim.x + tile) * ED + e] =
+            (red[e] + red[EB_N + e]) + (red[2 * EB_N + e] + red[3 * EB_N + e]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<EB_TMEM_COLS>(tbase);
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static inline size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t embed_tc_workspace_bytes(const Geom& g) {
+  const EmbGeom eg = emb_geom(g);
+  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64);
+}
+int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
+
+// Computes Q [B][Nq][196], K [B][Nk][196] (fp32), K column-sum partials [B][ntile][196] and the maxima
+// of Q and K into absmax[B][4] (slots 0, 1); absmax slot 3 (max |G|) must already be filled.
+int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+                    const float* fc2_b, float* Q, float* K, float* colsum_partial, unsigned* absmax, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
+  const EmbGeom eg = emb_geom(g);
+  if (ws_bytes < embed_tc_workspace_bytes(g)) {
+    call_state().err = "embed (tc) workspace too small";
+    return -3;
+  }
+  char* p = static_cast<char*>(ws);
+  uint8_t* ghi = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
+  uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
+  uint8_t* w1 = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)KK * EB_WTAP_BYTES);
+  uint8_t* w2 = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)KK * EB_WTAP_BYTES);
+  unsigned* wmax = reinterpret_cast<unsigned*>(p);
+
+  DAGL_CUDA_OK(cudaMemsetAsync(wmax, 0, 2 * sizeof(unsigned), st));
+  absmax_flat_kernel<<<64, 256, 0, st>>>(fc1_w, ED * VD, wmax + 0);
+  DAGL_LAUNCH_CHECK();
+  absmax_flat_kernel<<<64, 256, 0, st>>>(fc2_w, ED * VD, wmax + 1);
+  DAGL_LAUNCH_CHECK();
+  pack_fc_kernel<<<KK, 256, 0, st>>>(fc1_w, wmax + 0, w1);
+  DAGL_LAUNCH_CHECK();
+  pack_fc_kernel<<<KK, 256, 0, st>>>(fc2_w, wmax + 1, w2);
+  DAGL_LAUNCH_CHECK();
+  pack_g_kernel<<<dim3((eg.NPG + 255) / 256, g.B), 256, 0, st>>>(g, eg, G, absmax, ghi, glo);
+  DAGL_LAUNCH_CHECK();
+
+  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
+  const int oy = PADK - g.qpad_top, ox = PADK - g.qpad_left;
+  dim3 grid(eg.ntile, g.B);
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q,
+                                                        nullptr, absmax);
+  DAGL_LAUNCH_CHECK();
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K,
+                                                        colsum_partial, absmax);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dagl

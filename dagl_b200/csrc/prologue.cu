@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(FM_THREADS)
 feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict__ g_w,
                     const float* __restrict__ g_b, const float* __restrict__ th_w,
                     const float* __restrict__ th_b, float* __restrict__ G, float* __restrict__ Th,
-                    unsigned* __restrict__ absmax /*nullable: [B][3], slot 2 = max|theta|*/) {
+                    unsigned* __restrict__ absmax /*nullable: [B][AMAX_STRIDE]*/) {
   extern __shared__ float smem[];
   float* gw_s = smem;                       // [C][9][16]
   float* tw_s = smem + g.C * 9 * CI;        // [C][16]
@@ -74,7 +74,7 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
       at[4 * j + 3] = fmaf(v[4], w.w, at[4 * j + 3]);
     }
   }
-  float tmax = 0.f;
+  float tmax = 0.f, gmax = 0.f;
   if (live) {
     float* Go = G + (size_t)img * CI * g.Nk + p;
     float* To = Th + (size_t)img * CI * g.Nk + p;
@@ -83,12 +83,19 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
       Go[(size_t)c * g.Nk] = ag[c];
       To[(size_t)c * g.Nk] = at[c];
       tmax = fmaxf(tmax, fabsf(at[c]));
+      gmax = fmaxf(gmax, fabsf(ag[c]));
     }
   }
   if (absmax != nullptr) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(absmax + img * 3 + 2, __float_as_uint(tmax));
+    for (int o = 16; o > 0; o >>= 1) {
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(absmax + img * AMAX_STRIDE + AMAX_THETA, __float_as_uint(tmax));
+      atomicMax(absmax + img * AMAX_STRIDE + AMAX_G, __float_as_uint(gmax));
+    }
   }
 }
 
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(EM_THREADS, 2)
 embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w,
              const float* __restrict__ fc_b, float* __restrict__ out,
              int ny, int nx, int s, int off_y, int off_x, float* __restrict__ colsum_partial,
-             unsigned* __restrict__ absmax /*nullable: this tensor's slot of image 0; stride 3 per image*/) {
+             unsigned* __restrict__ absmax /*nullable: [B][AMAX_STRIDE]*/, int absmax_slot) {
   extern __shared__ float smem[];
   float* Ws = smem;                              // [49][225]
   float* As = smem + EM_WS_FLOATS;               // [49][64]
@@ -238,7 +245,7 @@ embed_kernel(Geom g, const float* __restrict__ G, const float* __restrict__ fc_w
   if (absmax != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) atomicMax(absmax + img * 3, __float_as_uint(vmax));   // values are >= 0: uint order == float order
+    if (lane == 0) atomicMax(absmax + img * AMAX_STRIDE + absmax_slot, __float_as_uint(vmax));   // values are >= 0: uint order == float order
   }
   if (colsum_partial != nullptr) {
     __syncthreads();
@@ -259,27 +266,36 @@ int embed_num_blocks(int npos) { return (npos + EM_POS - 1) / EM_POS; }
 
 int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* fc_b, float* out,
                  int ny, int nx, int s, int off_y, int off_x, float* colsum_partial, unsigned* absmax,
-                 cudaStream_t st) {
+                 int absmax_slot, cudaStream_t st) {
   size_t smem = (size_t)(EM_WS_FLOATS + KK * EM_POS) * sizeof(float);
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(embed_num_blocks(ny * nx), g.B);
-  embed_kernel<<<grid, EM_THREADS, smem, st>>>(g, G, fc_w, fc_b, out, ny, nx, s, off_y, off_x, colsum_partial, absmax);
+  embed_kernel<<<grid, EM_THREADS, smem, st>>>(g, G, fc_w, fc_b, out, ny, nx, s, off_y, off_x, colsum_partial, absmax, absmax_slot);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
 
-// Kbar[e] = (1/Nk) * sum over CTAs of the partial column sums, fixed order, fp64 accumulate.
-__global__ void kbar_kernel(const float* __restrict__ partial, int nblk, int Nk, float* __restrict__ Kbar) {
+// Kbar[e] = (1/Nk) * sum over CTAs of the partial column sums; fixed summation order (8 interleaved
+// fp64 chains, then a fixed tree), so the result is deterministic.
+__global__ void __launch_bounds__(256) kbar_kernel(const float* __restrict__ partial, int nblk, int Nk, float* __restrict__ Kbar) {
+  __shared__ double acc_s[8][ED];
   const int img = blockIdx.x;
-  for (int e = threadIdx.x; e < ED; e += blockDim.x) {
+  const int lane8 = threadIdx.x / 32;                    // 8 chains
+  for (int e = threadIdx.x % 32; e < ED; e += 32) {
     double s = 0.0;
-    for (int k = 0; k < nblk; ++k) s += (double)partial[((size_t)img * nblk + k) * ED + e];
+    for (int k = lane8; k < nblk; k += 8) s += (double)__ldg(partial + ((size_t)img * nblk + k) * ED + e);
+    acc_s[lane8][e] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ED; e += 256) {
+    const double s = ((acc_s[0][e] + acc_s[1][e]) + (acc_s[2][e] + acc_s[3][e])) +
+                     ((acc_s[4][e] + acc_s[5][e]) + (acc_s[6][e] + acc_s[7][e]));
     Kbar[(size_t)img * ED + e] = (float)(s / (double)Nk);
   }
 }
 
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st) {
-  kbar_kernel<<<g.B, 224, 0, st>>>(colsum_partial, nblk, g.Nk, Kbar);
+  kbar_kernel<<<g.B, 256, 0, st>>>(colsum_partial, nblk, g.Nk, Kbar);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
