@@ -288,7 +288,7 @@ size_t attend_simt_workspace_bytes(const Geom& g) {
   int ns, ntx, tw;
   simt_tiling(g, &ns, &ntx, &tw);
   const size_t rows = (size_t)g.B * ns * g.Nq;
-  return align_up(rows * VD * sizeof(float)) + 3 * align_up(rows * sizeof(float));
+  return align_up(rows * VD * sizeof(float)) + 3 * align_up(rows * sizeof(float)) + align_up(merge_fold_scratch_bytes(g));
 }
 
 int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st) {
@@ -303,7 +303,8 @@ int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st) {
   float* Opart = reinterpret_cast<float*>(p); p += align_up(rows * VD * sizeof(float));
   float* mpart = reinterpret_cast<float*>(p); p += align_up(rows * sizeof(float));
   float* lpart = reinterpret_cast<float*>(p); p += align_up(rows * sizeof(float));
-  float* coef = reinterpret_cast<float*>(p);
+  float* coef = reinterpret_cast<float*>(p); p += align_up(rows * sizeof(float));
+  float* Om = reinterpret_cast<float*>(p);
 
   const int nwords = (g.Nk + 31) / 32;
   if (a.mask_bits) DAGL_CUDA_OK(cudaMemsetAsync(a.mask_bits, 0, (size_t)g.B * g.Nq * nwords * sizeof(uint32_t), st));
@@ -317,7 +318,7 @@ int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st) {
                                                      ns, ntx, tw, Opart, mpart, lpart, a.mask_bits, a.nnz);
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
-  return launch_merge_fold(g, ns, Opart, mpart, lpart, coef, a.y, /*log2_units=*/0, /*shift_major=*/0, 1.f, st);
+  return launch_merge_fold(g, ns, Opart, mpart, lpart, coef, Om, a.y, /*log2_units=*/0, /*shift_major=*/0, 1.f, st);
 }
 
 }  // namespace dagl

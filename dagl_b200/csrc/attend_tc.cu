@@ -555,6 +555,445 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
 }
 
+// =============================================================================================
+// v2: 2-CTA cluster per query tile.  The two value-column halves (CTA rank 0 / 1) no longer both
+// compute the scores: CTA h owns the key tiles j with (j & 1) == h, runs S + softmax for them and
+// writes the fp16 P tile into BOTH CTAs' shared memory (DSMEM); both CTAs run P.V for every tile on
+// their own half of the value columns (P read from smem; the four value-column groups of a k-step
+// share it through the A collector).  Sharing P across CTAs needs one softmax reference per query row
+// that both agree on, so the reference is fixed up front: a cheap pre-pass (rowmax_tc_kernel, Qh.Kh
+// only) gives max_k S[q,k] to fp16 accuracy, and exponent(s) = c*s*relu(s - T) is monotone in s >= 0,
+// so ref_q = exponent(1.004 * smax_q) bounds every term.  No online maximum, no accumulator rescale,
+// and key-split partials merge by plain sums.
+// =============================================================================================
+constexpr int RM_TILES = 4;                                 // key tiles per pre-pass step (A operand re-used 4x)
+constexpr int RM_STAGE_BYTES = RM_TILES * K_HALF_BYTES;     // 79872
+constexpr int RM_SM_Q = 0;
+constexpr int RM_SM_K = Q_HALF_BYTES;                       // 53248 = 52 * 1024
+constexpr int RM_SM_BAR = RM_SM_K + 2 * RM_STAGE_BYTES;
+constexpr int RM_SM_TOTAL = RM_SM_BAR + 128;
+constexpr int RM_THREADS = 192;
+static_assert(RM_SM_K % 1024 == 0, "pre-pass smem alignment");
+
+// smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits
+__global__ void __launch_bounds__(RM_THREADS, 1)
+rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
+                 unsigned* __restrict__ smax) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* d_full = bars + 5;    // [2]
+  uint64_t* d_empty = bars + 7;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int qt = blockIdx.x, split = blockIdx.y, img = blockIdx.z;
+  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int nsteps = (t_end - t_begin + RM_TILES - 1) / RM_TILES;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, Q_HALF_BYTES);
+      bulk_g2s(smem + RM_SM_Q, Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES, Q_HALF_BYTES, q_full);
+      for (int st = 0; st < nsteps; ++st) {
+        const int s = st & 1;
+        mbar_wait(k_empty + s, ((uint32_t)(st >> 1) & 1u) ^ 1u);
+        const int t0 = t_begin + st * RM_TILES;
+        const int nt = min(RM_TILES, t_end - t0);
+        mbar_arrive_expect_tx(k_full + s, (uint32_t)nt * K_HALF_BYTES);
+        for (int i = 0; i < nt; ++i)
+          bulk_g2s(smem + RM_SM_K + s * RM_STAGE_BYTES + i * K_HALF_BYTES,
+                   Kp + ((size_t)img * tg.NT + t0 + i) * K_TILE_BYTES, K_HALF_BYTES, k_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
+      const uint64_t dq = smem_desc(smem_u32(smem + RM_SM_Q), (TC_BM / 8) * 128, 128);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int st = 0; st < nsteps; ++st) {
+        const int s = st & 1;
+        const uint32_t ph = (uint32_t)(st >> 1) & 1u;
+        mbar_wait(k_full + s, ph);
+        mbar_wait(d_empty + s, ph ^ 1u);
+        tc_fence_after();
+        const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
+        const uint32_t kb = smem_u32(smem + RM_SM_K + s * RM_STAGE_BYTES);
+#pragma unroll 1
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+          const uint32_t ko = ks * 2 * (TC_BN / 8) * 128;
+          for (int i = 0; i < nt; ++i) {
+            const uint64_t dk = smem_desc(kb + i * K_HALF_BYTES + ko, (TC_BN / 8) * 128, 128);
+            const uint32_t d = tbase + s * (RM_TILES * TC_BN) + i * TC_BN;
+            if (i == 0) mma_f16_ss_a_fill(d, dq + qo, dk, idS, ks > 0);      // Qh slab read once per k-step ...
+            else mma_f16_ss_a_use(d, dq + qo, dk, idS, ks > 0);              // ... and re-used for the other tiles
+          }
+        }
+        mma_commit(k_empty + s);
+        mma_commit(d_full + s);
+      }
+    }
+  } else {
+    const int quad = warp & 3, lane = tid & 31;
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    float m = 0.f;
+    for (int st = 0; st < nsteps; ++st) {
+      const int s = st & 1;
+      mbar_wait(d_full + s, (uint32_t)(st >> 1) & 1u);
+      tc_fence_after();
+      const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
+      for (int c0 = 0; c0 < nt * TC_BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + s * (RM_TILES * TC_BN) + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(d_empty + s);
+    }
+    atomicMax(smax + ((size_t)img * tg.nqt + qt) * TC_BM + quad * 32 + lane, __float_as_uint(m));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tbase);
+}
+
+constexpr int P_SLOT_BYTES = TC_BM * TC_BN * 2;             // 12288: one P tile, K-major no-swizzle A operand
+constexpr int S2_Q = 0;
+constexpr int S2_K = S2_Q + Q_TILE_BYTES;
+constexpr int S2_T = S2_K + 2 * K_TILE_BYTES;
+constexpr int S2_P = S2_T + 2 * TH_STAGE_BYTES;
+constexpr int S2_BAR = S2_P + 2 * P_SLOT_BYTES;
+constexpr int S2_RED = S2_BAR + 256;                         // [4 quad][3 sub][32] floats, then the same as ints
+constexpr int S2_TOTAL = S2_RED + 2 * 4 * 3 * 32 * 4;
+static_assert(S2_P % 1024 == 0, "P slots alignment");
+static_assert(S2_TOTAL <= 232448, "v2 kernel exceeds the 227 KB dynamic shared memory limit");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
+                  const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
+                  const float* __restrict__ thrA, const float* __restrict__ thrB,
+                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
+                  int nsplit, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
+                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2] ring over OWN tiles
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* t_full = bars + 5;    // [2] ring over ALL tiles
+  uint64_t* t_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] S buffers (own tiles)
+  uint64_t* s_free = bars + 11;   // [2] the softmax warps have read the S buffer
+  uint64_t* p_full = bars + 13;   // [2] slot r is written by CTA rank r (into both CTAs)
+  uint64_t* p_free = bars + 15;   // [2] slot r consumed by the P.V of both CTAs (only slot `rank` is waited on here)
+  uint64_t* pv_last = bars + 17;  // final P.V complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int img = blockIdx.z, split = blockIdx.y;
+  const int qt = blockIdx.x >> 1;
+  const int half = (int)cluster_ctarank();                  // == blockIdx.x & 1
+  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int ntiles = t_end - t_begin;
+  const int n_own = (ntiles - half + 1) / 2;                // local tiles j with (j & 1) == half
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
+      mbar_init(s_full + i, 1); mbar_init(s_free + i, 384);
+      mbar_init(p_full + i, 384); mbar_init(p_free + i, 2);
+    }
+    mbar_init(pv_last, 1);
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // peer barriers are initialised before any remote access
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
+      mbar_arrive_expect_tx(q_full, Q_TILE_BYTES);
+      bulk_g2s(smem + S2_Q, qsrc, Q_HALF_BYTES, q_full);
+      bulk_g2s(smem + S2_Q + Q_HALF_BYTES, qsrc + Q_HALF_BYTES, Q_HALF_BYTES, q_full);
+      const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
+      auto load_k = [&](int i) {                            // own tile i  (local tile 2i + half)
+        const int s = i & 1;
+        mbar_wait(k_empty + s, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
+        bulk_g2s(smem + S2_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t_begin + 2 * i + half) * K_TILE_BYTES,
+                 K_TILE_BYTES, k_full + s);
+      };
+      auto load_t = [&](int j) {
+        const int s = j & 1, t = t_begin + j;
+        mbar_wait(t_empty + s, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(t_full + s, TH_STAGE_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < TH_SLOTS; ++sl) {
+          const int first = (t * TC_BN + c_groups[half][sl].dy * tg.Wp) & ~7;
+          bulk_g2s(smem + S2_T + s * TH_STAGE_BYTES + sl * TH_SEG_BYTES, thp + (size_t)first * 32, TH_SEG_BYTES, t_full + s);
+        }
+      };
+      if (n_own > 0) load_k(0);
+      for (int p = 0; 2 * p < ntiles; ++p) {
+        if (p + 1 < n_own) load_k(p + 1);
+        load_t(2 * p);
+        if (2 * p + 1 < ntiles) load_t(2 * p + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
+      const uint32_t q_hi = smem_u32(smem + S2_Q), q_lo = q_hi + Q_HALF_BYTES;
+      const uint64_t dq_hi = smem_desc(q_hi, (TC_BM / 8) * 128, 128);
+      const uint64_t dq_lo = smem_desc(q_lo, (TC_BM / 8) * 128, 128);
+      const uint32_t p_free_prod[2] = {mapa(smem_u32(p_free + 0), 0), mapa(smem_u32(p_free + 1), 1)};
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+
+      auto issue_S = [&](int i) {                           // own tile i
+        const int s = i & 1;
+        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(k_full + s, ph);
+        mbar_wait(s_free + s, ph ^ 1u);                     // softmax has pulled the previous contents of this S buffer
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(smem + S2_K + s * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
+        const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
+        const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
+        const uint32_t d = tbase + TC_S_COL0 + s * TC_BN;
+#pragma unroll
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+          mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, ks > 0);             // Ql.Kh first (small terms; see v1)
+        }
+#pragma unroll
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+          mma_f16_ss_a_fill(d, dq_hi + qo, dk_lo + ko, idS, 1);           // Qh.Kl
+          mma_f16_ss_a_lastuse(d, dq_hi + qo, dk_hi + ko, idS, 1);        // Qh.Kh (A from the collector)
+        }
+        mma_commit(s_full + s);
+        mma_commit(k_empty + s);
+      };
+
+      if (n_own > 0) issue_S(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if ((j & 1) == 0 && (j >> 1) + 1 < n_own) issue_S((j >> 1) + 1);   // scores one tile pair ahead
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait_cluster(p_full + s, ph);
+        mbar_wait(t_full + s, ph);
+        tc_fence_after();
+        const int t = t_begin + j;
+        const uint32_t tstage = smem_u32(smem + S2_T + s * TH_STAGE_BYTES);
+        const uint32_t pbase = smem_u32(smem + S2_P + s * P_SLOT_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < TC_BN / 16; ++ks) {
+          const uint64_t ad = smem_desc(pbase + ks * 2 * (TC_BM / 8) * 128, (TC_BM / 8) * 128, 128);
+#pragma unroll
+          for (int sl = 0; sl < TH_SLOTS; ++sl) {
+            const PvGroup gp = c_groups[half][sl];
+            const int off = ((t * TC_BN + gp.dy * tg.Wp) & 7) + gp.dx0 + ks * 16;
+            const uint32_t start = tstage + sl * TH_SEG_BYTES + off * 32;
+            const uint64_t bd = (uint64_t)((start >> 4) & 0x3FFF) | ((uint64_t)(32 >> 4) << 16) |
+                                ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+            const uint32_t idP = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
+            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+            // the four value-column groups of a k-step share the P slab through the A collector
+            if (sl == 0) mma_f16_ss_a_fill(tbase + gp.col0, ad, bd, idP, acc);
+            else if (sl == TH_SLOTS - 1) mma_f16_ss_a_lastuse(tbase + gp.col0, ad, bd, idP, acc);
+            else mma_f16_ss_a_use(tbase + gp.col0, ad, bd, idP, acc);
+          }
+        }
+        mma_commit(t_empty + s);
+        if (j + 2 < ntiles) mma_commit_caddr(p_free_prod[s]);   // slot s may be refilled by its producer CTA
+        if (j == ntiles - 1) mma_commit(pv_last);
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int lane = tid & 31;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
+    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
+    const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) *
+                               pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
+    const int q = qt * TC_BM + row;
+    const bool qvalid = q < g.Nq;
+    // fixed softmax reference: exponent of an upper bound of the row maximum (the pre-pass is Qh.Kh only, 2^-10 rel.)
+    float ref;
+    {
+      const float s_hi = __uint_as_float(__ldg(smax + qidx)) * inv_s * 1.00390625f;
+      const float rl = fmaxf((s_hi - tA) + tB, 0.f);
+      // ... minus 12: P is stored as fp16, so the row maximum is placed near 2^12 (fp16 max is 2^16) to keep the
+      // long tail of small weights (which carries real mass in dense rows) out of the fp16 subnormal range
+      ref = (s_hi * rl) * sm_scale_log2 - 12.f;
+    }
+    float l_run = 0.f;
+    int cnt = 0;
+    const int nwords = (g.Nk + 31) / 32;
+    const uint32_t peer = (uint32_t)(half ^ 1);
+    // my 2 chunks (keys 16*sub .. 16*sub+15) of P slot `half`: chunk stride 2048 B, 16 B per row
+    const uint32_t p_local = smem_u32(smem + S2_P + half * P_SLOT_BYTES) + (2 * sub) * (TC_BM / 8) * 128 + row * 16;
+    const uint32_t p_remote = mapa(p_local, peer);
+    const uint32_t pfull_remote = mapa(smem_u32(p_full + half), peer);
+
+    for (int i = 0; i < n_own; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int t = t_begin + 2 * i + half;
+      const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
+      mbar_wait(s_full + s, ph);
+      tc_fence_after();
+      float sv[16];
+      {
+        uint32_t r0[16];
+        tmem_ld16(trow + TC_S_COL0 + s * TC_BN + 16 * sub, r0);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sv[k] = __uint_as_float(r0[k]);
+      }
+      tc_fence_before();
+      mbar_arrive(s_free + s);                              // the S buffer may now be overwritten (scores two own tiles ahead)
+      unsigned mk = 0u;
+      uint32_t pk[8];
+      float psum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        float p[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float sc = sv[k + u] * inv_s;               // exact: inv_s is a power of two
+          const float rl = fmaxf((sc - tA) + tB, 0.f);      // relu(S - mu*gamma + beta), dagl.py:256
+          const bool valid = (vbits >> (k + u)) & 1u;
+          const float pe = valid ? ex2_approx((sc * rl) * sm_scale_log2 - ref) : 0.f;   // dummy key slots contribute nothing
+          const bool nb = valid && (rl != 0.f);             // mask_b, dagl.py:257
+          if (nb) mk |= 1u << (k + u);
+          p[u] = nb ? pe : 0.f;                             // numerator: neighbours only
+          if (!nb) psum += pe;                              // denominator: every valid key ...
+        }
+        pk[k / 2] = pack_half2(p[0], p[1]);
+        // ... with the neighbours entering as the fp16 values the tensor core will see, so that the
+        // rounding of a dominant weight cancels between numerator and denominator
+        const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
+        psum += pr.x + pr.y;
+      }
+      l_run += psum;
+      cnt += __popc(mk);
+      // slot `half` must have been drained by the P.V of BOTH CTAs for my previous tile
+      mbar_wait_cluster(p_free + half, (uint32_t)(i & 1) ^ 1u);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      st_cluster_v4(p_remote, pk[0], pk[1], pk[2], pk[3]);
+      st_cluster_v4(p_remote + 2048, pk[4], pk[5], pk[6], pk[7]);
+      fence_proxy_async_all();                              // generic-proxy writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(p_full + half);
+      mbar_arrive_cluster(pfull_remote);
+
+      if (mask_bits != nullptr && qvalid && mk != 0u) {     // debug path only
+        uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
+        unsigned rem = mk;
+        while (rem) {
+          const int b = __ffs((int)rem) - 1;
+          rem &= rem - 1;
+          const int kp = t * TC_BN + 16 * sub + b;
+          const int kk = (kp / tg.Wp) * g.W + (kp % tg.Wp);
+          atomicOr(mrow + (kk >> 5), 1u << (kk & 31));
+        }
+      }
+    }
+
+    // ---- epilogue: partial accumulator -> global ----
+    if (ntiles > 0) {
+      mbar_wait(pv_last, 0);
+      tc_fence_after();
+    }
+    const float inv_t = 1.f / pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
+    const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
+    float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
+    int chunk = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < TH_SLOTS; ++sl) {
+      const PvGroup gp = c_groups[half][sl];
+      for (int gdx = 0; gdx < gp.n / 16; ++gdx, ++chunk) {
+        if (chunk % 3 != sub) continue;                     // warp-uniform: the three warps of a quadrant share the columns
+        uint32_t v[16];
+        tmem_ld16(trow + gp.col0 + gdx * 16, v);
+        tmem_wait_ld();
+        if (qvalid) {
+          float4* dst = reinterpret_cast<float4*>(orow + (gp.dy * KS + gp.dx0 + gdx) * CI);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_float4(__uint_as_float(v[4 * k]) * inv_t, __uint_as_float(v[4 * k + 1]) * inv_t,
+                                 __uint_as_float(v[4 * k + 2]) * inv_t, __uint_as_float(v[4 * k + 3]) * inv_t);
+        }
+      }
+    }
+    // row sums / neighbour counts of the three column groups (this CTA's own tiles only)
+    float* xl = reinterpret_cast<float*>(smem + S2_RED) + (quad * 3) * 32;
+    int* xc = reinterpret_cast<int*>(smem + S2_RED + 4 * 3 * 32 * 4) + (quad * 3) * 32;
+    xl[sub * 32 + lane] = l_run;
+    xc[sub * 32 + lane] = cnt;
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
+    if (sub == 0 && qvalid) {
+      lpart[(((size_t)img * nsplit + split) * 2 + half) * g.Nq + q] = (xl[lane] + xl[32 + lane]) + xl[64 + lane];
+      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                       // nobody leaves while the peer can still write here
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
+}
+
+// coef[b][s][q] = 1 / sum_{s,h} l   (fixed-reference partials merge by plain sums)
+__global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, const float* __restrict__ lpart, float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Nq) return;
+  const int img = i / Nq, q = i % Nq;
+  float L = 0.f;
+  for (int s = 0; s < nsplit; ++s)
+    for (int h = 0; h < 2; ++h) L += lpart[(((size_t)img * nsplit + s) * 2 + h) * Nq + q];
+  const float inv = 1.f / L;
+  for (int s = 0; s < nsplit; ++s) coef[((size_t)img * nsplit + s) * Nq + q] = inv;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -575,7 +1014,7 @@ static int tc_splits(const Geom& g, const TcGeom& tg) {
 }
 
 struct TcWs {
-  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, total;
+  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, Om, smax, total;
   int nsplit;
 };
 
@@ -594,15 +1033,17 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
   w.Opart = take(rows * VD * 4);
   w.mpart = take(rows * 4);
-  w.lpart = take(rows * 4);
+  w.lpart = take(2 * rows * 4);                 // v2 keeps one row-sum partial per cluster rank
   w.coef = take(rows * 4);
+  w.Om = take(merge_fold_scratch_bytes(g));
+  w.smax = take((size_t)g.B * tg.nqt * TC_BM * 4);
   w.total = off;
   return w;
 }
 
 size_t attend_tc_workspace_bytes(const Geom& g) { return tc_ws(g, tc_geom(g)).total; }
 
-int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, cudaStream_t st) {
+int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, int variant, cudaStream_t st) {
   const TcGeom tg = tc_geom(g);
   const TcWs w = tc_ws(g, tg);
   if (a.ws_bytes < w.total) {
@@ -621,6 +1062,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   float* mpart = reinterpret_cast<float*>(base + w.mpart);
   float* lpart = reinterpret_cast<float*>(base + w.lpart);
   float* coef = reinterpret_cast<float*>(base + w.coef);
+  float* Om = reinterpret_cast<float*>(base + w.Om);
 
   if (absmax_in != nullptr) {
     absmax = const_cast<unsigned*>(absmax_in);      // filled by the prologue kernels of the same forward
@@ -651,15 +1093,37 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     DAGL_LAUNCH_CHECK();
   }
 
-  DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   const float sm_scale_log2 = a.scale * 1.4426950408889634f;
   dim3 grid(tg.nqt * 2, w.nsplit, g.B);
+  if (variant == 2) {
+    unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
+    DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, (size_t)g.B * tg.nqt * TC_BM * 4, st));
+    // pre-pass: row maxima of the scores (Qh.Kh only)
+    int pre_split = 148 / (tg.nqt * g.B);
+    if (pre_split < 1) pre_split = 1;
+    const int max_split = (tg.NT + RM_TILES - 1) / RM_TILES;
+    if (pre_split > max_split) pre_split = max_split;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
+    rowmax_tc_kernel<<<dim3(tg.nqt, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, smax);
+    DAGL_LAUNCH_CHECK();
+    DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
+    if (int rc = prof_begin(st)) return rc;
+    attend_tc2_kernel<<<grid, TC_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+                                                          sm_scale_log2, w.nsplit, Opart, lpart, a.mask_bits, a.nnz);
+    DAGL_LAUNCH_CHECK();
+    if (int rc = prof_end(st)) return rc;
+    const int nq_total = g.B * g.Nq;
+    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, lpart, coef);
+    DAGL_LAUNCH_CHECK();
+    return launch_rows_fold(g, w.nsplit, Opart, coef, Om, a.y, /*shift_major=*/1, st);
+  }
+  DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   if (int rc = prof_begin(st)) return rc;
   attend_tc_kernel<<<grid, TC_THREADS, SM_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, sm_scale_log2,
                                                        w.nsplit, Opart, mpart, lpart, a.mask_bits, a.nnz);
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
-  return launch_merge_fold(g, w.nsplit, Opart, mpart, lpart, coef, a.y, /*log2_units=*/1, /*shift_major=*/1, 1.f, st);
+  return launch_merge_fold(g, w.nsplit, Opart, mpart, lpart, coef, Om, a.y, /*log2_units=*/1, /*shift_major=*/1, 1.f, st);
 }
 
 }  // namespace dagl

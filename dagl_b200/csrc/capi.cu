@@ -90,7 +90,11 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
   if (impl == DAGL_IMPL_AUTO) impl = DAGL_IMPL_TC;
   if (impl == DAGL_IMPL_TC) {
     call_state().impl = "tc";
-    return launch_attend_tc(g, a, absmax, st);
+    return launch_attend_tc(g, a, absmax, 2, st);
+  }
+  if (impl == DAGL_IMPL_TC1) {
+    call_state().impl = "tc1";
+    return launch_attend_tc(g, a, absmax, 1, st);
   }
   if (impl != DAGL_IMPL_SIMT) {
     call_state().err = "unknown impl";

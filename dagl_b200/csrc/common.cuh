@@ -106,14 +106,19 @@ struct AttendArgs {
   uint32_t* mask_bits; int32_t* nnz;
   void* ws; size_t ws_bytes;
 };
+size_t merge_fold_scratch_bytes(const Geom& g);      // Omerged [B][Nq][784]
+int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
+                     int shift_major, cudaStream_t st);
 int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
-                      float* coef, float* y, int log2_units, int shift_major, float out_scale, cudaStream_t st);
+                      float* coef, float* Omerged, float* y, int log2_units, int shift_major, float out_scale,
+                      cudaStream_t st);
 size_t attend_simt_workspace_bytes(const Geom& g);
 int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st);
 
 // tensor-core path (attend_tc.cu).  `absmax` [B][AMAX_STRIDE] holds max Q, max K, max|theta| as float bits;
 // when null the launcher computes it with a reduction kernel (split entry).
 size_t attend_tc_workspace_bytes(const Geom& g);
-int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, cudaStream_t st);
+// variant 1: one CTA per value-column half (scores computed twice); variant 2: 2-CTA clusters sharing P (DSMEM)
+int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, int variant, cudaStream_t st);
 
 }  // namespace dagl

@@ -29,11 +29,30 @@ __global__ void merge_coef_kernel(int B, int Nq, int nsplit, int log2_units, flo
   }
 }
 
+// Omerged[q][d] = sum_s coef[s][q] * Opart[s][q][d]   (streaming, float4)
+__global__ void __launch_bounds__(256)
+merge_rows_kernel(int B, int Nq, int nsplit, const float* __restrict__ Opart, const float* __restrict__ coef,
+                  float* __restrict__ Om) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over B*Nq*(VD/4)
+  const size_t total = (size_t)B * Nq * (VD / 4);
+  if (i >= total) return;
+  const int d4 = (int)(i % (VD / 4));
+  const size_t bq = i / (VD / 4);
+  const int img = (int)(bq / Nq), q = (int)(bq % Nq);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nsplit; ++s) {
+    const size_t j = ((size_t)img * nsplit + s) * Nq + q;
+    const float c = __ldg(coef + j);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(Opart + j * VD) + d4);
+    acc.x = fmaf(c, v.x, acc.x); acc.y = fmaf(c, v.y, acc.y); acc.z = fmaf(c, v.z, acc.z); acc.w = fmaf(c, v.w, acc.w);
+  }
+  reinterpret_cast<float4*>(Om + bq * VD)[d4] = acc;
+}
+
 // y[c][py][px] = (1/cnt) * sum over the <=2x2 queries whose folded 7x7 patch covers the pixel
 // (F.fold with kernel 7, padding 3, stride 4, then / coverage count: dagl.py:265-272).
-// Partial layout per query row: shift_major=0 -> [c][dy][dx] (reference order), 1 -> [dy*7+dx][c].
-__global__ void fold_kernel(Geom g, int nsplit, int shift_major, const float* __restrict__ Opart,
-                            const float* __restrict__ coef, float* __restrict__ y) {
+// Row layout: shift_major=0 -> [c][dy][dx] (reference order), 1 -> [dy*7+dx][c].
+__global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ Om, float* __restrict__ y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = g.B * CI * g.Nk;
   if (i >= total) return;
@@ -46,26 +65,33 @@ __global__ void fold_kernel(Geom g, int nsplit, int shift_major, const float* __
       const int q = qy * g.nqx + qx;
       const int sh = (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
       const int d = shift_major ? sh * CI + c : c * KK + sh;
-      float v = 0.f;
-      for (int s = 0; s < nsplit; ++s) {
-        const size_t j = ((size_t)img * nsplit + s) * g.Nq + q;
-        v = fmaf(coef[j], Opart[j * VD + d], v);
-      }
-      sum += v;
+      sum += __ldg(Om + ((size_t)img * g.Nq + q) * VD + d);
     }
   const float cntf = (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
   y[i] = sum / cntf;
 }
 
+size_t merge_fold_scratch_bytes(const Geom& g) { return (size_t)g.B * g.Nq * VD * sizeof(float); }
+
+// merge (given coefficients) + fold
+int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
+                     int shift_major, cudaStream_t st) {
+  const size_t n4 = (size_t)g.B * g.Nq * (VD / 4);
+  merge_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(g.B, g.Nq, nsplit, Opart, coef, Omerged);
+  DAGL_LAUNCH_CHECK();
+  const int total = g.B * CI * g.Nk;
+  fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, shift_major, Omerged, y);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
-                      float* coef, float* y, int log2_units, int shift_major, float out_scale, cudaStream_t st) {
+                      float* coef, float* Omerged, float* y, int log2_units, int shift_major, float out_scale,
+                      cudaStream_t st) {
   const int nq_total = g.B * g.Nq;
   merge_coef_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, nsplit, log2_units, out_scale, mpart, lpart, coef);
   DAGL_LAUNCH_CHECK();
-  const int total = g.B * CI * g.Nk;
-  fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, nsplit, shift_major, Opart, coef, y);
-  DAGL_LAUNCH_CHECK();
-  return 0;
+  return launch_rows_fold(g, nsplit, Opart, coef, Omerged, y, shift_major, st);
 }
 
 }  // namespace dagl

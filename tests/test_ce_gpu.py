@@ -19,8 +19,9 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-3          # north_star: <= 1e-3 relative fp32
 TIE_ULPS = 16           # a flipped mask entry must sit within this many fp32 ulps of the threshold
 IMPLS = ["simt", "tc"]
-# fp32 kernel: bit-faithful mask, fp32 sums.  tc kernel: split-fp16 scores (fp32-accurate), fp16 P and V
-# operands (2^-11 relative each) -> a few 1e-4 relative on the output, still inside the 1e-3 bar.
+# simt: fp32 kernel, bit-faithful mask, fp32 sums.  tc: tensor-core kernel, split-fp16 scores (fp32-accurate),
+# fp16 P and V operands (2^-11 relative each) -> a few 1e-4 relative on the output, inside the 1e-3 bar; 2-CTA
+# clusters + fixed softmax reference.  tc1: the earlier non-cluster tensor-core variant (online softmax).
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +66,7 @@ def assert_mask_parity(bits_gpu, aux, max_flips_frac=2e-6):
     return nflip
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + ["tc1"])
 def test_cfg1_golden(dev, rand_weights, impl):
     """BASELINE config 1: 1x64x64x64, reference-made weights/input/output."""
     g = load_npz("ce_cfg1_64x64.npz")
@@ -84,7 +85,7 @@ def test_cfg1_golden(dev, rand_weights, impl):
     assert torch.equal(y2, y)
 
 
-@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("impl", IMPLS + ["tc1"])
 def test_ragged_golden(dev, rand_weights, impl):
     """H, W not multiples of 4, non-square, batch 2, tiny (7x9), chop-leaf 72x72."""
     g = load_npz("ce_ragged.npz")
