@@ -112,20 +112,22 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n_per_img, uns
 //   MODE 0: queries, ROWS=128, row r of tile t <- Q[t*128 + r]; also emits tA = mu*gamma, tB = beta
 //   MODE 1: keys, ROWS=48, padded-flat slot k' = t*48 + r <- K[y*W + x] if x < W (y = k'/Wp, x = k'%Wp)
 // ---------------------------------------------------------------------------------------------
-template <int ROWS, int MODE>
+template <int ROWS, int MODE, int RPB /*rows per block; ROWS % RPB == 0*/>
 __global__ void __launch_bounds__(256)
 pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsigned* __restrict__ absmax,
                   uint8_t* __restrict__ tiles, unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ Kbar, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float* __restrict__ thrA, float* __restrict__ thrB) {
-  extern __shared__ __align__(16) float rows_s[];            // [ROWS][196]
-  const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+  extern __shared__ __align__(16) float rows_s[];            // [RPB][196]
+  constexpr int BPT = ROWS / RPB;                            // blocks per tile
+  const int t = blockIdx.x / BPT, r0 = (blockIdx.x % BPT) * RPB, img = blockIdx.y, tid = threadIdx.x;
+  const int ntile = gridDim.x / BPT;
   const int nrows_src = MODE == 0 ? g.Nq : g.Nk;
   const float* si = src + (size_t)img * nrows_src * ED;
   const float scale = pow2_scale(absmax[img * AMAX_STRIDE + MODE], 14);
 
-  for (int i = tid; i < ROWS * (ED / 4); i += 256) {
-    const int r = i / (ED / 4), e4 = i % (ED / 4);
+  for (int i = tid; i < RPB * (ED / 4); i += 256) {
+    const int r = r0 + i / (ED / 4), e4 = i % (ED / 4);
     int srow = -1;
     if (MODE == 0) {
       const int q = t * ROWS + r;
@@ -141,23 +143,23 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
   }
   __syncthreads();
 
-  uint8_t* tile = tiles + ((size_t)img * gridDim.x + t) * (size_t)(2 * ROWS * TC_EP * 2);
+  uint8_t* tile = tiles + ((size_t)img * ntile + t) * (size_t)(2 * ROWS * TC_EP * 2);
   constexpr int HALF = ROWS * TC_EP * 2;
-  // one thread per 16-byte output chunk, in output order (coalesced stores)
-  for (int o = tid; o < HALF / 16; o += 256) {
-    const int kc = o / ROWS, r = o % ROWS;          // chunk order inside a half: [kc][row-group][row%8] == [kc][row]
+  // one thread per 16-byte output chunk; consecutive threads -> consecutive rows of one chunk column (coalesced)
+  for (int o = tid; o < TC_ECH * RPB; o += 256) {
+    const int kc = o / RPB, rl = o % RPB;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float x0 = 0.f, x1 = 0.f;
       const int e = kc * 8 + 2 * j;
-      if (e < ED) { x0 = rows_s[r * ED + e] * scale; x1 = rows_s[r * ED + e + 1] * scale; }
+      if (e < ED) { x0 = rows_s[rl * ED + e] * scale; x1 = rows_s[rl * ED + e + 1] * scale; }
       const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
       const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
       hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    const uint32_t off = tile_chunk_off(r, kc, ROWS);   // == 16 * o
+    const uint32_t off = tile_chunk_off(r0 + rl, kc, ROWS);
     *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(tile + HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -168,19 +170,20 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
         const int kp = t * ROWS + r;
         if (kp < tg.NkP && (kp % tg.Wp) < g.W) m |= 1ull << r;
       }
-      tilemask[(size_t)img * gridDim.x + t] = m;
+      tilemask[(size_t)img * ntile + t] = m;
     }
   } else {
     // per-query threshold terms: mu = Q[q,:] . Kbar (fp64 accumulate), tA = mu*gamma, tB = beta  (dagl.py:256)
     const int lane = tid & 31, warp = tid >> 5;
-    for (int r = warp; r < ROWS; r += 8) {
+    for (int rl = warp; rl < RPB; rl += 8) {
+      const int r = r0 + rl;
       const int q = t * ROWS + r;
       double s = 0.0;
-      for (int e = lane; e < ED; e += 32) s += (double)rows_s[r * ED + e] * (double)__ldg(Kbar + (size_t)img * ED + e);
+      for (int e = lane; e < ED; e += 32) s += (double)rows_s[rl * ED + e] * (double)__ldg(Kbar + (size_t)img * ED + e);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) {
-        const size_t idx = ((size_t)img * gridDim.x + t) * ROWS + r;
+        const size_t idx = ((size_t)img * ntile + t) * ROWS + r;
         const float mu = (float)s;
         thrA[idx] = (q < g.Nq) ? mu * __ldg(gamma + (size_t)img * g.Nq + q) : 0.f;
         thrB[idx] = (q < g.Nq) ? __ldg(beta + (size_t)img * g.Nq + q) : -1.f;
@@ -566,40 +569,43 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
 // so ref_q = exponent(1.004 * smax_q) bounds every term.  No online maximum, no accumulator rescale,
 // and key-split partials merge by plain sums.
 // =============================================================================================
-constexpr int RM_TILES = 4;                                 // key tiles per pre-pass step (A operand re-used 4x)
-constexpr int RM_STAGE_BYTES = RM_TILES * K_HALF_BYTES;     // 79872
+constexpr int RM_TILES = 2;                                 // key tiles per pre-pass step
+constexpr int RM_QT = 2;                                    // query tiles per CTA (each K tile is fetched once for both)
+constexpr int RM_STAGE_BYTES = RM_TILES * K_HALF_BYTES;     // 39936
 constexpr int RM_SM_Q = 0;
-constexpr int RM_SM_K = Q_HALF_BYTES;                       // 53248 = 52 * 1024
-constexpr int RM_SM_BAR = RM_SM_K + 2 * RM_STAGE_BYTES;
+constexpr int RM_SM_K = RM_QT * Q_HALF_BYTES;               // 106496 = 104 * 1024
+constexpr int RM_KSTAGES = 3;
+constexpr int RM_SM_BAR = RM_SM_K + RM_KSTAGES * RM_STAGE_BYTES;
 constexpr int RM_SM_TOTAL = RM_SM_BAR + 128;
 constexpr int RM_THREADS = 192;
+constexpr int RM_DCOLS = RM_QT * RM_TILES * TC_BN;          // 192 accumulator columns per TMEM buffer
 static_assert(RM_SM_K % 1024 == 0, "pre-pass smem alignment");
 
-// smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits
+// smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits.
+// The pre-pass is bound by the L2 -> SM traffic of the K tiles, so a CTA serves two query tiles per K fetch.
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
                  unsigned* __restrict__ smax) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* d_full = bars + 5;    // [2]
-  uint64_t* d_empty = bars + 7;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* d_full = bars + 7;    // [2]
+  uint64_t* d_empty = bars + 9;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int qt = blockIdx.x, split = blockIdx.y, img = blockIdx.z;
+  const int qt0 = blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
+  const int nq_here = min(RM_QT, tg.nqt - qt0);
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int nsteps = (t_end - t_begin + RM_TILES - 1) / RM_TILES;
 
   if (tid == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 128);
-    }
+    for (int i = 0; i < RM_KSTAGES; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 128); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -610,11 +616,12 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, Q_HALF_BYTES);
-      bulk_g2s(smem + RM_SM_Q, Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES, Q_HALF_BYTES, q_full);
+      mbar_arrive_expect_tx(q_full, (uint32_t)nq_here * Q_HALF_BYTES);
+      for (int qi = 0; qi < nq_here; ++qi)
+        bulk_g2s(smem + RM_SM_Q + qi * Q_HALF_BYTES, Qp + ((size_t)img * tg.nqt + qt0 + qi) * Q_TILE_BYTES, Q_HALF_BYTES, q_full);
       for (int st = 0; st < nsteps; ++st) {
-        const int s = st & 1;
-        mbar_wait(k_empty + s, ((uint32_t)(st >> 1) & 1u) ^ 1u);
+        const int s = st % RM_KSTAGES;
+        mbar_wait(k_empty + s, ((uint32_t)(st / RM_KSTAGES) & 1u) ^ 1u);
         const int t0 = t_begin + st * RM_TILES;
         const int nt = min(RM_TILES, t_end - t0);
         mbar_arrive_expect_tx(k_full + s, (uint32_t)nt * K_HALF_BYTES);
@@ -626,58 +633,71 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
-      const uint64_t dq = smem_desc(smem_u32(smem + RM_SM_Q), (TC_BM / 8) * 128, 128);
+      const uint64_t dq0 = smem_desc(smem_u32(smem + RM_SM_Q), (TC_BM / 8) * 128, 128);
+      const uint64_t dq1 = smem_desc(smem_u32(smem + RM_SM_Q + Q_HALF_BYTES), (TC_BM / 8) * 128, 128);
       mbar_wait(q_full, 0);
       tc_fence_after();
       for (int st = 0; st < nsteps; ++st) {
-        const int s = st & 1;
-        const uint32_t ph = (uint32_t)(st >> 1) & 1u;
-        mbar_wait(k_full + s, ph);
-        mbar_wait(d_empty + s, ph ^ 1u);
+        const int s = st % RM_KSTAGES, db = st & 1;
+        mbar_wait(k_full + s, (uint32_t)(st / RM_KSTAGES) & 1u);
+        mbar_wait(d_empty + db, ((uint32_t)(st >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
         const uint32_t kb = smem_u32(smem + RM_SM_K + s * RM_STAGE_BYTES);
-#pragma unroll 1
+        // single-thread issue: keep the descriptor arithmetic out of the loop (fully unrolled, constants folded)
+        const uint64_t dk0 = smem_desc(kb, (TC_BN / 8) * 128, 128);
+        const uint64_t dk1 = smem_desc(kb + K_HALF_BYTES, (TC_BN / 8) * 128, 128);
+        const uint32_t d0 = tbase + db * RM_DCOLS;
+        const bool two_k = nt > 1, two_q = nq_here > 1;
+#pragma unroll
         for (int ks = 0; ks < TC_KSTEPS; ++ks) {
           const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
-          const uint32_t ko = ks * 2 * (TC_BN / 8) * 128;
-          for (int i = 0; i < nt; ++i) {
-            const uint64_t dk = smem_desc(kb + i * K_HALF_BYTES + ko, (TC_BN / 8) * 128, 128);
-            const uint32_t d = tbase + s * (RM_TILES * TC_BN) + i * TC_BN;
-            if (i == 0) mma_f16_ss_a_fill(d, dq + qo, dk, idS, ks > 0);      // Qh slab read once per k-step ...
-            else mma_f16_ss_a_use(d, dq + qo, dk, idS, ks > 0);              // ... and re-used for the other tiles
+          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+          mma_f16_ss_a_fill(d0, dq0 + qo, dk0 + ko, idS, ks > 0);                        // Qh slab read once ...
+          if (two_k) mma_f16_ss_a_lastuse(d0 + TC_BN, dq0 + qo, dk1 + ko, idS, ks > 0);  // ... re-used for the 2nd key tile
+          if (two_q) {
+            mma_f16_ss_a_fill(d0 + 2 * TC_BN, dq1 + qo, dk0 + ko, idS, ks > 0);
+            if (two_k) mma_f16_ss_a_lastuse(d0 + 3 * TC_BN, dq1 + qo, dk1 + ko, idS, ks > 0);
           }
         }
         mma_commit(k_empty + s);
-        mma_commit(d_full + s);
+        mma_commit(d_full + db);
       }
     }
   } else {
     const int quad = warp & 3, lane = tid & 31;
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
-    float m = 0.f;
+    float m[RM_QT] = {0.f, 0.f};
     for (int st = 0; st < nsteps; ++st) {
-      const int s = st & 1;
-      mbar_wait(d_full + s, (uint32_t)(st >> 1) & 1u);
+      const int db = st & 1;
+      mbar_wait(d_full + db, (uint32_t)(st >> 1) & 1u);
       tc_fence_after();
       const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
-      for (int c0 = 0; c0 < nt * TC_BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + s * (RM_TILES * TC_BN) + c0, v);
-        tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+      for (int qi = 0; qi < RM_QT; ++qi) {
+        if (qi >= nq_here) break;
+        for (int c0 = 0; c0 < nt * TC_BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(trow + db * RM_DCOLS + qi * RM_TILES * TC_BN + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) m[qi] = fmaxf(m[qi], __uint_as_float(v[i]));
+        }
       }
       tc_fence_before();
-      mbar_arrive(d_empty + s);
+      mbar_arrive(d_empty + db);
     }
-    atomicMax(smax + ((size_t)img * tg.nqt + qt) * TC_BM + quad * 32 + lane, __float_as_uint(m));
+#pragma unroll
+    for (int qi = 0; qi < RM_QT; ++qi)
+      if (qi < nq_here)
+        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + quad * 32 + lane, __float_as_uint(m[qi]));
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tbase);
 }
 
+constexpr int TC2_THREADS = TC_THREADS + 32;                // + one warp that forwards P tiles to the peer CTA
 constexpr int P_SLOT_BYTES = TC_BM * TC_BN * 2;             // 12288: one P tile, K-major no-swizzle A operand
 constexpr int S2_Q = 0;
 constexpr int S2_K = S2_Q + Q_TILE_BYTES;
@@ -689,7 +709,7 @@ constexpr int S2_TOTAL = S2_RED + 2 * 4 * 3 * 32 * 4;
 static_assert(S2_P % 1024 == 0, "P slots alignment");
 static_assert(S2_TOTAL <= 232448, "v2 kernel exceeds the 227 KB dynamic shared memory limit");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ thrA, const float* __restrict__ thrB,
@@ -719,6 +739,11 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int ntiles = t_end - t_begin;
   const int n_own = (ntiles - half + 1) / 2;                // local tiles j with (j & 1) == half
+#ifdef DAGL_TC_TRACE
+  long long tr_a = 0, tr_b = 0, tr_c = 0;
+  const long long tr_start = clock64();
+  const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#endif
 
   if (tid == 0) {
     mbar_init(q_full, 1);
@@ -726,7 +751,8 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
       mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
       mbar_init(s_full + i, 1); mbar_init(s_free + i, 384);
-      mbar_init(p_full + i, 384); mbar_init(p_free + i, 2);
+      // P slot i is produced by CTA rank i: locally by 384 softmax threads, remotely by one bulk DSMEM copy (tx bytes)
+      mbar_init(p_full + i, i == half ? 384 : 1); mbar_init(p_free + i, 2);
     }
     mbar_init(pv_last, 1);
     mbar_init_fence();
@@ -784,8 +810,8 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       auto issue_S = [&](int i) {                           // own tile i
         const int s = i & 1;
         const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(k_full + s, ph);
-        mbar_wait(s_free + s, ph ^ 1u);                     // softmax has pulled the previous contents of this S buffer
+        { TRACE_T0(); mbar_wait(k_full + s, ph); TRACE_ADD(tr_a); }
+        { TRACE_T0(); mbar_wait(s_free + s, ph ^ 1u); TRACE_ADD(tr_a); }   // softmax has pulled the previous contents of this S buffer
         tc_fence_after();
         const uint32_t k_hi = smem_u32(smem + S2_K + s * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
         const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
@@ -808,38 +834,69 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         mma_commit(k_empty + s);
       };
 
+      // per-CTA constants of the four value-column groups (single-thread issue: keep the loop body lean)
+      uint32_t g_idesc[TH_SLOTS], g_col[TH_SLOTS];
+      int g_dywp[TH_SLOTS], g_dx0[TH_SLOTS];
+#pragma unroll
+      for (int sl = 0; sl < TH_SLOTS; ++sl) {
+        const PvGroup gp = c_groups[half][sl];
+        g_idesc[sl] = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
+        g_col[sl] = tbase + gp.col0;
+        g_dywp[sl] = gp.dy * tg.Wp;
+        g_dx0[sl] = gp.dx0;
+      }
+      // MN-major, SWIZZLE_32B: LBO = 32 B (next 16-channel N group = next pixel), SBO = 256 B (next 8 keys)
+      const uint64_t bd_hi = ((uint64_t)(32 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+
       if (n_own > 0) issue_S(0);
       for (int j = 0; j < ntiles; ++j) {
         if ((j & 1) == 0 && (j >> 1) + 1 < n_own) issue_S((j >> 1) + 1);   // scores one tile pair ahead
         const int s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait_cluster(p_full + s, ph);
-        mbar_wait(t_full + s, ph);
-        tc_fence_after();
         const int t = t_begin + j;
         const uint32_t tstage = smem_u32(smem + S2_T + s * TH_STAGE_BYTES);
         const uint32_t pbase = smem_u32(smem + S2_P + s * P_SLOT_BYTES);
+        uint32_t g_start[TH_SLOTS];
+#pragma unroll
+        for (int sl = 0; sl < TH_SLOTS; ++sl)
+          g_start[sl] = (tstage + sl * TH_SEG_BYTES + ((((t * TC_BN + g_dywp[sl]) & 7) + g_dx0[sl]) << 5)) >> 4;
+        const uint64_t ad0 = smem_desc(pbase, (TC_BM / 8) * 128, 128);
+        if (s != half) mbar_arrive_expect_tx(p_full + s, P_SLOT_BYTES);   // peer tile: arrives as a bulk copy into my slot
+        { TRACE_T0(); mbar_wait(p_full + s, ph); TRACE_ADD(tr_b); }
+        { TRACE_T0(); mbar_wait(t_full + s, ph); TRACE_ADD(tr_c); }
+        tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < TC_BN / 16; ++ks) {
-          const uint64_t ad = smem_desc(pbase + ks * 2 * (TC_BM / 8) * 128, (TC_BM / 8) * 128, 128);
+          const uint64_t ad = ad0 + (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
           for (int sl = 0; sl < TH_SLOTS; ++sl) {
-            const PvGroup gp = c_groups[half][sl];
-            const int off = ((t * TC_BN + gp.dy * tg.Wp) & 7) + gp.dx0 + ks * 16;
-            const uint32_t start = tstage + sl * TH_SEG_BYTES + off * 32;
-            const uint64_t bd = (uint64_t)((start >> 4) & 0x3FFF) | ((uint64_t)(32 >> 4) << 16) |
-                                ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-            const uint32_t idP = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
-            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t bd = bd_hi | (uint64_t)((g_start[sl] + ks * 32) & 0x3FFF);   // + 16 keys = 512 B
             // the four value-column groups of a k-step share the P slab through the A collector
-            if (sl == 0) mma_f16_ss_a_fill(tbase + gp.col0, ad, bd, idP, acc);
-            else if (sl == TH_SLOTS - 1) mma_f16_ss_a_lastuse(tbase + gp.col0, ad, bd, idP, acc);
-            else mma_f16_ss_a_use(tbase + gp.col0, ad, bd, idP, acc);
+            if (sl == 0) mma_f16_ss_a_fill(g_col[sl], ad, bd, g_idesc[sl], acc);
+            else if (sl == TH_SLOTS - 1) mma_f16_ss_a_lastuse(g_col[sl], ad, bd, g_idesc[sl], acc);
+            else mma_f16_ss_a_use(g_col[sl], ad, bd, g_idesc[sl], acc);
           }
         }
         mma_commit(t_empty + s);
         if (j + 2 < ntiles) mma_commit_caddr(p_free_prod[s]);   // slot s may be refilled by its producer CTA
         if (j == ntiles - 1) mma_commit(pv_last);
+      }
+    }
+  } else if (warp == TC_THREADS / 32) {
+    // ===================== P forwarder =====================
+    // Pushes every P tile produced in this CTA into the peer's slot with one bulk DSMEM copy that signals the
+    // peer's p_full barrier through its transaction count (async proxy end to end: no cluster-scope fences in
+    // the softmax warps).
+    if (elect_one()) {
+      const uint32_t peer = (uint32_t)(half ^ 1);
+      const uint32_t src = smem_u32(smem + S2_P + half * P_SLOT_BYTES);
+      const uint32_t dst = mapa(src, peer);
+      const uint32_t rbar = mapa(smem_u32(p_full + half), peer);
+      for (int i = 0; i < n_own; ++i) {
+        mbar_wait(p_full + half, (uint32_t)(i & 1));       // all 384 softmax threads have written + fenced
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "r"(src), "r"((uint32_t)P_SLOT_BYTES), "r"(rbar) : "memory");
       }
     }
   } else {
@@ -867,18 +924,17 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     float l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
-    const uint32_t peer = (uint32_t)(half ^ 1);
     // my 2 chunks (keys 16*sub .. 16*sub+15) of P slot `half`: chunk stride 2048 B, 16 B per row
     const uint32_t p_local = smem_u32(smem + S2_P + half * P_SLOT_BYTES) + (2 * sub) * (TC_BM / 8) * 128 + row * 16;
-    const uint32_t p_remote = mapa(p_local, peer);
-    const uint32_t pfull_remote = mapa(smem_u32(p_full + half), peer);
+    const bool want_mask = (mask_bits != nullptr) || (nnz != nullptr);
+    const float neg_ref = -ref;
 
     for (int i = 0; i < n_own; ++i) {
       const int s = i & 1;
       const uint32_t ph = (uint32_t)(i >> 1) & 1u;
       const int t = t_begin + 2 * i + half;
       const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
-      mbar_wait(s_full + s, ph);
+      { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
       tc_fence_after();
       float sv[16];
       {
@@ -893,37 +949,53 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       unsigned mk = 0u;
       uint32_t pk[8];
       float psum = 0.f;
+      if (vbits == 0xffffu && !want_mask) {
+        // common case: no dummy key slots in my 16 columns, no mask report requested
 #pragma unroll
-      for (int k = 0; k < 16; k += 2) {
-        float p[2];
+        for (int k = 0; k < 16; k += 2) {
+          float p[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float sc = sv[k + u] * inv_s;               // exact: inv_s is a power of two
-          const float rl = fmaxf((sc - tA) + tB, 0.f);      // relu(S - mu*gamma + beta), dagl.py:256
-          const bool valid = (vbits >> (k + u)) & 1u;
-          const float pe = valid ? ex2_approx((sc * rl) * sm_scale_log2 - ref) : 0.f;   // dummy key slots contribute nothing
-          const bool nb = valid && (rl != 0.f);             // mask_b, dagl.py:257
-          if (nb) mk |= 1u << (k + u);
-          p[u] = nb ? pe : 0.f;                             // numerator: neighbours only
-          if (!nb) psum += pe;                              // denominator: every valid key ...
+          for (int u = 0; u < 2; ++u) {
+            const float sc = sv[k + u] * inv_s;             // exact: inv_s is a power of two
+            const float rl = fmaxf((sc - tA) + tB, 0.f);    // relu(S - mu*gamma + beta), dagl.py:256
+            const float pe = ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref));
+            p[u] = (rl != 0.f) ? pe : 0.f;                  // numerator: neighbours only (mask_b, dagl.py:257)
+            if (rl == 0.f) psum += pe;                      // denominator: every key ...
+          }
+          pk[k / 2] = pack_half2(p[0], p[1]);
+          // ... with the neighbours entering as the fp16 values the tensor core will see, so that the
+          // rounding of a dominant weight cancels between numerator and denominator
+          const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
+          psum += pr.x + pr.y;
         }
-        pk[k / 2] = pack_half2(p[0], p[1]);
-        // ... with the neighbours entering as the fp16 values the tensor core will see, so that the
-        // rounding of a dominant weight cancels between numerator and denominator
-        const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
-        psum += pr.x + pr.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          float p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float sc = sv[k + u] * inv_s;
+            const float rl = fmaxf((sc - tA) + tB, 0.f);
+            const bool valid = (vbits >> (k + u)) & 1u;
+            const float pe = valid ? ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref)) : 0.f;   // dummy key slots contribute nothing
+            const bool nb = valid && (rl != 0.f);
+            if (nb) mk |= 1u << (k + u);
+            p[u] = nb ? pe : 0.f;
+            if (!nb) psum += pe;
+          }
+          pk[k / 2] = pack_half2(p[0], p[1]);
+          const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
+          psum += pr.x + pr.y;
+        }
+        cnt += __popc(mk);
       }
       l_run += psum;
-      cnt += __popc(mk);
       // slot `half` must have been drained by the P.V of BOTH CTAs for my previous tile
-      mbar_wait_cluster(p_free + half, (uint32_t)(i & 1) ^ 1u);
+      { TRACE_T0(); mbar_wait(p_free + half, (uint32_t)(i & 1) ^ 1u); TRACE_ADD(tr_b); }
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-      st_cluster_v4(p_remote, pk[0], pk[1], pk[2], pk[3]);
-      st_cluster_v4(p_remote + 2048, pk[4], pk[5], pk[6], pk[7]);
-      fence_proxy_async_all();                              // generic-proxy writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(p_full + half);
-      mbar_arrive_cluster(pfull_remote);
+      fence_async_smem();                                   // generic-proxy writes -> visible to the async proxy (UMMA, bulk copy)
+      mbar_arrive(p_full + half);                           // local consumers: my P.V and the forwarder warp
 
       if (mask_bits != nullptr && qvalid && mk != 0u) {     // debug path only
         uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
@@ -976,6 +1048,13 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     }
   }
 
+#ifdef DAGL_TC_TRACE
+  if (tr_cta < 1024 && (tid & 31) == 0 && warp <= 2) {
+    long long* o = g_tc_trace[tr_cta] + warp * 4;        // warp 0 producer, 1 mma, 2 softmax
+    o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
+    if (warp == 0) { g_tc_trace[tr_cta][12] = ntiles; g_tc_trace[tr_cta][14] = tr_start; }
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                       // nobody leaves while the peer can still write here
@@ -1080,12 +1159,11 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   if (a.nnz) DAGL_CUDA_OK(cudaMemsetAsync(a.nnz, 0, (size_t)g.B * g.Nq * sizeof(int32_t), st));
 
   {
-    auto kq = pack_tiles_kernel<TC_BM, 0>;
-    const size_t smem = (size_t)TC_BM * ED * 4;
-    DAGL_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kq<<<dim3(tg.nqt, g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, a.Kbar, a.gamma, a.beta, thrA, thrB);
+    auto kq = pack_tiles_kernel<TC_BM, 0, 16>;
+    const size_t smem = (size_t)16 * ED * 4;
+    kq<<<dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, a.Kbar, a.gamma, a.beta, thrA, thrB);
     DAGL_LAUNCH_CHECK();
-    auto kk = pack_tiles_kernel<TC_BN, 1>;
+    auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
     const size_t smem_k = (size_t)TC_BN * ED * 4;
     kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr);
     DAGL_LAUNCH_CHECK();
@@ -1099,16 +1177,17 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
     DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, (size_t)g.B * tg.nqt * TC_BM * 4, st));
     // pre-pass: row maxima of the scores (Qh.Kh only)
-    int pre_split = 148 / (tg.nqt * g.B);
+    const int nqg = (tg.nqt + RM_QT - 1) / RM_QT;
+    int pre_split = 148 / (nqg * g.B);
     if (pre_split < 1) pre_split = 1;
     const int max_split = (tg.NT + RM_TILES - 1) / RM_TILES;
     if (pre_split > max_split) pre_split = max_split;
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-    rowmax_tc_kernel<<<dim3(tg.nqt, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, smax);
+    rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, smax);
     DAGL_LAUNCH_CHECK();
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
     if (int rc = prof_begin(st)) return rc;
-    attend_tc2_kernel<<<grid, TC_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+    attend_tc2_kernel<<<grid, TC2_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
                                                           sm_scale_log2, w.nsplit, Opart, lpart, a.mask_bits, a.nnz);
     DAGL_LAUNCH_CHECK();
     if (int rc = prof_end(st)) return rc;

@@ -20,9 +20,9 @@ dev = torch.device("cuda:0")
 H = W = int(os.environ.get("HW", "256"))
 params = O.init_ce_params(1000)
 x = torch.randn(1, 64, H, W, generator=torch.Generator().manual_seed(2000)).to(dev)
-ce = dagl_b200.CE(in_channels=64, impl="tc"); ce.load_state_dict(params); ce = ce.to(dev).eval()
+ce = dagl_b200.CE(in_channels=64, impl=os.environ.get("IMPL", "tc")); ce.load_state_dict(params); ce = ce.to(dev).eval()
 L = _lib.lib()
-for mode in (0, 1, 2, 3):
+for mode in ((0,) if os.environ.get('IMPL', 'tc') == 'tc' else (0, 1, 2, 3)):
   L.dagl_debug_set_tc_mode(mode)
   print(f"=== dbg mode {mode} (bit0: no S MMAs, bit1: no P.V MMAs) ===")
   with torch.no_grad():
@@ -38,7 +38,7 @@ for mode in (0, 1, 2, 3):
   def per_tile(col): return (b[:, col] / nt)
   print("per tile (cycles), mean over CTAs:")
   print(f"  producer : wait k_empty {per_tile(0).mean():8.0f}  wait t_empty {per_tile(1).mean():8.0f}  total {per_tile(3).mean():8.0f}")
-  print(f"  mma      : wait k_full  {per_tile(4).mean():8.0f}  wait p_full  {per_tile(5).mean():8.0f}  wait t_full {per_tile(6).mean():8.0f}  total {per_tile(7).mean():8.0f}")
-  print(f"  softmax  : wait s_full  {per_tile(8).mean():8.0f}  named bar    {per_tile(9).mean():8.0f}  total {per_tile(11).mean():8.0f}")
+  print(f"  mma      : wait k_full(+s_free) {per_tile(4).mean():8.0f}  wait p_full  {per_tile(5).mean():8.0f}  wait t_full {per_tile(6).mean():8.0f}  total {per_tile(7).mean():8.0f}")
+  print(f"  softmax  : wait s_full  {per_tile(8).mean():8.0f}  named bar / p_free {per_tile(9).mean():8.0f}  total {per_tile(11).mean():8.0f}")
   t0 = b[:, 14].min(); 
   print("kernel span cycles:", (b[:, 14] + b[:, 3]).max() - t0, " CTA total mean", b[:, 3].mean())
