@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256)
 pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsigned* __restrict__ absmax,
                   uint8_t* __restrict__ tiles, unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ Kbar, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  float* __restrict__ thrA, float* __restrict__ thrB) {
+                  float* __restrict__ thrA, float* __restrict__ thrB, float* __restrict__ colsum_partial) {
   extern __shared__ __align__(16) float rows_s[];            // [RPB][196]
   constexpr int BPT = ROWS / RPB;                            // blocks per tile
   const int t = blockIdx.x / BPT, r0 = (blockIdx.x % BPT) * RPB, img = blockIdx.y, tid = threadIdx.x;
@@ -172,6 +172,14 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
       }
       tilemask[(size_t)img * ntile + t] = m;
     }
+    // column sums of this tile's rows for Kbar = mean_k K (dummy slots are zero rows); fixed order -> deterministic
+    if (colsum_partial != nullptr)
+      for (int e = tid; e < ED; e += 256) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < RPB; ++r) sum += rows_s[r * ED + e];
+        colsum_partial[((size_t)img * ntile + t) * ED + e] = sum;
+      }
   } else {
     // per-query threshold terms: mu = Q[q,:] . Kbar (fp64 accumulate), tA = mu*gamma, tB = beta  (dagl.py:256)
     const int lane = tid & 31, warp = tid >> 5;
@@ -1093,7 +1101,7 @@ static int tc_splits(const Geom& g, const TcGeom& tg) {
 }
 
 struct TcWs {
-  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, Om, smax, total;
+  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, Om, smax, colsum, kbar, total;
   int nsplit;
 };
 
@@ -1116,6 +1124,8 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   w.coef = take(rows * 4);
   w.Om = take(merge_fold_scratch_bytes(g));
   w.smax = take((size_t)g.B * tg.nqt * TC_BM * 4);
+  w.colsum = take((size_t)g.B * tg.NT * ED * 4);
+  w.kbar = take((size_t)g.B * ED * 4);
   w.total = off;
   return w;
 }
@@ -1159,13 +1169,23 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   if (a.nnz) DAGL_CUDA_OK(cudaMemsetAsync(a.nnz, 0, (size_t)g.B * g.Nq * sizeof(int32_t), st));
 
   {
-    auto kq = pack_tiles_kernel<TC_BM, 0, 16>;
-    const size_t smem = (size_t)16 * ED * 4;
-    kq<<<dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, a.Kbar, a.gamma, a.beta, thrA, thrB);
-    DAGL_LAUNCH_CHECK();
+    // keys first: the pack kernel also produces the per-tile column sums from which Kbar is formed when the
+    // caller did not supply it (full forward); the query pack needs Kbar for the per-query thresholds.
+    const float* Kbar = a.Kbar;
+    float* colsum = nullptr;
+    if (Kbar == nullptr) colsum = reinterpret_cast<float*>(base + w.colsum);
     auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
     const size_t smem_k = (size_t)TC_BN * ED * 4;
-    kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr);
+    kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr, colsum);
+    DAGL_LAUNCH_CHECK();
+    if (Kbar == nullptr) {
+      float* kb = a.kbar_out ? a.kbar_out : reinterpret_cast<float*>(base + w.kbar);
+      if (int rc = launch_kbar(g, colsum, tg.NT, kb, st)) return rc;
+      Kbar = kb;
+    }
+    auto kq = pack_tiles_kernel<TC_BM, 0, 16>;
+    const size_t smem = (size_t)16 * ED * 4;
+    kq<<<dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thrA, thrB, nullptr);
     DAGL_LAUNCH_CHECK();
     pack_theta_kernel<<<dim3((tg.NP + 255) / 256, g.B), 256, 0, st>>>(g, tg, a.theta, absmax, Thp);
     DAGL_LAUNCH_CHECK();

@@ -141,15 +141,16 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax, AMAX_K, st))) return rc;
     if ((rc = launch_kbar(g, kpart, L.kblocks_simt, Kbar, st))) return rc;
   } else {
-    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, K, kpart, absmax, base + L.embed,
+    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, K, absmax, base + L.embed,
                               L.attend - L.embed, st))) return rc;
-    if ((rc = launch_kbar(g, kpart, L.kblocks_tc, Kbar, st))) return rc;
+    Kbar = nullptr;      // formed inside the tensor-core launcher from the key-pack column sums
   }
 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
+  a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
   return run_attend(g, a, impl, absmax, st);
 }
 }  // namespace dagl
@@ -238,7 +239,7 @@ int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar,
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = theta; a.y = y;
   a.scale = softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
-  a.ws = workspace; a.ws_bytes = workspace_bytes;
+  a.ws = workspace; a.ws_bytes = workspace_bytes; a.kbar_out = nullptr;
   return run_attend(g, a, impl, nullptr, static_cast<cudaStream_t>(stream));
 }
 

@@ -93,18 +93,19 @@ int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* 
 int embed_num_blocks(int npos);
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st);
 
-// tensor-core embeddings (embed_tc.cu): Q, K fp32 + K column-sum partials [B][embed_tc_num_tiles][196]
+// tensor-core embeddings (embed_tc.cu): Q, K fp32
 size_t embed_tc_workspace_bytes(const Geom& g);
 int embed_tc_num_tiles(const Geom& g);
 int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                    const float* fc2_b, float* Q, float* K, float* colsum_partial, unsigned* absmax, void* ws,
-                    size_t ws_bytes, cudaStream_t st);
+                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
   const float* theta; float* y; float scale;
   uint32_t* mask_bits; int32_t* nnz;
   void* ws; size_t ws_bytes;
+  float* kbar_out;     // optional: where a launcher that forms Kbar itself (Kbar == nullptr) also stores it
 };
 size_t merge_fold_scratch_bytes(const Geom& g);      // Omerged [B][Nq][784]
 int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,

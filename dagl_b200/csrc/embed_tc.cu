@@ -34,10 +34,11 @@ constexpr int EB_WSTAGES = 3;
 constexpr int EB_SM_G = 0;
 constexpr int EB_SM_W = EB_G_BYTES;                                  // 64512 = 63 * 1024
 constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WTAP_BYTES;      // 104448
-constexpr int EB_SM_RED = EB_SM_BAR + 128;                           // [4 warps][208] floats
-constexpr int EB_SM_TOTAL = EB_SM_RED + 4 * EB_N * 4;
+constexpr int EB_SM_TOTAL = EB_SM_BAR + 128;
 constexpr int EB_THREADS = 192;
-constexpr int EB_TMEM_COLS = 512;                  // main (hi.hi) accumulator at column 0, cross-term accumulator at 256
+constexpr int EB_TMEM_COLS = 256;                  // per CTA: main (hi.hi) accumulator at column 0, cross-term accumulator at 128
+constexpr int EB_N0 = 112, EB_N1 = EB_N - EB_N0;   // the 208 outputs are split over two CTAs (N = 112 / 96): 2 CTAs per SM overlap
+                                                   // the halo load, MMA and epilogue phases of different tiles
 static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
 
 struct EmbGeom {
@@ -133,11 +134,11 @@ pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* _
 
 // mode 0: keys (every pixel) -> out[y*W+x][196], column sums for Kbar, absmax slot 1
 // mode 1: queries (pixels (4qy+oy, 4qx+ox)) -> out[qy*nqx+qx][196], absmax slot 0
-__global__ void __launch_bounds__(EB_THREADS, 1)
+__global__ void __launch_bounds__(EB_THREADS, 2)
 embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __restrict__ ghi,
                 const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
                 const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
-                float* __restrict__ out, float* __restrict__ colsum_partial, unsigned* __restrict__ absmax_out) {
+                float* __restrict__ out, unsigned* __restrict__ absmax_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
   uint64_t* g_full = bars + 0;
@@ -145,11 +146,11 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
   uint64_t* w_empty = bars + 4;                // [3]
   uint64_t* d_full = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  float* red = reinterpret_cast<float*>(smem + EB_SM_RED);
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int img = blockIdx.y, tile = blockIdx.x;
+  const int img = blockIdx.z, tile = blockIdx.x, eh = blockIdx.y;          // eh: which part of the 208 outputs
+  const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
   const int p0 = tile * EB_M;
 
   // query mode: skip tiles whose rows hold no query centre
@@ -192,7 +193,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = instr_desc(EB_M, EB_N, FMT_F16, FMT_F16, 0, 0);
+      const uint32_t idesc = instr_desc(EB_M, (uint32_t)ncols, FMT_F16, FMT_F16, 0, 0);
       mbar_wait(g_full, 0);
       tc_fence_after();
       const uint32_t gbase = smem_u32(smem + EB_SM_G);
@@ -209,15 +210,15 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
                                ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
         const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
                                ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WTAP_BYTES);
+        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WTAP_BYTES) + (e0 / 8) * 128;   // rows e0.. of the packed tap
         const uint64_t db_hi = smem_desc(w_hi, (EB_N / 8) * 128, 128);
         const uint64_t db_lo = smem_desc(w_hi + EB_WPART_BYTES, (EB_N / 8) * 128, 128);
         // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
         // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
         // the epilogue adds the two in round-to-nearest fp32.
         mma_f16_ss_a_fill(tbase, da_hi, db_hi, idesc, t > 0);                // Gh.Wh
-        mma_f16_ss_a_lastuse(tbase + 256, da_hi, db_lo, idesc, t > 0);       // Gh.Wl
-        mma_f16_ss(tbase + 256, da_lo, db_hi, idesc, 1);                     // Gl.Wh
+        mma_f16_ss_a_lastuse(tbase + 128, da_hi, db_lo, idesc, t > 0);       // Gh.Wl
+        mma_f16_ss(tbase + 128, da_lo, db_hi, idesc, 1);                     // Gl.Wh
         mma_commit(w_empty + s);
       }
       mma_commit(d_full);
@@ -244,43 +245,29 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
     mbar_wait(d_full, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c16 = 0; c16 < EB_N / 16; ++c16) {
+    for (int c16 = 0; c16 < ncols / 16; ++c16) {
       uint32_t v[16], vc[16];
       tmem_ld16(trow + c16 * 16, v);
-      tmem_ld16(trow + 256 + c16 * 16, vc);
+      tmem_ld16(trow + 128 + c16 * 16, vc);
       tmem_wait_ld();
+      const int eb = e0 + c16 * 16;
       float f[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int e = c16 * 16 + i;
+        const int e = eb + i;
         const float b = (e < ED) ? __ldg(bias + e) : 0.f;
         f[i] = valid ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
         vmax = fmaxf(vmax, f[i]);
       }
       if (valid) {
-        float4* dst = reinterpret_cast<float4*>(out + orow * ED + c16 * 16);
-        const int n4 = (c16 == EB_N / 16 - 1) ? 1 : 4;          // 196 = 12*16 + 4
+        float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
+        const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
         for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      }
-      if (colsum_partial != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float sum = f[i];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == i) red[quad * EB_N + c16 * 16 + i] = sum;
-        }
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if (lane == 0) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
-    if (colsum_partial != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int e = tid - 64; e < ED; e += 128)
-        colsum_partial[((size_t)img * gridDim.x + tile) * ED + e] =
-            (red[e] + red[EB_N + e]) + (red[2 * EB_N + e] + red[3 * EB_N + e]);
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -296,11 +283,11 @@ size_t embed_tc_workspace_bytes(const Geom& g) {
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
-// Computes Q [B][Nq][196], K [B][Nk][196] (fp32), K column-sum partials [B][ntile][196] and the maxima
-// of Q and K into absmax[B][4] (slots 0, 1); absmax slot 3 (max |G|) must already be filled.
+// Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
+// absmax slot 3 (max |G|) must already be filled.
 int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                    const float* fc2_b, float* Q, float* K, float* colsum_partial, unsigned* absmax, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   const EmbGeom eg = emb_geom(g);
   if (ws_bytes < embed_tc_workspace_bytes(g)) {
     call_state().err = "embed (tc) workspace too small";
@@ -327,12 +314,10 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
 
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   const int oy = PADK - g.qpad_top, ox = PADK - g.qpad_left;
-  dim3 grid(eg.ntile, g.B);
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q,
-                                                        nullptr, absmax);
+  dim3 grid(eg.ntile, 2, g.B);
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q, absmax);
   DAGL_LAUNCH_CHECK();
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K,
-                                                        colsum_partial, absmax);
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K, absmax);
   DAGL_LAUNCH_CHECK();
   return 0;
 }

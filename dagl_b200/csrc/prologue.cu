@@ -14,7 +14,6 @@ namespace dagl {
 // [ci][tap][16] so each tap costs four broadcast LDS.128.
 // ---------------------------------------------------------------------------
 constexpr int FM_THREADS = 128;
-constexpr int FM_PX = 2;            // horizontally adjacent pixels per thread (halves the weight LDS per FMA)
 
 __global__ void __launch_bounds__(FM_THREADS)
 feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict__ g_w,
@@ -36,75 +35,55 @@ feature_maps_kernel(Geom g, const float* __restrict__ b, const float* __restrict
   __syncthreads();
 
   const int img = blockIdx.y;
-  const int wpairs = (g.W + FM_PX - 1) / FM_PX;
-  const int pp = blockIdx.x * FM_THREADS + threadIdx.x;       // pixel-pair index
-  const bool live = pp < g.H * wpairs;
-  const int y = pp / wpairs, x0 = (pp % wpairs) * FM_PX;
+  const int p = blockIdx.x * FM_THREADS + threadIdx.x;
+  const bool live = p < g.Nk;
+  const int y = p / g.W, x = p % g.W;
   const float* bi = b + (size_t)img * C * g.Nk;
 
-  float ag[FM_PX][CI], at[FM_PX][CI];
+  float ag[CI], at[CI];
 #pragma unroll
-  for (int px = 0; px < FM_PX; ++px)
-#pragma unroll
-    for (int c = 0; c < CI; ++c) { ag[px][c] = g_b[c]; at[px][c] = th_b[c]; }
+  for (int c = 0; c < CI; ++c) { ag[c] = g_b[c]; at[c] = th_b[c]; }
 
   for (int ci = 0; live && ci < C; ++ci) {
     const float* bc = bi + (size_t)ci * g.Nk;
-    float v[3][FM_PX + 2];                                     // rows y-1..y+1, cols x0-1..x0+FM_PX
+    float v[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yy = y + r - 1;
-#pragma unroll
-      for (int cc = 0; cc < FM_PX + 2; ++cc) {
-        const int xx = x0 + cc - 1;
-        v[r][cc] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(bc + yy * g.W + xx) : 0.f;
-      }
+    for (int t = 0; t < 9; ++t) {
+      int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      v[t] = (yy >= 0 && yy < g.H && xx >= 0 && xx < g.W) ? __ldg(bc + yy * g.W + xx) : 0.f;
     }
     const float4* w4 = reinterpret_cast<const float4*>(gw_s + ci * 9 * CI);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 w = w4[t * 4 + j];
-#pragma unroll
-        for (int px = 0; px < FM_PX; ++px) {
-          const float a = v[t / 3][t % 3 + px];
-          ag[px][4 * j + 0] = fmaf(a, w.x, ag[px][4 * j + 0]);
-          ag[px][4 * j + 1] = fmaf(a, w.y, ag[px][4 * j + 1]);
-          ag[px][4 * j + 2] = fmaf(a, w.z, ag[px][4 * j + 2]);
-          ag[px][4 * j + 3] = fmaf(a, w.w, ag[px][4 * j + 3]);
-        }
+        float4 w = w4[t * 4 + j];
+        ag[4 * j + 0] = fmaf(v[t], w.x, ag[4 * j + 0]);
+        ag[4 * j + 1] = fmaf(v[t], w.y, ag[4 * j + 1]);
+        ag[4 * j + 2] = fmaf(v[t], w.z, ag[4 * j + 2]);
+        ag[4 * j + 3] = fmaf(v[t], w.w, ag[4 * j + 3]);
       }
     }
     const float4* t4 = reinterpret_cast<const float4*>(tw_s + ci * CI);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 w = t4[j];
-#pragma unroll
-      for (int px = 0; px < FM_PX; ++px) {
-        const float a = v[1][1 + px];
-        at[px][4 * j + 0] = fmaf(a, w.x, at[px][4 * j + 0]);
-        at[px][4 * j + 1] = fmaf(a, w.y, at[px][4 * j + 1]);
-        at[px][4 * j + 2] = fmaf(a, w.z, at[px][4 * j + 2]);
-        at[px][4 * j + 3] = fmaf(a, w.w, at[px][4 * j + 3]);
-      }
+      float4 w = t4[j];
+      at[4 * j + 0] = fmaf(v[4], w.x, at[4 * j + 0]);
+      at[4 * j + 1] = fmaf(v[4], w.y, at[4 * j + 1]);
+      at[4 * j + 2] = fmaf(v[4], w.z, at[4 * j + 2]);
+      at[4 * j + 3] = fmaf(v[4], w.w, at[4 * j + 3]);
     }
   }
   float tmax = 0.f, gmax = 0.f;
   if (live) {
+    float* Go = G + (size_t)img * CI * g.Nk + p;
+    float* To = Th + (size_t)img * CI * g.Nk + p;
 #pragma unroll
-    for (int px = 0; px < FM_PX; ++px) {
-      if (x0 + px >= g.W) continue;
-      const size_t p = (size_t)y * g.W + x0 + px;
-      float* Go = G + (size_t)img * CI * g.Nk + p;
-      float* To = Th + (size_t)img * CI * g.Nk + p;
-#pragma unroll
-      for (int c = 0; c < CI; ++c) {
-        Go[(size_t)c * g.Nk] = ag[px][c];
-        To[(size_t)c * g.Nk] = at[px][c];
-        tmax = fmaxf(tmax, fabsf(at[px][c]));
-        gmax = fmaxf(gmax, fabsf(ag[px][c]));
-      }
+    for (int c = 0; c < CI; ++c) {
+      Go[(size_t)c * g.Nk] = ag[c];
+      To[(size_t)c * g.Nk] = at[c];
+      tmax = fmaxf(tmax, fabsf(at[c]));
+      gmax = fmaxf(gmax, fabsf(ag[c]));
     }
   }
   if (absmax != nullptr) {
@@ -125,8 +104,7 @@ int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const f
   size_t smem = (size_t)(g.C * 9 * CI + g.C * CI) * sizeof(float);
   if (smem > 48 * 1024)
     DAGL_CUDA_OK(cudaFuncSetAttribute(feature_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int npairs = g.H * ((g.W + FM_PX - 1) / FM_PX);
-  dim3 grid((npairs + FM_THREADS - 1) / FM_THREADS, g.B);
+  dim3 grid((g.Nk + FM_THREADS - 1) / FM_THREADS, g.B);
   feature_maps_kernel<<<grid, FM_THREADS, smem, st>>>(g, b, g_w, g_b, th_w, th_b, G, Th, absmax);
   DAGL_LAUNCH_CHECK();
   return 0;
@@ -149,6 +127,7 @@ gamma_beta_kernel(Geom g, const float* __restrict__ b, const float* __restrict__
   const float* bi = b + (size_t)img * g.C * g.Nk;
   float a0 = 0.f, a1 = 0.f;
   const int n = g.C * KK;
+#pragma unroll 7
   for (int i = lane; i < n; i += 32) {
     int ci = i / KK, t = i % KK;
     int yy = y0 + t / KS, xx = x0 + t % KS;
@@ -297,28 +276,31 @@ int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* 
   return 0;
 }
 
-// Kbar[e] = (1/Nk) * sum over CTAs of the partial column sums; fixed summation order (8 interleaved
+// Kbar[e] = (1/Nk) * sum over CTAs of the partial column sums; fixed summation order (32 interleaved
 // fp64 chains per column, then a fixed tree), so the result is deterministic.  grid = (7, B): 32 columns
-// per block.
-__global__ void __launch_bounds__(256) kbar_kernel(const float* __restrict__ partial, int nblk, int Nk, float* __restrict__ Kbar) {
-  __shared__ double acc_s[8][32];
+// per block, 1024 threads.
+__global__ void __launch_bounds__(1024) kbar_kernel(const float* __restrict__ partial, int nblk, int Nk, float* __restrict__ Kbar) {
+  __shared__ double acc_s[32][33];
   const int img = blockIdx.y;
   const int chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 32 + lane;
   double s = 0.0;
-  if (e < ED)
-    for (int k = chain; k < nblk; k += 8) s += (double)__ldg(partial + ((size_t)img * nblk + k) * ED + e);
+  if (e < ED) {
+#pragma unroll 4
+    for (int k = chain; k < nblk; k += 32) s += (double)__ldg(partial + ((size_t)img * nblk + k) * ED + e);
+  }
   acc_s[chain][lane] = s;
   __syncthreads();
   if (chain == 0 && e < ED) {
-    const double t = ((acc_s[0][lane] + acc_s[1][lane]) + (acc_s[2][lane] + acc_s[3][lane])) +
-                     ((acc_s[4][lane] + acc_s[5][lane]) + (acc_s[6][lane] + acc_s[7][lane]));
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) t += acc_s[c][lane];
     Kbar[(size_t)img * ED + e] = (float)(t / (double)Nk);
   }
 }
 
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st) {
-  kbar_kernel<<<dim3((ED + 31) / 32, g.B), 256, 0, st>>>(colsum_partial, nblk, g.Nk, Kbar);
+  kbar_kernel<<<dim3((ED + 31) / 32, g.B), 1024, 0, st>>>(colsum_partial, nblk, g.Nk, Kbar);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
