@@ -16,6 +16,7 @@ EXPORTS = [
     "dagl_ce_forward_debug_f32", "dagl_ce_host_staging_bytes", "dagl_ce_forward_host_f32",
     "dagl_graph_attend_workspace_bytes", "dagl_graph_attend_f32", "dagl_ce_workspace_view",
     "dagl_last_impl", "dagl_last_launch_count", "dagl_profile_enable", "dagl_profile_read",
+    "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
 ]
 
 
@@ -61,6 +62,12 @@ def lib() -> C.CDLL:
     L.dagl_graph_attend_f32.argtypes = [vp] * 7 + [i32, i32, i32, C.c_float, vp, sz, i32, vp, vp, vp]
     L.dagl_ce_workspace_view.restype = vp
     L.dagl_ce_workspace_view.argtypes = [vp, i32, i32, i32, i32, i32]
+    L.dagl_ce_num_query_tiles.restype = i32
+    L.dagl_ce_num_query_tiles.argtypes = [i32, i32]
+    L.dagl_ce_forward_rows_f32.restype = i32
+    L.dagl_ce_forward_rows_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.dagl_ce_fold_rows_f32.restype = i32
+    L.dagl_ce_fold_rows_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.dagl_profile_enable.restype = i32
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32

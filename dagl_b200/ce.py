@@ -171,6 +171,48 @@ class CE(nn.Module):
             out[name] = ws[off:off + 4 * n].view(torch.float32).view(*shp).clone()
         return out
 
+    def forward_query_sharded(self, b: torch.Tensor, group=None) -> torch.Tensor:
+        """Single-image (or small-batch) multi-GPU forward: every rank holds the same input ``b``, runs the cheap
+        prologue redundantly and the fused graph stage for its share of the 128-query tiles only; the merged
+        aggregation rows are exchanged with ONE all-gather and every rank folds the full result
+        (SURVEY §8e scheme 3: rows of the score matrix are independent given all keys).  Without an
+        initialised process group this is ``forward``."""
+        import torch.distributed as dist
+        from . import parallel
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.forward(b)
+        self._check_input(b)
+        if not b.is_cuda:
+            raise RuntimeError("dagl_b200.CE has no CPU path")
+        L = _lib.lib()
+        b = b.contiguous()
+        B, Cc, H, W = b.shape
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nqt = L.dagl_ce_num_query_tiles(H, W)
+        nq = ((H + 3) // 4) * ((W + 3) // 4)
+        tpr = (nqt + world - 1) // world                      # tiles per rank (last ranks may own fewer / none)
+        t0, t1 = min(nqt, rank * tpr), min(nqt, (rank + 1) * tpr)
+        with torch.cuda.device(b.device):
+            rows = torch.zeros(B, nqt * 128, 784, dtype=torch.float32, device=b.device)
+            stream = torch.cuda.current_stream(b.device).cuda_stream
+            if t1 > t0:
+                ws = _workspace(b.device, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+                w, keep = self._weights(b.device)
+                # the library writes rows [B][Nq][784]; use a view with the true row count, then pad to tiles
+                rows_nq = torch.empty(B, nq, 784, dtype=torch.float32, device=b.device)
+                rc = L.dagl_ce_forward_rows_f32(C.byref(w), b.data_ptr(), rows_nq.data_ptr(), B, H, W, t0, t1,
+                                                ws.data_ptr(), ws.numel(), stream)
+                _lib.check(rc, "dagl_ce_forward_rows_f32")
+                self.last_impl = L.dagl_last_impl().decode()
+                self.last_launches = L.dagl_last_launch_count()
+                q0, q1 = t0 * 128, min(nq, t1 * 128)
+                rows[:, q0:q1] = rows_nq[:, q0:q1]
+            full = parallel.gather_query_rows(rows, tpr * 128, nq, group=group)     # [B, Nq, 784] on every rank
+            y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
+            rc = L.dagl_ce_fold_rows_f32(full.data_ptr(), y.data_ptr(), B, H, W, stream)
+            _lib.check(rc, "dagl_ce_fold_rows_f32")
+        return y
+
     def forward_host(self, b_host: torch.Tensor, y_host: Optional[torch.Tensor] = None,
                      device: Optional[torch.device] = None, sync: bool = True) -> torch.Tensor:
         """Host-buffer entry (``dagl_ce_forward_host_f32``): ``b_host`` is a CPU

@@ -593,7 +593,7 @@ static_assert(RM_SM_K % 1024 == 0, "pre-pass smem alignment");
 // The pre-pass is bound by the L2 -> SM traffic of the K tiles, so a CTA serves two query tiles per K fetch.
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
-                 unsigned* __restrict__ smax) {
+                 int qt_base, int qt_end, unsigned* __restrict__ smax) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
   uint64_t* q_full = bars + 0;
@@ -604,8 +604,8 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int qt0 = blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
-  const int nq_here = min(RM_QT, tg.nqt - qt0);
+  const int qt0 = qt_base + blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
+  const int nq_here = min(RM_QT, qt_end - qt0);
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int nsteps = (t_end - t_begin + RM_TILES - 1) / RM_TILES;
@@ -722,7 +722,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ thrA, const float* __restrict__ thrB,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
-                  int nsplit, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
+                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_BAR);
@@ -741,7 +741,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const int img = blockIdx.z, split = blockIdx.y;
-  const int qt = blockIdx.x >> 1;
+  const int qt = qt_base + (blockIdx.x >> 1);
   const int half = (int)cluster_ctarank();                  // == blockIdx.x & 1
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
@@ -1070,10 +1070,12 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 }
 
 // coef[b][s][q] = 1 / sum_{s,h} l   (fixed-reference partials merge by plain sums)
-__global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, const float* __restrict__ lpart, float* __restrict__ coef) {
+__global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int q_begin, int q_end, const float* __restrict__ lpart,
+                                        float* __restrict__ coef) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Nq) return;
   const int img = i / Nq, q = i % Nq;
+  if (q < q_begin || q >= q_end) return;
   float L = 0.f;
   for (int s = 0; s < nsplit; ++s)
     for (int h = 0; h < 2; ++h) L += lpart[(((size_t)img * nsplit + s) * 2 + h) * Nq + q];
@@ -1086,8 +1088,8 @@ __global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, const float* 
 // ---------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int tc_splits(const Geom& g, const TcGeom& tg) {
-  const long long base = (long long)g.B * tg.nqt * 2;
+static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range) {
+  const long long base = (long long)g.B * nqt_range * 2;
   const int smax = tg.NT < 32 ? tg.NT : 32;
   int best = 1;
   double best_cost = 1e30;
@@ -1107,7 +1109,11 @@ struct TcWs {
 
 static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   TcWs w;
-  w.nsplit = tc_splits(g, tg);
+  // key-split factor the workspace is sized for: the larger of the full launch and an 8-way query-sharded launch
+  {
+    const int full = tc_splits(g, tg, tg.nqt), shard = tc_splits(g, tg, tg.nqt >= 8 ? tg.nqt / 8 : 1);
+    w.nsplit = full > shard ? full : shard;
+  }
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
   w.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
@@ -1134,7 +1140,21 @@ size_t attend_tc_workspace_bytes(const Geom& g) { return tc_ws(g, tc_geom(g)).to
 
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, int variant, cudaStream_t st) {
   const TcGeom tg = tc_geom(g);
-  const TcWs w = tc_ws(g, tg);
+  TcWs w = tc_ws(g, tg);
+  const int qt_begin = a.qt_begin > 0 ? a.qt_begin : 0;
+  const int qt_end = (a.qt_end > 0 && a.qt_end < tg.nqt) ? a.qt_end : tg.nqt;
+  if (qt_begin >= qt_end) {
+    call_state().err = "empty query-tile range";
+    return -1;
+  }
+  if ((qt_begin != 0 || qt_end != tg.nqt || a.rows_out != nullptr) && variant != 2) {
+    call_state().err = "query-tile ranges / row output need the clustered tensor-core kernel (impl tc)";
+    return -2;
+  }
+  {
+    const int want = tc_splits(g, tg, qt_end - qt_begin);
+    if (want < w.nsplit) w.nsplit = want;           // never more splits than the workspace was sized for
+  }
   if (a.ws_bytes < w.total) {
     call_state().err = "attend (tc) workspace too small";
     return -3;
@@ -1192,29 +1212,34 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   }
 
   const float sm_scale_log2 = a.scale * 1.4426950408889634f;
-  dim3 grid(tg.nqt * 2, w.nsplit, g.B);
+  dim3 grid((qt_end - qt_begin) * 2, w.nsplit, g.B);
   if (variant == 2) {
     unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
     DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, (size_t)g.B * tg.nqt * TC_BM * 4, st));
     // pre-pass: row maxima of the scores (Qh.Kh only)
-    const int nqg = (tg.nqt + RM_QT - 1) / RM_QT;
+    const int nqg = (qt_end - qt_begin + RM_QT - 1) / RM_QT;
     int pre_split = 148 / (nqg * g.B);
     if (pre_split < 1) pre_split = 1;
     const int max_split = (tg.NT + RM_TILES - 1) / RM_TILES;
     if (pre_split > max_split) pre_split = max_split;
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-    rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, smax);
+    rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, qt_begin, qt_end, smax);
     DAGL_LAUNCH_CHECK();
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
     if (int rc = prof_begin(st)) return rc;
     attend_tc2_kernel<<<grid, TC2_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
-                                                          sm_scale_log2, w.nsplit, Opart, lpart, a.mask_bits, a.nnz);
+                                                          sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
+                                                          a.nnz);
     DAGL_LAUNCH_CHECK();
     if (int rc = prof_end(st)) return rc;
+    const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
     const int nq_total = g.B * g.Nq;
-    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, lpart, coef);
+    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, q_begin, q_end, lpart, coef);
     DAGL_LAUNCH_CHECK();
-    return launch_rows_fold(g, w.nsplit, Opart, coef, Om, a.y, /*shift_major=*/1, st);
+    if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
+      return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
+    if (int rc = launch_merge_rows(g, w.nsplit, 0, g.Nq, Opart, coef, Om, st)) return rc;
+    return launch_fold_rows(g, Om, a.y, /*shift_major=*/1, st);
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   if (int rc = prof_begin(st)) return rc;

@@ -105,14 +105,15 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
 }
 
 static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B, int H, int W, void* ws,
-                        size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz) {
+                        size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz,
+                        float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0) {
   call_state().launches = 0;
   call_state().impl = "none";
   int rc = check_weights(w);
   if (rc) return rc;
   rc = check_shape(B, H, W);
   if (rc) return rc;
-  if (!b || !y || !ws) {
+  if (!b || (!y && !rows_out) || !ws) {
     call_state().err = "null buffer";
     return DAGL_ERR_INVALID_ARG;
   }
@@ -151,6 +152,7 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
   a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
+  a.rows_out = rows_out; a.qt_begin = qt_begin; a.qt_end = qt_end;
   return run_attend(g, a, impl, absmax, st);
 }
 }  // namespace dagl
@@ -214,6 +216,34 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
   if (rc) return rc;
   DAGL_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, y_bytes, cudaMemcpyDeviceToHost, st));
   return 0;
+}
+
+int32_t dagl_ce_num_query_tiles(int32_t H, int32_t W) {
+  if (H <= 0 || W <= 0) return 0;
+  const Geom g = make_geom(1, 64, H, W);
+  return (g.Nq + 127) / 128;
+}
+
+int32_t dagl_ce_forward_rows_f32(const DaglCEWeights* w, const float* b, float* rows, int32_t B, int32_t H, int32_t W,
+                                 int32_t q_tile_begin, int32_t q_tile_end, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  if (q_tile_begin < 0 || q_tile_end <= q_tile_begin || q_tile_end > dagl_ce_num_query_tiles(H, W)) {
+    call_state().err = "bad query-tile range";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  return forward_impl(w, b, nullptr, B, H, W, workspace, workspace_bytes, DAGL_IMPL_TC, static_cast<cudaStream_t>(stream),
+                      nullptr, nullptr, rows, q_tile_begin, q_tile_end);
+}
+
+int32_t dagl_ce_fold_rows_f32(const float* rows, float* y, int32_t B, int32_t H, int32_t W, void* stream) {
+  call_state().launches = 0;
+  int rc = check_shape(B, H, W);
+  if (rc) return rc;
+  if (!rows || !y) {
+    call_state().err = "null buffer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  return launch_fold_rows(make_geom(B, 64, H, W), rows, y, /*shift_major=*/1, static_cast<cudaStream_t>(stream));
 }
 
 size_t dagl_graph_attend_workspace_bytes(int32_t B, int32_t H, int32_t W) {

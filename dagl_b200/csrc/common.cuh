@@ -106,10 +106,17 @@ struct AttendArgs {
   uint32_t* mask_bits; int32_t* nnz;
   void* ws; size_t ws_bytes;
   float* kbar_out;     // optional: where a launcher that forms Kbar itself (Kbar == nullptr) also stores it
+  // query sharding (multi-GPU): only the 128-query tiles [qt_begin, qt_end) are computed (0 / <=0: all); when
+  // rows_out is set the merged rows [B][Nq][49][16] are written there and the fold is left to the caller
+  int qt_begin = 0, qt_end = 0;
+  float* rows_out = nullptr;
 };
 size_t merge_fold_scratch_bytes(const Geom& g);      // Omerged [B][Nq][784]
 int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
                      int shift_major, cudaStream_t st);
+int launch_merge_rows(const Geom& g, int nsplit, int q_begin, int q_end, const float* Opart, const float* coef,
+                      float* Omerged, cudaStream_t st);
+int launch_fold_rows(const Geom& g, const float* Omerged, float* y, int shift_major, cudaStream_t st);
 int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
                       float* coef, float* Omerged, float* y, int log2_units, int shift_major, float out_scale,
                       cudaStream_t st);

@@ -31,14 +31,16 @@ __global__ void merge_coef_kernel(int B, int Nq, int nsplit, int log2_units, flo
 
 // Omerged[q][d] = sum_s coef[s][q] * Opart[s][q][d]   (streaming, float4)
 __global__ void __launch_bounds__(256)
-merge_rows_kernel(int B, int Nq, int nsplit, const float* __restrict__ Opart, const float* __restrict__ coef,
-                  float* __restrict__ Om) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over B*Nq*(VD/4)
-  const size_t total = (size_t)B * Nq * (VD / 4);
+merge_rows_kernel(int B, int Nq, int nsplit, int q_begin, int q_end, const float* __restrict__ Opart,
+                  const float* __restrict__ coef, float* __restrict__ Om) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // over B*(q_end-q_begin)*(VD/4)
+  const int nq = q_end - q_begin;
+  const size_t total = (size_t)B * nq * (VD / 4);
   if (i >= total) return;
   const int d4 = (int)(i % (VD / 4));
-  const size_t bq = i / (VD / 4);
-  const int img = (int)(bq / Nq), q = (int)(bq % Nq);
+  const size_t bqr = i / (VD / 4);
+  const int img = (int)(bqr / nq), q = q_begin + (int)(bqr % nq);
+  const size_t bq = (size_t)img * Nq + q;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < nsplit; ++s) {
     const size_t j = ((size_t)img * nsplit + s) * Nq + q;
@@ -73,16 +75,28 @@ __global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ O
 
 size_t merge_fold_scratch_bytes(const Geom& g) { return (size_t)g.B * g.Nq * VD * sizeof(float); }
 
-// merge (given coefficients) + fold
-int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
-                     int shift_major, cudaStream_t st) {
-  const size_t n4 = (size_t)g.B * g.Nq * (VD / 4);
-  merge_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(g.B, g.Nq, nsplit, Opart, coef, Omerged);
+// Omerged rows [q_begin, q_end) of every image <- sum over splits of coef * partial
+int launch_merge_rows(const Geom& g, int nsplit, int q_begin, int q_end, const float* Opart, const float* coef,
+                      float* Omerged, cudaStream_t st) {
+  const size_t n4 = (size_t)g.B * (q_end - q_begin) * (VD / 4);
+  merge_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(g.B, g.Nq, nsplit, q_begin, q_end, Opart, coef, Omerged);
   DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = fold(rows) / coverage count
+int launch_fold_rows(const Geom& g, const float* Omerged, float* y, int shift_major, cudaStream_t st) {
   const int total = g.B * CI * g.Nk;
   fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, shift_major, Omerged, y);
   DAGL_LAUNCH_CHECK();
   return 0;
+}
+
+// merge (given coefficients) + fold
+int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
+                     int shift_major, cudaStream_t st) {
+  if (int rc = launch_merge_rows(g, nsplit, 0, g.Nq, Opart, coef, Omerged, st)) return rc;
+  return launch_fold_rows(g, Omerged, y, shift_major, st);
 }
 
 int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,

@@ -70,3 +70,21 @@ def forward_sharded(fn, batch: torch.Tensor, gather: bool = True) -> torch.Tenso
         r0, r1 = partition(batch.shape[0], world, r)
         parts.append(outs[r][: r1 - r0])
     return torch.cat(parts, dim=0)
+
+
+def gather_query_rows(rows: torch.Tensor, rows_per_rank: int, n_rows: int, group=None) -> torch.Tensor:
+    """All-gather of per-rank query rows for single-image query sharding.
+
+    ``rows`` is [B, world*rows_per_rank (>= n_rows), D] on every rank with only this rank's slice
+    [rank*rows_per_rank, (rank+1)*rows_per_rank) filled.  Returns the assembled [B, n_rows, D] tensor (the same
+    on every rank).  One collective: ``all_gather_into_tensor`` of the owned slices."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, _, D = rows.shape
+    if rows.shape[1] < world * rows_per_rank:
+        pad = torch.zeros(B, world * rows_per_rank - rows.shape[1], D, dtype=rows.dtype, device=rows.device)
+        rows = torch.cat([rows, pad], dim=1)
+    mine = rows[:, rank * rows_per_rank:(rank + 1) * rows_per_rank].contiguous()          # [B, rpr, D]
+    out = torch.empty((world * B, rows_per_rank, D), dtype=rows.dtype, device=rows.device)   # ranks concatenated on dim 0
+    dist.all_gather_into_tensor(out, mine, group=group)
+    full = out.view(world, B, rows_per_rank, D).permute(1, 0, 2, 3).reshape(B, world * rows_per_rank, D)
+    return full[:, :n_rows].contiguous()

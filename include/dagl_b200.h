@@ -99,6 +99,19 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
                                  void* workspace, size_t workspace_bytes,
                                  int32_t impl, void* stream);
 
+/* Query sharding across GPUs (one image, several ranks; SURVEY §8e scheme 3).  Rows of the score matrix are
+ * independent given all keys, so each rank runs the (cheap) prologue redundantly and the fused graph stage only
+ * for the 128-query tiles [q_tile_begin, q_tile_end); it writes the merged, normalised aggregation rows
+ *   rows [B][Nq][49 shifts (dy*7+dx)][16 channels]      (dagl.py:263-264, before the fold)
+ * for its queries (other rows untouched).  After the ranks exchange their rows (one all-gather),
+ * dagl_ce_fold_rows_f32 performs the fold + coverage normalisation (dagl.py:265-272).                         */
+int32_t dagl_ce_num_query_tiles(int32_t H, int32_t W);
+int32_t dagl_ce_forward_rows_f32(const DaglCEWeights* w, const float* b, float* rows,
+                                 int32_t B, int32_t H, int32_t W,
+                                 int32_t q_tile_begin, int32_t q_tile_end,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int32_t dagl_ce_fold_rows_f32(const float* rows, float* y, int32_t B, int32_t H, int32_t W, void* stream);
+
 /* Split entry for the fused graph stage alone (dagl.py:250-272), taking the
  * embeddings as inputs:
  *   Q [B][Nq][196], K [B][Nk][196] (post-ReLU), Kbar [B][196] = mean_k K,

@@ -298,3 +298,49 @@ def test_auto_dispatch_uses_tensor_core_kernel(dev, rand_weights):
     with torch.no_grad():
         ce(torch.zeros(1, 64, 32, 32, device=dev))
     assert ce.last_impl == "tc"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", [(1, 64, 4, 4), (1, 64, 3, 11), (2, 64, 8, 5)])
+def test_tiny_inputs(dev, rand_weights, impl, shape):
+    """Inputs smaller than one 7x7 patch / one query stride (everything is padding)."""
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(*shape, generator=gen)
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y, bits, nnz = ce.forward_debug(x.to(dev))
+    yref, aux = O.ce_forward(rand_weights, x, return_aux=True)
+    assert rel_err(y.cpu(), yref) <= REL_TOL
+    assert_mask_parity(bits, aux)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_other_channel_count(dev, impl):
+    """in_channels = 32 (the reference CE takes in_channels as a constructor argument)."""
+    p = O.init_ce_params(77, in_channels=32)
+    gen = torch.Generator().manual_seed(32)
+    x = torch.randn(1, 32, 26, 22, generator=gen)
+    ce = make_ce(p, dev, impl)
+    with torch.no_grad():
+        y = ce(x.to(dev))
+    assert rel_err(y.cpu(), O.ce_forward(p, x)) <= REL_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_other_softmax_scale(dev, rand_weights, impl):
+    import dagl_b200
+    gen = torch.Generator().manual_seed(33)
+    x = torch.randn(1, 64, 24, 28, generator=gen)
+    old = O.SOFTMAX_SCALE
+    try:
+        for scale in (1.0, 25.0):
+            O.SOFTMAX_SCALE = scale
+            yref = O.ce_forward(rand_weights, x)
+            ce = dagl_b200.CE(in_channels=64, impl=impl, softmax_scale=scale)
+            ce.load_state_dict(rand_weights)
+            ce = ce.to(dev).eval()
+            with torch.no_grad():
+                y = ce(x.to(dev))
+            assert rel_err(y.cpu(), yref) <= REL_TOL, scale
+    finally:
+        O.SOFTMAX_SCALE = old

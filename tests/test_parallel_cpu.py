@@ -71,3 +71,38 @@ def test_forward_sharded_gloo_world2(nimg):
         assert s == float(nimg)              # every image processed exactly once
         b0, b1 = parallel.partition(nimg, 2, rank)
         assert n_local == (b1 - b0)
+
+
+def _rows_worker(rank, world, port, nq, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, D = 2, 5
+        gen = torch.Generator().manual_seed(0)
+        truth = torch.randn(B, nq, D, generator=gen)
+        ntile = (nq + 127) // 128
+        tpr = (ntile + world - 1) // world
+        rows = torch.zeros(B, ntile * 128, D)
+        q0, q1 = min(nq, rank * tpr * 128), min(nq, (rank + 1) * tpr * 128)
+        rows[:, q0:q1] = truth[:, q0:q1]                       # this rank's query tiles only
+        full = parallel.gather_query_rows(rows, tpr * 128, nq)
+        q.put((rank, torch.equal(full, truth)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [4096, 300, 100])
+def test_gather_query_rows_gloo_world2(nq):
+    """Host logic of single-image query sharding: owned tile slices -> one all-gather -> full rows."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, nq, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
