@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="auto", choices=["auto", "simt", "tc", "reference"])
+    ap.add_argument("--impl", default="auto", choices=["auto", "simt", "tc", "tc1", "tc4", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -292,7 +292,7 @@ def main():
             "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 dense burst (MEASURED_PEAKS.json)",
-            "kernel": f"attend_{impl_used}", "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
+            "kernel": {"tc": "attend_tc2_kernel", "tc4": "attend_tc4_kernel", "tc1": "attend_tc_kernel", "simt": "attend_simt_kernel"}.get(impl_used, impl_used), "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
             "flops_per_launch": B_PER_GPU * FLOPS_ALG, "bytes_per_launch": B_PER_GPU * BYTES_ALG,
             "hbm_gbs_algorithmic": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9,
             "hbm_frac_of_measured": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],

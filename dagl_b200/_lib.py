@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdagl_b200.so")
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC1 = 0, 1, 2, 3
-IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC, "tc1": IMPL_TC1}
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC1, IMPL_TC4 = 0, 1, 2, 3, 4
+IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC, "tc1": IMPL_TC1, "tc4": IMPL_TC4}
 
 EXPORTS = [
     "dagl_abi_version", "dagl_last_error", "dagl_ce_workspace_bytes", "dagl_ce_forward_f32",

@@ -1069,16 +1069,424 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
 }
 
+// =============================================================================================
+// v4: 4-CTA cluster per query tile.  Each CTA owns one QUARTER of the value columns (<= 208), which
+// leaves room in TMEM for the whole query tile (hi + lo = 208 columns): the score MMAs take their A
+// operand from TMEM (no 4 KB smem re-read per MMA: 28 instead of ~51 cycles at N = 48), and the 104 KB
+// of smem the query tile used to occupy go to deeper K / theta rings.  CTA r owns the key tiles j with
+// (j & 3) == r, computes S + softmax for them and forwards the fp16 P tile to the three peers with bulk
+// DSMEM copies; all four run P.V for every tile on their column quarter.  Same fixed softmax reference
+// (rowmax pre-pass) as v2.
+//   TMEM: O [0,208) | Qh [208,312) | Ql [312,416) | S0 [416,464) | S1 [464,512)
+// =============================================================================================
+constexpr int V4_THREADS = TC_THREADS + 64;                 // + forwarder warp + score-MMA issuer warp
+constexpr int V4_KST = 2, V4_TST = 2, V4_TSLOTS = 3;
+constexpr int V4_PSLOTS = 8;                                // P slots: (producer rank) + 4 * (round parity): double buffered
+constexpr int V4_TSTAGE_BYTES = 4 * V4_TSLOTS * TH_SEG_BYTES;   // one stage = the theta segments of a round of 4 tiles: 24576
+constexpr int V4_O_COLS = 208, V4_QH_COL = 208, V4_QL_COL = 312, V4_S_COL0 = 416;
+constexpr int S4_K = 0;
+constexpr int S4_T = S4_K + V4_KST * K_TILE_BYTES;          // 79872 = 78 * 1024
+constexpr int S4_P = S4_T + V4_TST * V4_TSTAGE_BYTES;       // + 49152
+constexpr int S4_BAR = S4_P + V4_PSLOTS * P_SLOT_BYTES;
+constexpr int S4_RED = S4_BAR + 512;
+constexpr int S4_TOTAL = S4_RED + 2 * 4 * 3 * 32 * 4;
+static_assert(S4_T % 1024 == 0 && S4_P % 1024 == 0, "v4 smem alignment");
+static_assert(S4_TOTAL <= 232448, "v4 smem");
+
+// value-column groups per cluster rank: shifts s = dy*7+dx; rank r owns s in [12r, 12r+12) (rank 3: 13 shifts)
+__constant__ PvGroup c_groups4[4][3] = {
+    {{0, 0, 112, 0}, {1, 0, 80, 112}, {0, 0, 0, 0}},
+    {{1, 5, 32, 0}, {2, 0, 112, 32}, {3, 0, 48, 144}},
+    {{3, 3, 64, 0}, {4, 0, 112, 64}, {5, 0, 16, 176}},
+    {{5, 1, 96, 0}, {6, 0, 112, 96}, {0, 0, 0, 0}}};
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(V4_THREADS, 1)
+attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
+                  const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
+                  const float* __restrict__ thrA, const float* __restrict__ thrB,
+                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
+                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][4][Nq]*/,
+                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
+  uint64_t* q_ready = bars + 0;   // query tile resident in TMEM (128 arrivals)
+  uint64_t* k_full = bars + 1;    // [2] ring over OWN tiles
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* t_full = bars + 7;    // [2] ring over ROUNDS of 4 tiles
+  uint64_t* t_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 13;   // [2]
+  uint64_t* s_free = bars + 15;   // [2]
+  uint64_t* p_full = bars + 17;   // [8] slot r + 4*parity is written by cluster rank r (into all four CTAs)
+  uint64_t* p_free = bars + 25;   // [8] only the slots of `rank` are waited on here: 4 commit arrivals (every CTA's P.V)
+  uint64_t* pv_last = bars + 33;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int img = blockIdx.z, split = blockIdx.y;
+  const int qt = qt_base + (blockIdx.x >> 2);
+  const int rank = (int)cluster_ctarank();                  // == blockIdx.x & 3
+  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int ntiles = t_end - t_begin;
+  const int n_own = (ntiles - rank + 3) / 4;                // local tiles j with (j & 3) == rank
+  const int ngroups = (rank == 0 || rank == 3) ? 2 : 3;
+#ifdef DAGL_TC_TRACE
+  long long tr_a = 0, tr_b = 0, tr_c = 0;
+  const long long tr_start = clock64();
+  const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+#endif
+
+  if (tid == 0) {
+    mbar_init(q_ready, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
+      mbar_init(s_full + i, 1); mbar_init(s_free + i, 384);
+    }
+    for (int i = 0; i < V4_PSLOTS; ++i) { mbar_init(p_full + i, (i & 3) == rank ? 384 : 1); mbar_init(p_free + i, 4); }
+    mbar_init(pv_last, 1);
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
+      auto load_k = [&](int i) {                            // own tile i  (local tile 4i + rank)
+        const int s = i % V4_KST;
+        mbar_wait(k_empty + s, ((uint32_t)(i / V4_KST) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
+        bulk_g2s(smem + S4_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t_begin + 4 * i + rank) * K_TILE_BYTES,
+                 K_TILE_BYTES, k_full + s);
+      };
+      auto load_t_round = [&](int p) {                     // theta segments of tiles 4p .. 4p+3, one barrier
+        const int s = p & 1;
+        const int nt = min(4, ntiles - 4 * p);
+        mbar_wait(t_empty + s, ((uint32_t)(p >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(t_full + s, (uint32_t)(nt * ngroups) * TH_SEG_BYTES);
+        for (int u = 0; u < nt; ++u) {
+          const int t = t_begin + 4 * p + u;
+          for (int sl = 0; sl < ngroups; ++sl) {
+            const int first = (t * TC_BN + c_groups4[rank][sl].dy * tg.Wp) & ~7;
+            bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES + (u * V4_TSLOTS + sl) * TH_SEG_BYTES, thp + (size_t)first * 32,
+                     TH_SEG_BYTES, t_full + s);
+          }
+        }
+      };
+      if (n_own > 0) load_k(0);
+      for (int p = 0; 4 * p < ntiles; ++p) {
+        if (p + 1 < n_own) load_k(p + 1);
+        load_t_round(p);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== P.V MMA issuer =====================
+    if (elect_one()) {
+      uint32_t p_free_prod[4];                                             // p_free[r] (parity 0) in the producer CTA r
+#pragma unroll
+      for (int r = 0; r < 4; ++r) p_free_prod[r] = mapa(smem_u32(p_free + r), (uint32_t)r);
+      uint32_t g_idesc[V4_TSLOTS], g_col[V4_TSLOTS];
+      int g_dywp[V4_TSLOTS], g_dx0[V4_TSLOTS];
+#pragma unroll
+      for (int sl = 0; sl < V4_TSLOTS; ++sl) {
+        const PvGroup gp = c_groups4[rank][sl];
+        g_idesc[sl] = instr_desc(128, (uint32_t)(gp.n > 0 ? gp.n : 16), FMT_F16, FMT_F16, 0, 1);
+        g_col[sl] = tbase + gp.col0;
+        g_dywp[sl] = gp.dy * tg.Wp;
+        g_dx0[sl] = gp.dx0;
+      }
+      const uint64_t bd_hi = ((uint64_t)(32 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+      for (int p = 0; 4 * p < ntiles; ++p) {
+        const int ts = p & 1;
+        { TRACE_T0(); mbar_wait(t_full + ts, (uint32_t)(p >> 1) & 1u); TRACE_ADD(tr_c); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = 4 * p + u;                                           // producer rank u, P slot u + 4 * (p & 1)
+          const int ps = u + 4 * (p & 1);
+          if (j >= ntiles) break;
+          const int t = t_begin + j;
+          const uint32_t tstage = smem_u32(smem + S4_T + ts * V4_TSTAGE_BYTES + u * V4_TSLOTS * TH_SEG_BYTES);
+          const uint32_t pbase = smem_u32(smem + S4_P + ps * P_SLOT_BYTES);
+          uint32_t g_start[V4_TSLOTS];
+#pragma unroll
+          for (int sl = 0; sl < V4_TSLOTS; ++sl)
+            g_start[sl] = (tstage + sl * TH_SEG_BYTES + ((((t * TC_BN + g_dywp[sl]) & 7) + g_dx0[sl]) << 5)) >> 4;
+          const uint64_t ad0 = smem_desc(pbase, (TC_BM / 8) * 128, 128);
+          if (u != rank) mbar_arrive_expect_tx(p_full + ps, P_SLOT_BYTES);   // peer tile: arrives as a bulk copy
+          { TRACE_T0(); mbar_wait(p_full + ps, (uint32_t)(p >> 1) & 1u); TRACE_ADD(tr_b); }
+          tc_fence_after();
+#ifdef DAGL_TC_TRACE
+          if (!(g_tc_dbg_mode & 2))
+#endif
+#pragma unroll
+          for (int ks = 0; ks < TC_BN / 16; ++ks) {
+            const uint64_t ad = ad0 + (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t b0 = bd_hi | (uint64_t)((g_start[0] + ks * 32) & 0x3FFF);
+            const uint64_t b1 = bd_hi | (uint64_t)((g_start[1] + ks * 32) & 0x3FFF);
+            mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], acc);            // the groups share the P slab (A collector)
+            if (ngroups == 2) {
+              mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], acc);
+            } else {
+              const uint64_t b2 = bd_hi | (uint64_t)((g_start[2] + ks * 32) & 0x3FFF);
+              mma_f16_ss_a_use(g_col[1], ad, b1, g_idesc[1], acc);
+              mma_f16_ss_a_lastuse(g_col[2], ad, b2, g_idesc[2], acc);
+            }
+          }
+          if (j + 8 < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p & 1));   // slot may be refilled by its producer CTA (+4 barriers)
+          if (j == ntiles - 1) mma_commit(pv_last);
+        }
+        mma_commit(t_empty + ts);
+      }
+    }
+  } else if (warp == TC_THREADS / 32 + 1) {
+    // ===================== score MMA issuer (own tiles; A operands Qh, Ql from TMEM) =====================
+    if (elect_one()) {
+      constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
+      const uint32_t qh = tbase + V4_QH_COL, ql = tbase + V4_QL_COL;
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      for (int i = 0; i < n_own; ++i) {
+        const int s = i & 1, ks_ = i % V4_KST;
+        { TRACE_T0(); mbar_wait(k_full + ks_, (uint32_t)(i / V4_KST) & 1u); TRACE_ADD(tr_a); }
+        { TRACE_T0(); mbar_wait(s_free + s, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_a); }
+        tc_fence_after();
+        const uint32_t k_hi = smem_u32(smem + S4_K + ks_ * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
+        const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
+        const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
+        const uint32_t d = tbase + V4_S_COL0 + s * TC_BN;
+#ifdef DAGL_TC_TRACE
+        if (!(g_tc_dbg_mode & 1))
+#endif
+        {
+#pragma unroll
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ts(d, ql + ks * 8, dk_hi + ko, idS, ks > 0);              // Ql.Kh first (small terms)
+          }
+#pragma unroll
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ts(d, qh + ks * 8, dk_lo + ko, idS, 1);                   // Qh.Kl
+            mma_f16_ts(d, qh + ks * 8, dk_hi + ko, idS, 1);                   // Qh.Kh
+          }
+        }
+        mma_commit(s_full + s);
+        mma_commit(k_empty + ks_);
+      }
+    }
+  } else if (warp == TC_THREADS / 32) {
+    // ===================== P forwarder: one bulk DSMEM copy per peer =====================
+    if (elect_one()) {
+      const uint32_t src0 = smem_u32(smem + S4_P + rank * P_SLOT_BYTES);
+      uint32_t dst[3], rbar[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const uint32_t peer = (uint32_t)((rank + 1 + u) & 3);
+        dst[u] = mapa(src0, peer);
+        rbar[u] = mapa(smem_u32(p_full + rank), peer);
+      }
+      for (int i = 0; i < n_own; ++i) {
+        const uint32_t par = (uint32_t)(i & 1);                            // slot rank + 4*par
+        mbar_wait(p_full + rank + 4 * par, (uint32_t)(i >> 1) & 1u);
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst[u] + par * 4 * P_SLOT_BYTES), "r"(src0 + par * 4 * P_SLOT_BYTES), "r"((uint32_t)P_SLOT_BYTES),
+                         "r"(rbar[u] + par * 32) : "memory");
+      }
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int lane = tid & 31;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
+    // ---- query tile -> TMEM (A operand of the score MMAs): lane = row, column j = elements (2j, 2j+1) ----
+    if (sub == 0) {
+      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+        const uint8_t* src = qsrc + part * Q_HALF_BYTES + row * 16;
+        const uint32_t col = part ? V4_QL_COL : V4_QH_COL;
+#pragma unroll 1
+        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+          const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
+          const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
+          const uint32_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          tmem_st8(trow + col + ks * 8, v);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(q_ready);
+    }
+    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
+    const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) *
+                               pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
+    const int q = qt * TC_BM + row;
+    const bool qvalid = q < g.Nq;
+    float ref;
+    {
+      const float s_hi = __uint_as_float(__ldg(smax + qidx)) * inv_s * 1.00390625f;
+      const float rl = fmaxf((s_hi - tA) + tB, 0.f);
+      ref = (s_hi * rl) * sm_scale_log2 - 12.f;             // see v2
+    }
+    float l_run = 0.f;
+    int cnt = 0;
+    const int nwords = (g.Nk + 31) / 32;
+    const uint32_t p_local0 = smem_u32(smem + S4_P + rank * P_SLOT_BYTES) + (2 * sub) * (TC_BM / 8) * 128 + row * 16;
+    const bool want_mask = (mask_bits != nullptr) || (nnz != nullptr);
+    const float neg_ref = -ref;
+
+    for (int i = 0; i < n_own; ++i) {
+      const int s = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int t = t_begin + 4 * i + rank;
+      const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
+      { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
+      tc_fence_after();
+      float sv[16];
+      {
+        uint32_t r0[16];
+        tmem_ld16(trow + V4_S_COL0 + s * TC_BN + 16 * sub, r0);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sv[k] = __uint_as_float(r0[k]);
+      }
+      tc_fence_before();
+      mbar_arrive(s_free + s);
+      unsigned mk = 0u;
+      uint32_t pk[8];
+      float psum = 0.f;
+      if (vbits == 0xffffu && !want_mask) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          float p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float sc = sv[k + u] * inv_s;
+            const float rl = fmaxf((sc - tA) + tB, 0.f);
+            const float pe = ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref));
+            p[u] = (rl != 0.f) ? pe : 0.f;
+            if (rl == 0.f) psum += pe;
+          }
+          pk[k / 2] = pack_half2(p[0], p[1]);
+          const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
+          psum += pr.x + pr.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          float p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float sc = sv[k + u] * inv_s;
+            const float rl = fmaxf((sc - tA) + tB, 0.f);
+            const bool valid = (vbits >> (k + u)) & 1u;
+            const float pe = valid ? ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref)) : 0.f;
+            const bool nb = valid && (rl != 0.f);
+            if (nb) mk |= 1u << (k + u);
+            p[u] = nb ? pe : 0.f;
+            if (!nb) psum += pe;
+          }
+          pk[k / 2] = pack_half2(p[0], p[1]);
+          const float2 pr = __half22float2(*reinterpret_cast<const __half2*>(&pk[k / 2]));
+          psum += pr.x + pr.y;
+        }
+        cnt += __popc(mk);
+      }
+      l_run += psum;
+      const int par = i & 1;                                // my slot for this tile: rank + 4*par (last used by own tile i-2)
+      const uint32_t p_local = p_local0 + par * 4 * P_SLOT_BYTES;
+      { TRACE_T0(); mbar_wait(p_free + rank + 4 * par, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      fence_async_smem();
+      mbar_arrive(p_full + rank + 4 * par);
+
+      if (mask_bits != nullptr && qvalid && mk != 0u) {     // debug path only
+        uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
+        unsigned rem = mk;
+        while (rem) {
+          const int b = __ffs((int)rem) - 1;
+          rem &= rem - 1;
+          const int kp = t * TC_BN + 16 * sub + b;
+          const int kk = (kp / tg.Wp) * g.W + (kp % tg.Wp);
+          atomicOr(mrow + (kk >> 5), 1u << (kk & 31));
+        }
+      }
+    }
+
+    // ---- epilogue: partial accumulator -> global ----
+    if (ntiles > 0) {
+      mbar_wait(pv_last, 0);
+      tc_fence_after();
+    }
+    const float inv_t = 1.f / pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
+    const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
+    float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
+    int chunk = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < ngroups; ++sl) {
+      const PvGroup gp = c_groups4[rank][sl];
+      for (int gdx = 0; gdx < gp.n / 16; ++gdx, ++chunk) {
+        if (chunk % 3 != sub) continue;
+        uint32_t v[16];
+        tmem_ld16(trow + gp.col0 + gdx * 16, v);
+        tmem_wait_ld();
+        if (qvalid) {
+          float4* dst = reinterpret_cast<float4*>(orow + (gp.dy * KS + gp.dx0 + gdx) * CI);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            dst[k] = make_float4(__uint_as_float(v[4 * k]) * inv_t, __uint_as_float(v[4 * k + 1]) * inv_t,
+                                 __uint_as_float(v[4 * k + 2]) * inv_t, __uint_as_float(v[4 * k + 3]) * inv_t);
+        }
+      }
+    }
+    float* xl = reinterpret_cast<float*>(smem + S4_RED) + (quad * 3) * 32;
+    int* xc = reinterpret_cast<int*>(smem + S4_RED + 4 * 3 * 32 * 4) + (quad * 3) * 32;
+    xl[sub * 32 + lane] = l_run;
+    xc[sub * 32 + lane] = cnt;
+    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
+    if (sub == 0 && qvalid) {
+      lpart[(((size_t)img * nsplit + split) * 4 + rank) * g.Nq + q] = (xl[lane] + xl[32 + lane]) + xl[64 + lane];
+      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
+    }
+  }
+
+#ifdef DAGL_TC_TRACE
+  if (tr_cta < 1024 && (tid & 31) == 0 && warp <= 2) {
+    long long* o = g_tc_trace[tr_cta] + warp * 4;
+    o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
+    if (warp == 0) { g_tc_trace[tr_cta][12] = ntiles; g_tc_trace[tr_cta][14] = tr_start; }
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
+}
+
 // coef[b][s][q] = 1 / sum_{s,h} l   (fixed-reference partials merge by plain sums)
-__global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int q_begin, int q_end, const float* __restrict__ lpart,
-                                        float* __restrict__ coef) {
+__global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int nparts, int q_begin, int q_end,
+                                        const float* __restrict__ lpart, float* __restrict__ coef) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Nq) return;
   const int img = i / Nq, q = i % Nq;
   if (q < q_begin || q >= q_end) return;
   float L = 0.f;
   for (int s = 0; s < nsplit; ++s)
-    for (int h = 0; h < 2; ++h) L += lpart[(((size_t)img * nsplit + s) * 2 + h) * Nq + q];
+    for (int h = 0; h < nparts; ++h) L += lpart[(((size_t)img * nsplit + s) * nparts + h) * Nq + q];
   const float inv = 1.f / L;
   for (int s = 0; s < nsplit; ++s) coef[((size_t)img * nsplit + s) * Nq + q] = inv;
 }
@@ -1088,13 +1496,14 @@ __global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int q_begin, 
 // ---------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range) {
-  const long long base = (long long)g.B * nqt_range * 2;
+static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range, int csize = 2) {
+  const long long base = (long long)g.B * nqt_range * csize;
+  const int sms = csize == 4 ? 132 : 148;          // 4-CTA clusters cannot use every SM (GPC sizes 16/18/20)
   const int smax = tg.NT < 32 ? tg.NT : 32;
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= smax; ++s) {
-    const double waves = (double)((base * s + 147) / 148);
+    const double waves = (double)((base * s + sms - 1) / sms);
     // time ~ waves * (tiles per CTA + fixed per-CTA overhead of ~6 tiles), plus partial traffic
     const double cost = waves * ((double)tg.NT / s + 6.0) + 0.5 * s;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
@@ -1112,7 +1521,9 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   // key-split factor the workspace is sized for: the larger of the full launch and an 8-way query-sharded launch
   {
     const int full = tc_splits(g, tg, tg.nqt), shard = tc_splits(g, tg, tg.nqt >= 8 ? tg.nqt / 8 : 1);
+    const int full4 = tc_splits(g, tg, tg.nqt, 4);
     w.nsplit = full > shard ? full : shard;
+    if (full4 > w.nsplit) w.nsplit = full4;
   }
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
@@ -1126,7 +1537,7 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
   w.Opart = take(rows * VD * 4);
   w.mpart = take(rows * 4);
-  w.lpart = take(2 * rows * 4);                 // v2 keeps one row-sum partial per cluster rank
+  w.lpart = take(4 * rows * 4);                 // v2 / v4 keep one row-sum partial per cluster rank
   w.coef = take(rows * 4);
   w.Om = take(merge_fold_scratch_bytes(g));
   w.smax = take((size_t)g.B * tg.nqt * TC_BM * 4);
@@ -1147,12 +1558,12 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     call_state().err = "empty query-tile range";
     return -1;
   }
-  if ((qt_begin != 0 || qt_end != tg.nqt || a.rows_out != nullptr) && variant != 2) {
+  if ((qt_begin != 0 || qt_end != tg.nqt || a.rows_out != nullptr) && variant != 2 && variant != 4) {
     call_state().err = "query-tile ranges / row output need the clustered tensor-core kernel (impl tc)";
     return -2;
   }
   {
-    const int want = tc_splits(g, tg, qt_end - qt_begin);
+    const int want = tc_splits(g, tg, qt_end - qt_begin, variant == 4 ? 4 : 2);
     if (want < w.nsplit) w.nsplit = want;           // never more splits than the workspace was sized for
   }
   if (a.ws_bytes < w.total) {
@@ -1212,8 +1623,8 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   }
 
   const float sm_scale_log2 = a.scale * 1.4426950408889634f;
-  dim3 grid((qt_end - qt_begin) * 2, w.nsplit, g.B);
-  if (variant == 2) {
+  dim3 grid((qt_end - qt_begin) * (variant == 4 ? 4 : 2), w.nsplit, g.B);
+  if (variant == 2 || variant == 4) {
     unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
     DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, (size_t)g.B * tg.nqt * TC_BM * 4, st));
     // pre-pass: row maxima of the scores (Qh.Kh only)
@@ -1225,16 +1636,23 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
     rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, qt_begin, qt_end, smax);
     DAGL_LAUNCH_CHECK();
-    DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
     if (int rc = prof_begin(st)) return rc;
-    attend_tc2_kernel<<<grid, TC2_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
-                                                          sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
-                                                          a.nnz);
+    if (variant == 4) {
+      DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
+      attend_tc4_kernel<<<grid, V4_THREADS, S4_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+                                                           sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
+                                                           a.nnz);
+    } else {
+      DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
+      attend_tc2_kernel<<<grid, TC2_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+                                                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
+                                                            a.nnz);
+    }
     DAGL_LAUNCH_CHECK();
     if (int rc = prof_end(st)) return rc;
     const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
     const int nq_total = g.B * g.Nq;
-    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, q_begin, q_end, lpart, coef);
+    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef);
     DAGL_LAUNCH_CHECK();
     if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
       return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);

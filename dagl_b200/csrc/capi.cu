@@ -87,10 +87,16 @@ static int check_shape(int B, int H, int W) {
 }
 
 static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsigned* absmax, cudaStream_t st) {
-  if (impl == DAGL_IMPL_AUTO) impl = DAGL_IMPL_TC;
+  // measured (profiles/r1): the 4-CTA-cluster kernel wins up to ~256^2 keys; beyond that the K tiles stop fitting in
+  // L2 next to four CTAs' worth of traffic and the 2-CTA kernel is slightly ahead
+  if (impl == DAGL_IMPL_AUTO) impl = ((long long)g.Nk <= 160000) ? DAGL_IMPL_TC4 : DAGL_IMPL_TC;
   if (impl == DAGL_IMPL_TC) {
     call_state().impl = "tc";
     return launch_attend_tc(g, a, absmax, 2, st);
+  }
+  if (impl == DAGL_IMPL_TC4) {
+    call_state().impl = "tc4";
+    return launch_attend_tc(g, a, absmax, 4, st);
   }
   if (impl == DAGL_IMPL_TC1) {
     call_state().impl = "tc1";

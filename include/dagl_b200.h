@@ -37,7 +37,8 @@ enum {
   DAGL_IMPL_AUTO = 0,   /* best available for the shape */
   DAGL_IMPL_SIMT = 1,   /* fp32 CUDA-core kernel (bit-faithful neighbour mask) */
   DAGL_IMPL_TC = 2,     /* tcgen05 tensor-core kernel (split-fp16 scores, fp16 P.V), 2-CTA clusters sharing P */
-  DAGL_IMPL_TC1 = 3     /* earlier tensor-core variant (no clusters, online softmax); kept for A/B checks */
+  DAGL_IMPL_TC1 = 3,    /* earlier tensor-core variant (no clusters, online softmax); kept for A/B checks */
+  DAGL_IMPL_TC4 = 4     /* 4-CTA clusters, query tile resident in TMEM (A operand of the score MMAs) */
 };
 
 /* Borrowed device pointers to one CE head's parameters, in the reference's

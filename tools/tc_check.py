@@ -18,7 +18,7 @@ for shape in shapes:
         mask_ref = aux["mask"]
     else:
         yref = O.ce_forward_chunked(params, x, chunk=256); mask_ref = None
-    for impl in ("simt", "tc1", "tc"):
+    for impl in ("tc", "tc4"):
         ce = dagl_b200.CE(in_channels=64, impl=impl); ce.load_state_dict(params); ce = ce.to(dev).eval()
         print(f"{shape} {impl}: launching", flush=True)
         with torch.no_grad():
