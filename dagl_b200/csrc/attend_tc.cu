@@ -62,11 +62,11 @@ struct TcGeom {
 
 static TcGeom tc_geom(const Geom& g) {
   TcGeom t;
-  t.Wp = g.W + 2 * PADK;
+  t.Wp = (g.W + 2 * PADK + 7) & ~7;   // multiple of 8: every dy row of a key tile starts at the same 8-pixel phase
   t.NkP = (g.H - 1) * t.Wp + g.W;
   t.NT = (t.NkP + TC_BN - 1) / TC_BN;
   int np = (g.H + 2 * PADK) * t.Wp;
-  int need = TC_BN * t.NT + 2 * PADK * t.Wp + TH_SEG_PIX + 8;
+  int need = TC_BN * (t.NT + 3) + 2 * PADK * t.Wp + TH_SEG_PIX + 8;   // v4 loads the theta rows of 4 tiles in one copy
   t.NP = ((np > need ? np : need) + 7) & ~7;
   t.nqt = (g.Nq + TC_BM - 1) / TC_BM;
   return t;
@@ -234,13 +234,17 @@ pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsi
 // ---------------------------------------------------------------------------------------------
 #ifdef DAGL_TC_TRACE
 // development aid (tools/tc_trace.py): per-CTA cycle counters of the pipeline roles
-__device__ long long g_tc_trace[1024][16];
+__device__ long long g_tc_trace[1024][24];
+__device__ long long g_tc_tl[4][32][24];   // tc4 timeline: [cluster rank][round - TL_P0][event], cycles since CTA start (cluster 0 only)
+#define TL_P0 100
+#define TL(round, ev) do { const int _r = (round) - TL_P0; if (tl_on && _r >= 0 && _r < 32) g_tc_tl[rank][_r][ev] = clock64() - tr_start; } while (0)
 __device__ int g_tc_dbg_mode = 0;      // bit0: skip the S MMAs, bit1: skip the P.V MMAs (timing experiments only)
 #define TRACE_T0() long long _t0 = clock64()
 #define TRACE_ADD(var) (var) += clock64() - _t0
 #else
 #define TRACE_T0()
 #define TRACE_ADD(var)
+#define TL(round, ev)
 #endif
 
 struct PvGroup { int dy, dx0, n, col0; };
@@ -1079,26 +1083,32 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 // (rowmax pre-pass) as v2.
 //   TMEM: O [0,208) | Qh [208,312) | Ql [312,416) | S0 [416,464) | S1 [464,512)
 // =============================================================================================
-constexpr int V4_THREADS = TC_THREADS + 64;                 // + forwarder warp + score-MMA issuer warp
-constexpr int V4_KST = 2, V4_TST = 2, V4_TSLOTS = 3;
+constexpr int V4_THREADS = TC_THREADS + 96;                 // + forwarder warp + score-MMA issuer warp + K loader warp
+constexpr int V4_KST = 2, V4_TST = 3, V4_TSLOTS = 4;
 constexpr int V4_PSLOTS = 8;                                // P slots: (producer rank) + 4 * (round parity): double buffered
-constexpr int V4_TSTAGE_BYTES = 4 * V4_TSLOTS * TH_SEG_BYTES;   // one stage = the theta segments of a round of 4 tiles: 24576
+constexpr int V4_TSEG_BYTES = (TC_BN + TH_SEG_PIX) * 32;    // one dy row of theta for a pair of tiles: 112 pixels = 3584 B
+constexpr int V4_TSTAGE_BYTES = V4_TSLOTS * V4_TSEG_BYTES;  // one stage = up to 4 theta rows of a tile pair: 14336
 constexpr int V4_O_COLS = 208, V4_QH_COL = 208, V4_QL_COL = 312, V4_S_COL0 = 416;
 constexpr int S4_K = 0;
 constexpr int S4_T = S4_K + V4_KST * K_TILE_BYTES;          // 79872 = 78 * 1024
-constexpr int S4_P = S4_T + V4_TST * V4_TSTAGE_BYTES;       // + 49152
+constexpr int S4_P = S4_T + V4_TST * V4_TSTAGE_BYTES;       // + 43008
 constexpr int S4_BAR = S4_P + V4_PSLOTS * P_SLOT_BYTES;
 constexpr int S4_RED = S4_BAR + 512;
 constexpr int S4_TOTAL = S4_RED + 2 * 4 * 3 * 32 * 4;
 static_assert(S4_T % 1024 == 0 && S4_P % 1024 == 0, "v4 smem alignment");
 static_assert(S4_TOTAL <= 232448, "v4 smem");
 
-// value-column groups per cluster rank: shifts s = dy*7+dx; rank r owns s in [12r, 12r+12) (rank 3: 13 shifts)
-__constant__ PvGroup c_groups4[4][3] = {
-    {{0, 0, 112, 0}, {1, 0, 80, 112}, {0, 0, 0, 0}},
-    {{1, 5, 32, 0}, {2, 0, 112, 32}, {3, 0, 48, 144}},
-    {{3, 3, 64, 0}, {4, 0, 112, 64}, {5, 0, 16, 176}},
-    {{5, 1, 96, 0}, {6, 0, 112, 96}, {0, 0, 0, 0}}};
+// Value columns per cluster rank: two MMAs per k-step for every rank (balanced tensor-pipe load).
+// Ranks 0..2 own the shift rows (2r, 2r+1) except shift (2r+1, dx 6): N = 112 + 96.  Rank 3 owns row 6 (N = 112) and the
+// three left-over shifts (dy 1,3,5; dx 6) as ONE MMA with N = 48 whose N-group stride is a theta row slot (the padded
+// width is a multiple of 8, so all rows of a tile share the 8-pixel phase and the slots are congruent).
+struct PvGroup4 { int slot, dx0, n, col0, vertical; };     // slot: index into c_rows4[rank] of the (first) theta row
+__constant__ int c_rows4[4][4] = {{0, 1, 0, 0}, {2, 3, 0, 0}, {4, 5, 0, 0}, {6, 1, 3, 5}};
+__constant__ PvGroup4 c_groups4[4][2] = {
+    {{0, 0, 112, 0, 0}, {1, 0, 96, 112, 0}},
+    {{0, 0, 112, 0, 0}, {1, 0, 96, 112, 0}},
+    {{0, 0, 112, 0, 0}, {1, 0, 96, 112, 0}},
+    {{0, 0, 112, 0, 0}, {1, 6, 48, 112, 1}}};
 
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(V4_THREADS, 1)
 attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
@@ -1112,8 +1122,8 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   uint64_t* q_ready = bars + 0;   // query tile resident in TMEM (128 arrivals)
   uint64_t* k_full = bars + 1;    // [2] ring over OWN tiles
   uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* t_full = bars + 7;    // [2] ring over ROUNDS of 4 tiles
-  uint64_t* t_empty = bars + 10;  // [2]
+  uint64_t* t_full = bars + 7;    // [3] ring over PAIRS of tiles
+  uint64_t* t_empty = bars + 10;  // [3]
   uint64_t* s_full = bars + 13;   // [2]
   uint64_t* s_free = bars + 15;   // [2]
   uint64_t* p_full = bars + 17;   // [8] slot r + 4*parity is written by cluster rank r (into all four CTAs)
@@ -1130,9 +1140,10 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int ntiles = t_end - t_begin;
   const int n_own = (ntiles - rank + 3) / 4;                // local tiles j with (j & 3) == rank
-  const int ngroups = (rank == 0 || rank == 3) ? 2 : 3;
+  const int nslots = rank == 3 ? 4 : 2;                     // theta rows this rank needs
 #ifdef DAGL_TC_TRACE
   long long tr_a = 0, tr_b = 0, tr_c = 0;
+  const bool tl_on = (blockIdx.x >> 2) == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   const long long tr_start = clock64();
   const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
 #endif
@@ -1141,9 +1152,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     mbar_init(q_ready, 128);
     for (int i = 0; i < 2; ++i) {
       mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
       mbar_init(s_full + i, 1); mbar_init(s_free + i, 384);
     }
+    for (int i = 0; i < V4_TST; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1); }
     for (int i = 0; i < V4_PSLOTS; ++i) { mbar_init(p_full + i, (i & 3) == rank ? 384 : 1); mbar_init(p_free + i, 4); }
     mbar_init(pv_last, 1);
     mbar_init_fence();
@@ -1159,31 +1170,43 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
-      auto load_k = [&](int i) {                            // own tile i  (local tile 4i + rank)
-        const int s = i % V4_KST;
-        mbar_wait(k_empty + s, ((uint32_t)(i / V4_KST) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
-        bulk_g2s(smem + S4_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t_begin + 4 * i + rank) * K_TILE_BYTES,
-                 K_TILE_BYTES, k_full + s);
-      };
-      auto load_t_round = [&](int p) {                     // theta segments of tiles 4p .. 4p+3, one barrier
-        const int s = p & 1;
-        const int nt = min(4, ntiles - 4 * p);
-        mbar_wait(t_empty + s, ((uint32_t)(p >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(t_full + s, (uint32_t)(nt * ngroups) * TH_SEG_BYTES);
-        for (int u = 0; u < nt; ++u) {
-          const int t = t_begin + 4 * p + u;
-          for (int sl = 0; sl < ngroups; ++sl) {
-            const int first = (t * TC_BN + c_groups4[rank][sl].dy * tg.Wp) & ~7;
-            bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES + (u * V4_TSLOTS + sl) * TH_SEG_BYTES, thp + (size_t)first * 32,
-                     TH_SEG_BYTES, t_full + s);
-          }
+      // theta rows of the tile pair (2h, 2h+1): 96 consecutive key slots + the 64-pixel window, ONE copy per row
+      const int nhalf = (ntiles + 1) >> 1;
+      for (int h = 0; h < nhalf; ++h) {
+        const int s = h % V4_TST;
+        { TRACE_T0(); mbar_wait(t_empty + s, ((uint32_t)(h / V4_TST) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+#ifdef DAGL_TC_TRACE
+        if (g_tc_dbg_mode & 8) {                             // timing experiment: one small segment per pair
+          mbar_arrive_expect_tx(t_full + s, 1024);
+          bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES, thp, 1024, t_full + s);
+          continue;
         }
-      };
-      if (n_own > 0) load_k(0);
-      for (int p = 0; 4 * p < ntiles; ++p) {
-        if (p + 1 < n_own) load_k(p + 1);
-        load_t_round(p);
+#endif
+        mbar_arrive_expect_tx(t_full + s, (uint32_t)nslots * V4_TSEG_BYTES);
+        const int k0 = (t_begin + 2 * h) * TC_BN;            // multiple of 8, and so is Wp
+        for (int sl = 0; sl < nslots; ++sl)
+          bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES + sl * V4_TSEG_BYTES, thp + (size_t)(k0 + c_rows4[rank][sl] * tg.Wp) * 32,
+                   V4_TSEG_BYTES, t_full + s);
+        TL(h >> 1, 20);
+      }
+    }
+  } else if (warp == TC_THREADS / 32 + 2) {
+    // ===================== K loader: own key tiles (local tile 4i + rank) =====================
+    if (elect_one()) {
+      const uint8_t* ksrc = Kp + ((size_t)img * tg.NT + t_begin + rank) * K_TILE_BYTES;
+      for (int i = 0; i < n_own; ++i, ksrc += 4 * (size_t)K_TILE_BYTES) {
+        const int s = i % V4_KST;
+        { TRACE_T0(); mbar_wait(k_empty + s, ((uint32_t)(i / V4_KST) & 1u) ^ 1u); TRACE_ADD(tr_a); }
+#ifdef DAGL_TC_TRACE
+        if (g_tc_dbg_mode & 16) {                            // timing experiment: 1 KB instead of the whole K tile
+          mbar_arrive_expect_tx(k_full + s, 1024);
+          bulk_g2s(smem + S4_K + s * K_TILE_BYTES, ksrc, 1024, k_full + s);
+          continue;
+        }
+#endif
+        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
+        bulk_g2s(smem + S4_K + s * K_TILE_BYTES, ksrc, K_TILE_BYTES, k_full + s);
+        TL(i, 19);
       }
     }
   } else if (warp == 1) {
@@ -1192,35 +1215,44 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       uint32_t p_free_prod[4];                                             // p_free[r] (parity 0) in the producer CTA r
 #pragma unroll
       for (int r = 0; r < 4; ++r) p_free_prod[r] = mapa(smem_u32(p_free + r), (uint32_t)r);
-      uint32_t g_idesc[V4_TSLOTS], g_col[V4_TSLOTS];
-      int g_dywp[V4_TSLOTS], g_dx0[V4_TSLOTS];
+      uint32_t g_idesc[2], g_col[2], g_off[2];
+      uint64_t g_bd[2];
 #pragma unroll
-      for (int sl = 0; sl < V4_TSLOTS; ++sl) {
-        const PvGroup gp = c_groups4[rank][sl];
-        g_idesc[sl] = instr_desc(128, (uint32_t)(gp.n > 0 ? gp.n : 16), FMT_F16, FMT_F16, 0, 1);
+      for (int sl = 0; sl < 2; ++sl) {
+        const PvGroup4 gp = c_groups4[rank][sl];
+        g_idesc[sl] = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
         g_col[sl] = tbase + gp.col0;
-        g_dywp[sl] = gp.dy * tg.Wp;
-        g_dx0[sl] = gp.dx0;
+        g_off[sl] = (uint32_t)(gp.slot * V4_TSEG_BYTES + gp.dx0 * 32);
+        // MN-major SWIZZLE_32B: SBO = 256 B (next 8 keys); LBO = stride between 16-channel N groups:
+        // one pixel (next dx) for a horizontal run, one theta row slot (next owned dy) for the vertical run
+        const uint32_t lbo = gp.vertical ? (uint32_t)V4_TSEG_BYTES : 32u;
+        g_bd[sl] = ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
       }
-      const uint64_t bd_hi = ((uint64_t)(32 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+      uint32_t tstage = 0;
+      int ts = 0;
       for (int p = 0; 4 * p < ntiles; ++p) {
-        const int ts = p & 1;
-        { TRACE_T0(); mbar_wait(t_full + ts, (uint32_t)(p >> 1) & 1u); TRACE_ADD(tr_c); }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = 4 * p + u;                                           // producer rank u, P slot u + 4 * (p & 1)
           const int ps = u + 4 * (p & 1);
           if (j >= ntiles) break;
-          const int t = t_begin + j;
-          const uint32_t tstage = smem_u32(smem + S4_T + ts * V4_TSTAGE_BYTES + u * V4_TSLOTS * TH_SEG_BYTES);
+          if ((u & 1) == 0) {                                                // a new tile pair: its theta rows
+            const int h = 2 * p + (u >> 1);
+            ts = h % V4_TST;
+            { TRACE_T0(); mbar_wait(t_full + ts, (uint32_t)(h / V4_TST) & 1u); TRACE_ADD(tr_c); }
+            tstage = smem_u32(smem + S4_T + ts * V4_TSTAGE_BYTES);
+            if (u == 0) TL(p, 16);
+          }
+          const uint32_t tile0 = tstage + (u & 1) * (TC_BN * 32);            // second tile of the pair: 48 pixels further
           const uint32_t pbase = smem_u32(smem + S4_P + ps * P_SLOT_BYTES);
-          uint32_t g_start[V4_TSLOTS];
-#pragma unroll
-          for (int sl = 0; sl < V4_TSLOTS; ++sl)
-            g_start[sl] = (tstage + sl * TH_SEG_BYTES + ((((t * TC_BN + g_dywp[sl]) & 7) + g_dx0[sl]) << 5)) >> 4;
+          const uint32_t g_start0 = (tile0 + g_off[0]) >> 4, g_start1 = (tile0 + g_off[1]) >> 4;
           const uint64_t ad0 = smem_desc(pbase, (TC_BM / 8) * 128, 128);
+#ifdef DAGL_TC_TRACE
+          if (u != rank && (g_tc_dbg_mode & 4)) mbar_arrive_expect_tx(p_full + ps, 16); else
+#endif
           if (u != rank) mbar_arrive_expect_tx(p_full + ps, P_SLOT_BYTES);   // peer tile: arrives as a bulk copy
           { TRACE_T0(); mbar_wait(p_full + ps, (uint32_t)(p >> 1) & 1u); TRACE_ADD(tr_b); }
+          TL(p, 8 + 2 * u);
           tc_fence_after();
 #ifdef DAGL_TC_TRACE
           if (!(g_tc_dbg_mode & 2))
@@ -1229,21 +1261,16 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
           for (int ks = 0; ks < TC_BN / 16; ++ks) {
             const uint64_t ad = ad0 + (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
             const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t b0 = bd_hi | (uint64_t)((g_start[0] + ks * 32) & 0x3FFF);
-            const uint64_t b1 = bd_hi | (uint64_t)((g_start[1] + ks * 32) & 0x3FFF);
-            mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], acc);            // the groups share the P slab (A collector)
-            if (ngroups == 2) {
-              mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], acc);
-            } else {
-              const uint64_t b2 = bd_hi | (uint64_t)((g_start[2] + ks * 32) & 0x3FFF);
-              mma_f16_ss_a_use(g_col[1], ad, b1, g_idesc[1], acc);
-              mma_f16_ss_a_lastuse(g_col[2], ad, b2, g_idesc[2], acc);
-            }
+            const uint64_t b0 = g_bd[0] | (uint64_t)((g_start0 + ks * 32) & 0x3FFF);      // 16 keys = 512 B further per k-step
+            const uint64_t b1 = g_bd[1] | (uint64_t)((g_start1 + ks * 32) & 0x3FFF);
+            mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], acc);            // the two groups share the P slab (A collector)
+            mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], acc);
           }
           if (j + 8 < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p & 1));   // slot may be refilled by its producer CTA (+4 barriers)
+          if ((u & 1) == 1 || j == ntiles - 1) mma_commit(t_empty + ts);
           if (j == ntiles - 1) mma_commit(pv_last);
+          TL(p, 9 + 2 * u);
         }
-        mma_commit(t_empty + ts);
       }
     }
   } else if (warp == TC_THREADS / 32 + 1) {
@@ -1256,7 +1283,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       for (int i = 0; i < n_own; ++i) {
         const int s = i & 1, ks_ = i % V4_KST;
         { TRACE_T0(); mbar_wait(k_full + ks_, (uint32_t)(i / V4_KST) & 1u); TRACE_ADD(tr_a); }
-        { TRACE_T0(); mbar_wait(s_free + s, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_a); }
+        TL(i, 5);
+        { TRACE_T0(); mbar_wait(s_free + s, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+        TL(i, 6);
         tc_fence_after();
         const uint32_t k_hi = smem_u32(smem + S4_K + ks_ * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
         const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
@@ -1280,6 +1309,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         }
         mma_commit(s_full + s);
         mma_commit(k_empty + ks_);
+        TL(i, 7);
       }
     }
   } else if (warp == TC_THREADS / 32) {
@@ -1296,10 +1326,16 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       for (int i = 0; i < n_own; ++i) {
         const uint32_t par = (uint32_t)(i & 1);                            // slot rank + 4*par
         mbar_wait(p_full + rank + 4 * par, (uint32_t)(i >> 1) & 1u);
+        TL(i, 17);
+#ifdef DAGL_TC_TRACE
+        const uint32_t fwd_bytes = (g_tc_dbg_mode & 4) ? 16u : (uint32_t)P_SLOT_BYTES;   // timing experiment: 16-byte forwards
+#else
+        const uint32_t fwd_bytes = (uint32_t)P_SLOT_BYTES;
+#endif
 #pragma unroll
         for (int u = 0; u < 3; ++u)
           asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst[u] + par * 4 * P_SLOT_BYTES), "r"(src0 + par * 4 * P_SLOT_BYTES), "r"((uint32_t)P_SLOT_BYTES),
+                       ::"r"(dst[u] + par * 4 * P_SLOT_BYTES), "r"(src0 + par * 4 * P_SLOT_BYTES), "r"(fwd_bytes),
                          "r"(rbar[u] + par * 32) : "memory");
       }
     }
@@ -1354,6 +1390,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       const int t = t_begin + 4 * i + rank;
       const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
       { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
+      if (warp == 2 && lane == 0) TL(i, 0);
       tc_fence_after();
       float sv[16];
       {
@@ -1365,6 +1402,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       }
       tc_fence_before();
       mbar_arrive(s_free + s);
+      if (warp == 2 && lane == 0) TL(i, 1);
       unsigned mk = 0u;
       uint32_t pk[8];
       float psum = 0.f;
@@ -1408,11 +1446,14 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       l_run += psum;
       const int par = i & 1;                                // my slot for this tile: rank + 4*par (last used by own tile i-2)
       const uint32_t p_local = p_local0 + par * 4 * P_SLOT_BYTES;
+      if (warp == 2 && lane == 0) TL(i, 2);
       { TRACE_T0(); mbar_wait(p_free + rank + 4 * par, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+      if (warp == 2 && lane == 0) TL(i, 3);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       fence_async_smem();
       mbar_arrive(p_full + rank + 4 * par);
+      if (warp == 2 && lane == 0) TL(i, 4);
 
       if (mask_bits != nullptr && qvalid && mk != 0u) {     // debug path only
         uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
@@ -1437,15 +1478,16 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
     int chunk = 0;
 #pragma unroll 1
-    for (int sl = 0; sl < ngroups; ++sl) {
-      const PvGroup gp = c_groups4[rank][sl];
+    for (int sl = 0; sl < 2; ++sl) {
+      const PvGroup4 gp = c_groups4[rank][sl];
       for (int gdx = 0; gdx < gp.n / 16; ++gdx, ++chunk) {
         if (chunk % 3 != sub) continue;
         uint32_t v[16];
         tmem_ld16(trow + gp.col0 + gdx * 16, v);
         tmem_wait_ld();
         if (qvalid) {
-          float4* dst = reinterpret_cast<float4*>(orow + (gp.dy * KS + gp.dx0 + gdx) * CI);
+          const int shift = gp.vertical ? c_rows4[rank][gp.slot + gdx] * KS + gp.dx0 : c_rows4[rank][gp.slot] * KS + gp.dx0 + gdx;
+          float4* dst = reinterpret_cast<float4*>(orow + shift * CI);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             dst[k] = make_float4(__uint_as_float(v[4 * k]) * inv_t, __uint_as_float(v[4 * k + 1]) * inv_t,
@@ -1469,6 +1511,10 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     long long* o = g_tc_trace[tr_cta] + warp * 4;
     o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
     if (warp == 0) { g_tc_trace[tr_cta][12] = ntiles; g_tc_trace[tr_cta][14] = tr_start; }
+  }
+  if (tr_cta < 1024 && (tid & 31) == 0 && warp == TC_THREADS / 32 + 1) {   // score issuer
+    long long* o = g_tc_trace[tr_cta] + 16;
+    o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
   }
 #endif
   tc_fence_before();
@@ -1674,7 +1720,10 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
 extern "C" int dagl_debug_set_tc_mode(int mode) {
   return (int)cudaMemcpyToSymbol(dagl::g_tc_dbg_mode, &mode, sizeof(int));
 }
-extern "C" int dagl_debug_read_tc_trace(long long* host_out /*[1024][16]*/) {
-  return (int)cudaMemcpyFromSymbol(host_out, dagl::g_tc_trace, sizeof(long long) * 1024 * 16);
+extern "C" int dagl_debug_read_tc_timeline(long long* host_out /*[4][32][24]*/) {
+  return (int)cudaMemcpyFromSymbol(host_out, dagl::g_tc_tl, sizeof(long long) * 4 * 32 * 24);
+}
+extern "C" int dagl_debug_read_tc_trace(long long* host_out /*[1024][24]*/) {
+  return (int)cudaMemcpyFromSymbol(host_out, dagl::g_tc_trace, sizeof(long long) * 1024 * 24);
 }
 #endif

@@ -22,13 +22,13 @@ params = O.init_ce_params(1000)
 x = torch.randn(1, 64, H, W, generator=torch.Generator().manual_seed(2000)).to(dev)
 ce = dagl_b200.CE(in_channels=64, impl=os.environ.get("IMPL", "tc")); ce.load_state_dict(params); ce = ce.to(dev).eval()
 L = _lib.lib()
-for mode in ((0,) if os.environ.get('IMPL', 'tc') == 'tc' else (0, 1, 2, 3)):
+for mode in [int(m) for m in os.environ.get('MODES', '0,1,2,3').split(',')]:
   L.dagl_debug_set_tc_mode(mode)
-  print(f"=== dbg mode {mode} (bit0: no S MMAs, bit1: no P.V MMAs) ===")
+  print(f"=== dbg mode {mode} (bit0: no S MMAs, bit1: no P.V MMAs, 4: tiny P forwards, 8: tiny theta loads, 16: tiny K loads) ===")
   with torch.no_grad():
     for _ in range(3): ce(x)
   torch.cuda.synchronize()
-  buf = np.zeros((1024, 16), dtype=np.int64)
+  buf = np.zeros((1024, 24), dtype=np.int64)
   rc = L.dagl_debug_read_tc_trace(buf.ctypes.data_as(ctypes.c_void_p))
   assert rc == 0
   n = int((buf[:, 12] > 0).sum())
@@ -40,5 +40,24 @@ for mode in ((0,) if os.environ.get('IMPL', 'tc') == 'tc' else (0, 1, 2, 3)):
   print(f"  producer : wait k_empty {per_tile(0).mean():8.0f}  wait t_empty {per_tile(1).mean():8.0f}  total {per_tile(3).mean():8.0f}")
   print(f"  mma      : wait k_full(+s_free) {per_tile(4).mean():8.0f}  wait p_full  {per_tile(5).mean():8.0f}  wait t_full {per_tile(6).mean():8.0f}  total {per_tile(7).mean():8.0f}")
   print(f"  softmax  : wait s_full  {per_tile(8).mean():8.0f}  named bar / p_free {per_tile(9).mean():8.0f}  total {per_tile(11).mean():8.0f}")
+  print(f"  score iss: wait k_full {per_tile(16).mean():8.0f}  wait s_free {per_tile(17).mean():8.0f}  total {per_tile(19).mean():8.0f}")
   t0 = b[:, 14].min(); 
   print("kernel span cycles:", (b[:, 14] + b[:, 3]).max() - t0, " CTA total mean", b[:, 3].mean())
+  if os.environ.get("TIMELINE"):
+    tl = np.zeros((4, 32, 24), dtype=np.int64)
+    assert L.dagl_debug_read_tc_timeline(tl.ctypes.data_as(ctypes.c_void_p)) == 0
+    names = {0: "sm:s_full", 1: "sm:ld_done", 2: "sm:computed", 3: "sm:p_free", 4: "sm:stored", 5: "sc:k_full", 6: "sc:s_free",
+             7: "sc:issued", 8: "pv0:p_full", 9: "pv0:issued", 10: "pv1:p_full", 11: "pv1:issued", 12: "pv2:p_full",
+             13: "pv2:issued", 14: "pv3:p_full", 15: "pv3:issued", 16: "pv:t_full", 17: "fw:p_full", 19: "pr:k_issued", 20: "pr:t_issued"}
+    for rank in (0, 2):
+      print(f"--- timeline, cluster 0 rank {rank}: (round, event) sorted by time, cycles relative to round {100}'s first event")
+      ev = []
+      for r in range(0, 6):
+        for e, nm in names.items():
+          if tl[rank, r, e] > 0: ev.append((int(tl[rank, r, e]), f"r{r}:{nm}"))
+      ev.sort()
+      t0 = ev[0][0]
+      line = []
+      for t, nm in ev:
+        line.append(f"{t - t0:6d} {nm}")
+      for k in range(0, len(line), 4): print("   ".join(f"{x:26s}" for x in line[k:k + 4]))
