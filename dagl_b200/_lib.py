@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdagl_b200.so")
+LIB_PATH = os.environ.get("DAGL_B200_LIB") or os.path.join(_HERE, "libdagl_b200.so")   # env override: A/B builds in development
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC1, IMPL_TC4 = 0, 1, 2, 3, 4
 IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC, "tc1": IMPL_TC1, "tc4": IMPL_TC4}

@@ -1083,6 +1083,12 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 // (rowmax pre-pass) as v2.
 //   TMEM: O [0,208) | Qh [208,312) | Ql [312,416) | S0 [416,464) | S1 [464,512)
 // =============================================================================================
+#ifndef V4_OPT_PREWAIT
+#define V4_OPT_PREWAIT 0
+#endif
+#ifndef V4_OPT_WARP_ARRIVE
+#define V4_OPT_WARP_ARRIVE 1
+#endif
 constexpr int V4_THREADS = TC_THREADS + 96;                 // + forwarder warp + score-MMA issuer warp + K loader warp
 constexpr int V4_KST = 2, V4_TST = 3, V4_TSLOTS = 4;
 constexpr int V4_PSLOTS = 8;                                // P slots: (producer rank) + 4 * (round parity): double buffered
@@ -1152,10 +1158,10 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     mbar_init(q_ready, 128);
     for (int i = 0; i < 2; ++i) {
       mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-      mbar_init(s_full + i, 1); mbar_init(s_free + i, 384);
+      mbar_init(s_full + i, 1); mbar_init(s_free + i, V4_OPT_WARP_ARRIVE ? 12 : 384);
     }
     for (int i = 0; i < V4_TST; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1); }
-    for (int i = 0; i < V4_PSLOTS; ++i) { mbar_init(p_full + i, (i & 3) == rank ? 384 : 1); mbar_init(p_free + i, 4); }
+    for (int i = 0; i < V4_PSLOTS; ++i) { mbar_init(p_full + i, (i & 3) == rank ? (V4_OPT_WARP_ARRIVE ? 12 : 384) : 1); mbar_init(p_free + i, 4); }
     mbar_init(pv_last, 1);
     mbar_init_fence();
   }
@@ -1212,9 +1218,6 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   } else if (warp == 1) {
     // ===================== P.V MMA issuer =====================
     if (elect_one()) {
-      uint32_t p_free_prod[4];                                             // p_free[r] (parity 0) in the producer CTA r
-#pragma unroll
-      for (int r = 0; r < 4; ++r) p_free_prod[r] = mapa(smem_u32(p_free + r), (uint32_t)r);
       uint32_t g_idesc[2], g_col[2], g_off[2];
       uint64_t g_bd[2];
 #pragma unroll
@@ -1228,50 +1231,82 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         const uint32_t lbo = gp.vertical ? (uint32_t)V4_TSEG_BYTES : 32u;
         g_bd[sl] = ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
       }
-      uint32_t tstage = 0;
-      int ts = 0;
+      // The barrier work of tile j+1 (theta rows of a new pair, P tile) is done between the k-steps of tile j, so the
+      // tensor pipe has queued work while this thread sits in try_wait / expect_tx; the waits normally pass at once.
+      // The loop is unrolled over the producer rank u = j & 3 so that all slot / barrier addresses are immediates.
+      uint32_t p_free_prod[4];                                               // p_free[r] (parity 0) in the producer CTA r
+#pragma unroll
+      for (int r = 0; r < 4; ++r) p_free_prod[r] = mapa(smem_u32(p_free + r), (uint32_t)r);
+      const uint32_t t_base = smem_u32(smem + S4_T), p_base = smem_u32(smem + S4_P);
+      int w_ts = -1; uint32_t w_ph = 1u;                                     // theta stage / phase of the pair last waited for
+      int i_ts = -1;                                                         // theta stage of the pair being issued
+#define V4_PREWAIT(JN, UN, PN)                                                                            \
+      do {                                                                                                \
+        if (((UN) & 1) == 0) {                                                                            \
+          if (++w_ts == V4_TST) w_ts = 0;                                                                 \
+          if (w_ts == 0) w_ph ^= 1u;                                                                      \
+          { TRACE_T0(); mbar_wait(t_full + w_ts, w_ph); TRACE_ADD(tr_c); }                                \
+          if ((UN) == 0) TL(PN, 16);                                                                      \
+        }                                                                                                 \
+        const int ps_ = (UN) + 4 * ((PN) & 1);                                                            \
+        if ((UN) != rank) mbar_arrive_expect_tx(p_full + ps_, V4_FWD_BYTES);                              \
+        { TRACE_T0(); mbar_wait(p_full + ps_, (uint32_t)((PN) >> 1) & 1u); TRACE_ADD(tr_b); }            \
+        TL(PN, 8 + 2 * (UN));                                                                             \
+        tc_fence_after();                                                                                 \
+      } while (0)
+#ifdef DAGL_TC_TRACE
+      const uint32_t V4_FWD_BYTES = (g_tc_dbg_mode & 4) ? 16u : (uint32_t)P_SLOT_BYTES;
+      const bool skip_pv = (g_tc_dbg_mode & 2) != 0;
+#else
+      constexpr uint32_t V4_FWD_BYTES = P_SLOT_BYTES;
+      constexpr bool skip_pv = false;
+#endif
+      if (ntiles > 0) V4_PREWAIT(0, 0, 0);
       for (int p = 0; 4 * p < ntiles; ++p) {
+        const uint32_t pslot0 = p_base + (p & 1) * (4 * P_SLOT_BYTES);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = 4 * p + u;                                           // producer rank u, P slot u + 4 * (p & 1)
-          const int ps = u + 4 * (p & 1);
           if (j >= ntiles) break;
-          if ((u & 1) == 0) {                                                // a new tile pair: its theta rows
-            const int h = 2 * p + (u >> 1);
-            ts = h % V4_TST;
-            { TRACE_T0(); mbar_wait(t_full + ts, (uint32_t)(h / V4_TST) & 1u); TRACE_ADD(tr_c); }
-            tstage = smem_u32(smem + S4_T + ts * V4_TSTAGE_BYTES);
-            if (u == 0) TL(p, 16);
-          }
-          const uint32_t tile0 = tstage + (u & 1) * (TC_BN * 32);            // second tile of the pair: 48 pixels further
-          const uint32_t pbase = smem_u32(smem + S4_P + ps * P_SLOT_BYTES);
+          if ((u & 1) == 0 && ++i_ts == V4_TST) i_ts = 0;
+          const uint32_t tile0 = t_base + i_ts * V4_TSTAGE_BYTES + (u & 1) * (TC_BN * 32);   // 2nd tile of the pair: +48 pixels
           const uint32_t g_start0 = (tile0 + g_off[0]) >> 4, g_start1 = (tile0 + g_off[1]) >> 4;
-          const uint64_t ad0 = smem_desc(pbase, (TC_BM / 8) * 128, 128);
-#ifdef DAGL_TC_TRACE
-          if (u != rank && (g_tc_dbg_mode & 4)) mbar_arrive_expect_tx(p_full + ps, 16); else
-#endif
-          if (u != rank) mbar_arrive_expect_tx(p_full + ps, P_SLOT_BYTES);   // peer tile: arrives as a bulk copy
-          { TRACE_T0(); mbar_wait(p_full + ps, (uint32_t)(p >> 1) & 1u); TRACE_ADD(tr_b); }
-          TL(p, 8 + 2 * u);
-          tc_fence_after();
-#ifdef DAGL_TC_TRACE
-          if (!(g_tc_dbg_mode & 2))
-#endif
+          const uint64_t ad0 = smem_desc(pslot0 + u * P_SLOT_BYTES, (TC_BM / 8) * 128, 128);
+          const uint32_t acc0 = j > 0 ? 1u : 0u;
+          if (!skip_pv) {
 #pragma unroll
-          for (int ks = 0; ks < TC_BN / 16; ++ks) {
-            const uint64_t ad = ad0 + (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
-            const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t b0 = g_bd[0] | (uint64_t)((g_start0 + ks * 32) & 0x3FFF);      // 16 keys = 512 B further per k-step
-            const uint64_t b1 = g_bd[1] | (uint64_t)((g_start1 + ks * 32) & 0x3FFF);
-            mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], acc);            // the two groups share the P slab (A collector)
-            mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], acc);
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ad = ad0 + (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
+              const uint64_t b0 = g_bd[0] | (uint64_t)((g_start0 + ks * 32) & 0x3FFF);    // 16 keys = 512 B further per k-step
+              const uint64_t b1 = g_bd[1] | (uint64_t)((g_start1 + ks * 32) & 0x3FFF);
+              mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], ks > 0 ? 1u : acc0);         // the two groups share the P slab (A collector)
+              mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], ks > 0 ? 1u : acc0);
+            }
+          }
+#if V4_OPT_PREWAIT
+          if (j + 1 < ntiles) {
+            if (u == 3) V4_PREWAIT(j + 1, 0, p + 1); else V4_PREWAIT(j + 1, u + 1, p);
+          }
+#endif
+          if (!skip_pv) {
+            const uint64_t ad = ad0 + (uint64_t)(2 * 2 * (TC_BM / 8) * 128 >> 4);
+            const uint64_t b0 = g_bd[0] | (uint64_t)((g_start0 + 2 * 32) & 0x3FFF);
+            const uint64_t b1 = g_bd[1] | (uint64_t)((g_start1 + 2 * 32) & 0x3FFF);
+            mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], 1u);
+            mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], 1u);
           }
           if (j + 8 < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p & 1));   // slot may be refilled by its producer CTA (+4 barriers)
-          if ((u & 1) == 1 || j == ntiles - 1) mma_commit(t_empty + ts);
+          if ((u & 1) == 1 || j == ntiles - 1) mma_commit(t_empty + i_ts);
           if (j == ntiles - 1) mma_commit(pv_last);
+#if !V4_OPT_PREWAIT
+          if (j + 1 < ntiles) {
+            if (u == 3) V4_PREWAIT(j + 1, 0, p + 1); else V4_PREWAIT(j + 1, u + 1, p);
+          }
+#endif
           TL(p, 9 + 2 * u);
         }
       }
+#undef V4_PREWAIT
     }
   } else if (warp == TC_THREADS / 32 + 1) {
     // ===================== score MMA issuer (own tiles; A operands Qh, Ql from TMEM) =====================
@@ -1384,11 +1419,13 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     const bool want_mask = (mask_bits != nullptr) || (nnz != nullptr);
     const float neg_ref = -ref;
 
+    unsigned long long vmask_next = n_own > 0 ? __ldg(tilemask + (size_t)img * tg.NT + t_begin + rank) : 0ull;
     for (int i = 0; i < n_own; ++i) {
       const int s = i & 1;
       const uint32_t ph = (uint32_t)(i >> 1) & 1u;
       const int t = t_begin + 4 * i + rank;
-      const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
+      const unsigned vbits = (unsigned)(vmask_next >> (16 * sub)) & 0xffffu;
+      if (i + 1 < n_own) vmask_next = __ldg(tilemask + (size_t)img * tg.NT + t + 4);     // prefetched one tile ahead
       { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
       if (warp == 2 && lane == 0) TL(i, 0);
       tc_fence_after();
@@ -1401,7 +1438,12 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         for (int k = 0; k < 16; ++k) sv[k] = __uint_as_float(r0[k]);
       }
       tc_fence_before();
+#if V4_OPT_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free + s);               // one arrival per warp (12 per tile)
+#else
       mbar_arrive(s_free + s);
+#endif
       if (warp == 2 && lane == 0) TL(i, 1);
       unsigned mk = 0u;
       uint32_t pk[8];
@@ -1452,7 +1494,12 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       fence_async_smem();
+#if V4_OPT_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + rank + 4 * par);  // one arrival per warp
+#else
       mbar_arrive(p_full + rank + 4 * par);
+#endif
       if (warp == 2 && lane == 0) TL(i, 4);
 
       if (mask_bits != nullptr && qvalid && mk != 0u) {     // debug path only
