@@ -1749,8 +1749,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     DAGL_LAUNCH_CHECK();
     if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
       return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
-    if (int rc = launch_merge_rows(g, w.nsplit, 0, g.Nq, Opart, coef, Om, st)) return rc;
-    return launch_fold_rows(g, Om, a.y, /*shift_major=*/1, st);
+    return launch_fold_partials(g, w.nsplit, Opart, coef, a.y, st);
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   if (int rc = prof_begin(st)) return rc;

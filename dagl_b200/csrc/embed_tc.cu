@@ -28,17 +28,22 @@ constexpr int EB_N = 208;                          // 196 padded to 13 * 16
 constexpr int EB_SEG_PIX = 144;                    // 128 + 6 (kx) + 7 (alignment) rounded up to 8
 constexpr int EB_SEG_BYTES = EB_SEG_PIX * 32;      // 4608
 constexpr int EB_G_BYTES = 2 * KS * EB_SEG_BYTES;  // hi | lo, 7 rows each: 64512
-constexpr int EB_WPART_BYTES = EB_N * 16 * 2;      // one tap, one part: 6656
+constexpr int EB_N0 = 112, EB_N1 = EB_N - EB_N0;   // the 208 outputs are split over two CTAs (N = 112 / 96): 2 CTAs per SM overlap
+                                                   // the halo load, MMA and epilogue phases of different tiles
+constexpr int EB_WPART_BYTES = EB_N * 16 * 2;      // one tap, one part (hi or lo), all 208 outputs: 6656
 constexpr int EB_WTAP_BYTES = 2 * EB_WPART_BYTES;  // hi | lo: 13312
-constexpr int EB_WSTAGES = 3;
+// packed weights: [output half][tap][hi | lo][2 k-chunks][rows of the half][8 ch] so that a CTA streams only its half
+constexpr int EB_WTAP0_BYTES = 2 * EB_N0 * 32;     // 7168: one tap of output half 0 (hi | lo)
+constexpr int EB_WTAP1_BYTES = 2 * EB_N1 * 32;     // 6144
+constexpr int EB_WHALF1_OFF = KK * EB_WTAP0_BYTES; // start of output half 1 in the packed array
+constexpr int EB_WSTAGE_BYTES = EB_WTAP0_BYTES;
+constexpr int EB_WSTAGES = 5;
 constexpr int EB_SM_G = 0;
 constexpr int EB_SM_W = EB_G_BYTES;                                  // 64512 = 63 * 1024
-constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WTAP_BYTES;      // 104448
+constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;    // 100352
 constexpr int EB_SM_TOTAL = EB_SM_BAR + 128;
 constexpr int EB_THREADS = 192;
 constexpr int EB_TMEM_COLS = 256;                  // per CTA: main (hi.hi) accumulator at column 0, cross-term accumulator at 128
-constexpr int EB_N0 = 112, EB_N1 = EB_N - EB_N0;   // the 208 outputs are split over two CTAs (N = 112 / 96): 2 CTAs per SM overlap
-                                                   // the halo load, MMA and epilogue phases of different tiles
 static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
 
 struct EmbGeom {
@@ -72,7 +77,7 @@ __global__ void absmax_flat_kernel(const float* __restrict__ x, int n, unsigned*
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-// fc weight [196][784] (e, (c,ky,kx)) -> per tap: [hi|lo][2 chunks][26 row groups][8 rows (e)][8 c] fp16
+// fc weight [196][784] (e, (c,ky,kx)) -> per output half and tap: [hi|lo][2 chunks][rows/8 row groups][8 rows (e)][8 c] fp16
 __global__ void __launch_bounds__(256)
 pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, uint8_t* __restrict__ out) {
   const int tap = blockIdx.x;
@@ -93,9 +98,11 @@ pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, u
       hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    uint8_t* base = out + (size_t)tap * EB_WTAP_BYTES + (size_t)o * 16;      // [kc][e] chunk order == K-major no-swizzle
+    const int half = e >= EB_N0, el = e - half * EB_N0, rows = half ? EB_N1 : EB_N0;
+    uint8_t* base = out + (half ? EB_WHALF1_OFF + (size_t)tap * EB_WTAP1_BYTES : (size_t)tap * EB_WTAP0_BYTES) +
+                    (size_t)(kc * rows + el) * 16;                             // [kc][e] chunk order == K-major no-swizzle
     *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + EB_WPART_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(base + rows * 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -142,10 +149,10 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
   uint64_t* g_full = bars + 0;
-  uint64_t* w_full = bars + 1;                 // [3]
-  uint64_t* w_empty = bars + 4;                // [3]
-  uint64_t* d_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* w_full = bars + 1;                 // [EB_WSTAGES]
+  uint64_t* w_empty = bars + 1 + EB_WSTAGES;   // [EB_WSTAGES]
+  uint64_t* d_full = bars + 1 + 2 * EB_WSTAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 + 2 * EB_WSTAGES);
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
@@ -183,12 +190,14 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
           bulk_g2s(smem + EB_SM_G + (part * KS + ky) * EB_SEG_BYTES, src + (size_t)first * 32, EB_SEG_BYTES, g_full);
         }
       }
+      const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
+      const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
       for (int t = 0; t < KK; ++t) {
         const int s = t % EB_WSTAGES;
         const uint32_t ph = (uint32_t)(t / EB_WSTAGES) & 1u;
         mbar_wait(w_empty + s, ph ^ 1u);
-        mbar_arrive_expect_tx(w_full + s, EB_WTAP_BYTES);
-        bulk_g2s(smem + EB_SM_W + s * EB_WTAP_BYTES, wp + (size_t)t * EB_WTAP_BYTES, EB_WTAP_BYTES, w_full + s);
+        mbar_arrive_expect_tx(w_full + s, tap_bytes);
+        bulk_g2s(smem + EB_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
       }
     }
   } else if (warp == 1) {
@@ -210,9 +219,9 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
                                ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
         const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
                                ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WTAP_BYTES) + (e0 / 8) * 128;   // rows e0.. of the packed tap
-        const uint64_t db_hi = smem_desc(w_hi, (EB_N / 8) * 128, 128);
-        const uint64_t db_lo = smem_desc(w_hi + EB_WPART_BYTES, (EB_N / 8) * 128, 128);
+        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WSTAGE_BYTES);                  // this CTA's output half only
+        const uint64_t db_hi = smem_desc(w_hi, (ncols / 8) * 128, 128);
+        const uint64_t db_lo = smem_desc(w_hi + ncols * 32, (ncols / 8) * 128, 128);
         // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
         // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
         // the epilogue adds the two in round-to-nearest fp32.

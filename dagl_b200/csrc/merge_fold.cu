@@ -73,6 +73,44 @@ __global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ O
   y[i] = sum / cntf;
 }
 
+// Fused merge + fold for the fixed-reference kernels (shift-major partial rows): every output pixel gathers its <= 2x2
+// covering queries straight from the key-split partials, scaled by coef[q] = 1 / sum of the row-sum partials
+// (dagl.py:265-272).  Thread = (pixel, 4 channels); fixed summation order, no atomics.
+__global__ void __launch_bounds__(256)
+fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const float* __restrict__ coef,
+                     float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = g.B * 4 * g.Nk;
+  if (i >= total) return;
+  const int px = i % g.W, py = (i / g.W) % g.H, c4 = (i / g.Nk) & 3, img = i / (4 * g.Nk);
+  const int qy_lo = py >> 2, qy_hi = min(g.nqy - 1, (py + PADK) >> 2);
+  const int qx_lo = px >> 2, qx_hi = min(g.nqx - 1, (px + PADK) >> 2);
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int qy = qy_lo; qy <= qy_hi; ++qy)
+    for (int qx = qx_lo; qx <= qx_hi; ++qx) {
+      const int q = qy * g.nqx + qx;
+      const int sh = (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < nsplit; ++s) {
+        const size_t row = ((size_t)img * nsplit + s) * g.Nq + q;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Opart + row * VD + sh * CI) + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const float c = __ldg(coef + (size_t)img * nsplit * g.Nq + q);      // same value for every split
+      sum.x = fmaf(c, acc.x, sum.x); sum.y = fmaf(c, acc.y, sum.y); sum.z = fmaf(c, acc.z, sum.z); sum.w = fmaf(c, acc.w, sum.w);
+    }
+  const float inv = 1.f / (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
+  float* yo = y + ((size_t)img * CI + 4 * c4) * g.Nk + (size_t)py * g.W + px;
+  yo[0] = sum.x * inv; yo[(size_t)g.Nk] = sum.y * inv; yo[2 * (size_t)g.Nk] = sum.z * inv; yo[3 * (size_t)g.Nk] = sum.w * inv;
+}
+
+int launch_fold_partials(const Geom& g, int nsplit, const float* Opart, const float* coef, float* y, cudaStream_t st) {
+  const int total = g.B * 4 * g.Nk;
+  fold_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, nsplit, Opart, coef, y);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t merge_fold_scratch_bytes(const Geom& g) { return (size_t)g.B * g.Nq * VD * sizeof(float); }
 
 // Omerged rows [q_begin, q_end) of every image <- sum over splits of coef * partial
