@@ -17,6 +17,7 @@ EXPORTS = [
     "dagl_graph_attend_workspace_bytes", "dagl_graph_attend_f32", "dagl_ce_workspace_view",
     "dagl_last_impl", "dagl_last_launch_count", "dagl_profile_enable", "dagl_profile_read",
     "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
+    "dagl_ces_heads_forward_f32",
 ]
 
 
@@ -52,6 +53,8 @@ def lib() -> C.CDLL:
     L.dagl_ce_host_staging_bytes.argtypes = [i32, i32, i32, i32]
     L.dagl_ce_forward_f32.restype = i32
     L.dagl_ce_forward_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, vp, sz, i32, vp]
+    L.dagl_ces_heads_forward_f32.restype = i32
+    L.dagl_ces_heads_forward_f32.argtypes = [C.POINTER(C.POINTER(DaglCEWeights)), i32, vp, vp, i32, i32, i32, vp, sz, i32, vp]
     L.dagl_ce_forward_debug_f32.restype = i32
     L.dagl_ce_forward_debug_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, vp, sz, i32, vp, vp, vp]
     L.dagl_ce_forward_host_f32.restype = i32

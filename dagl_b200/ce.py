@@ -242,6 +242,39 @@ class CE(nn.Module):
         return y_host
 
 
+def stage_heads_forward(heads, x: torch.Tensor) -> torch.Tensor:
+    """``torch.cat([h(x) for h in heads], dim=1)`` of dagl.py:114-118 in one C-ABI call
+    (``dagl_ces_heads_forward_f32``): every head writes its 16 channels directly into the
+    concatenated [B, 16*len(heads), H, W] buffer."""
+    heads = list(heads)
+    h0 = heads[0]
+    for h in heads:
+        h._check_input(x)
+    if not x.is_cuda:
+        raise RuntimeError("dagl_b200.CE has no CPU path: input must be a CUDA tensor")
+    L = _lib.lib()
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    with torch.cuda.device(x.device):
+        ycat = torch.empty(B, h0.inter_channels * len(heads), H, W, dtype=torch.float32, device=x.device)
+        ws = _workspace(x.device, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+        structs, keep = [], []
+        for h in heads:
+            w, k = h._weights(x.device)
+            structs.append(w)
+            keep.append(k)
+        arr = (C.POINTER(_lib.DaglCEWeights) * len(heads))(*[C.pointer(w) for w in structs])
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = L.dagl_ces_heads_forward_f32(arr, len(heads), x.data_ptr(), ycat.data_ptr(), B, H, W, ws.data_ptr(),
+                                          ws.numel(), _lib.IMPL_BY_NAME[h0.impl], stream)
+        _lib.check(rc, "dagl_ces_heads_forward_f32")
+        impl = L.dagl_last_impl().decode()
+        for h in heads:
+            h.last_impl = impl
+        h0.last_launches = L.dagl_last_launch_count()
+    return ycat
+
+
 class _ResBlock(nn.Module):
     """conv3x3 - PReLU - conv3x3, + x  (reference common.ResBlock, common.py:59-79,
     same parameter names: body.0 / body.1 / body.2)."""
@@ -268,8 +301,8 @@ class CES(nn.Module):
             setattr(self, f"c{s}_c", nn.Conv2d(in_channels, in_channels, 1, 1, 0))
 
     def _stage(self, s: int, x: torch.Tensor) -> torch.Tensor:
-        heads = [getattr(self, f"c{s}_{h}")(x) for h in (1, 2, 3, 4)]
-        return getattr(self, f"c{s}_c")(torch.cat(heads, dim=1)) + x
+        heads = [getattr(self, f"c{s}_{h}") for h in (1, 2, 3, 4)]
+        return getattr(self, f"c{s}_c")(stage_heads_forward(heads, x)) + x
 
     def forward(self, x):
         out = self._stage(1, x)

@@ -112,7 +112,7 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
 
 static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B, int H, int W, void* ws,
                         size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz,
-                        float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0) {
+                        float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0, long long y_img_stride = 0) {
   call_state().launches = 0;
   call_state().impl = "none";
   int rc = check_weights(w);
@@ -123,7 +123,14 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     call_state().err = "null buffer";
     return DAGL_ERR_INVALID_ARG;
   }
-  const Geom g = make_geom(B, w->in_channels, H, W);
+  Geom g = make_geom(B, w->in_channels, H, W);
+  if (y_img_stride != 0) {
+    if (y_img_stride < g.y_img_stride) {
+      call_state().err = "output image stride smaller than one [16,H,W] result";
+      return DAGL_ERR_INVALID_ARG;
+    }
+    g.y_img_stride = y_img_stride;
+  }
   const WsLayout L = ws_layout(g);
   if (ws_bytes < L.total) {
     call_state().err = "workspace too small";
@@ -187,6 +194,26 @@ int32_t dagl_ce_forward_debug_f32(const DaglCEWeights* w, const float* b, float*
                                   void* workspace, size_t workspace_bytes, int32_t impl, void* stream,
                                   uint32_t* mask_bits, int32_t* nnz) {
   return forward_impl(w, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), mask_bits, nnz);
+}
+
+int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_heads, const float* b, float* ycat,
+                                   int32_t B, int32_t H, int32_t W, void* workspace, size_t workspace_bytes,
+                                   int32_t impl, void* stream) {
+  if (!heads || n_heads <= 0 || n_heads > 16) {
+    call_state().err = "bad head list";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  int total_launches = 0;
+  const long long stride = (long long)n_heads * CI * H * W;
+  for (int h = 0; h < n_heads; ++h) {
+    float* yh = ycat ? ycat + (size_t)h * CI * H * W : nullptr;
+    const int rc = forward_impl(heads[h], b, yh, B, H, W, workspace, workspace_bytes, impl,
+                                static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, 0, 0, stride);
+    if (rc) return rc;
+    total_launches += call_state().launches;
+  }
+  call_state().launches = total_launches;
+  return 0;
 }
 
 size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {

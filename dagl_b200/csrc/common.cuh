@@ -22,6 +22,7 @@ struct Geom {
   int B, C, H, W;
   int nqy, nqx, Nq, Nk;
   int qpad_top, qpad_left;       // SAME pad of the stride-4 unfold (dagl.py:126-136)
+  long long y_img_stride;        // elements between consecutive images of the OUTPUT (CI*Nk, or the channel-concatenated stage buffer)
 };
 
 __host__ __device__ inline int same_pad_before(int n, int k, int s) {
@@ -38,6 +39,7 @@ inline Geom make_geom(int B, int C, int H, int W) {
   g.Nq = g.nqy * g.nqx; g.Nk = H * W;
   g.qpad_top = same_pad_before(H, KS, SQ);
   g.qpad_left = same_pad_before(W, KS, SQ);
+  g.y_img_stride = (long long)CI * H * W;
   return g;
 }
 

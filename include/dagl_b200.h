@@ -79,6 +79,15 @@ int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y,
                             void* workspace, size_t workspace_bytes,
                             int32_t impl, void* stream);
 
+/* The heads of one CES stage (reference CES.forward, dagl.py:114-118: `torch.cat([c_1(x), .., c_4(x)], dim=1)`):
+ * head h of `heads[0..n_heads)` runs on the shared input b[B,C,H,W] and writes its 16 channels straight into
+ * channels [16h, 16h+16) of ycat[B, 16*n_heads, H, W] — the concatenation is never a separate copy.  The 1x1 merge
+ * conv and the residual of the stage stay with the caller.  Workspace: dagl_ce_workspace_bytes() (reused per head). */
+int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_heads, const float* b, float* ycat,
+                                   int32_t B, int32_t H, int32_t W,
+                                   void* workspace, size_t workspace_bytes,
+                                   int32_t impl, void* stream);
+
 /* Same, and also reports the neighbour selection of dagl.py:256-257:
  *   mask_bits [B][Nq][ceil(Nk/32)] : bit j of word w set <=> key 32w+j is a
  *                                    neighbour of the query (mask_b != 0)

@@ -345,3 +345,23 @@ def test_other_softmax_scale(dev, rand_weights, impl):
             assert rel_err(y.cpu(), yref) <= REL_TOL, scale
     finally:
         O.SOFTMAX_SCALE = old
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc4"])
+def test_stage_entry_equals_cat_of_heads(dev, impl):
+    """dagl_ces_heads_forward_f32 (heads write into the concatenated buffer) == torch.cat of single-head calls
+    (CES.forward, dagl.py:114-118), bit for bit; B = 2 exercises the image stride of the shared buffer."""
+    import dagl_b200
+    from dagl_b200.ce import stage_heads_forward
+    heads = []
+    for h in range(4):
+        ce = dagl_b200.CE(in_channels=64, impl=impl)
+        ce.load_state_dict(O.init_ce_params(40 + h))
+        heads.append(ce.to(dev).eval())
+    x = torch.randn(2, 64, 22, 27, generator=torch.Generator().manual_seed(8)).to(dev)
+    with torch.no_grad():
+        want = torch.cat([h(x) for h in heads], dim=1)
+        got = stage_heads_forward(heads, x)
+    assert got.shape == (2, 64, 22, 27)
+    assert torch.equal(got, want)
+    assert heads[0].last_impl == impl
