@@ -17,7 +17,7 @@ EXPORTS = [
     "dagl_graph_attend_workspace_bytes", "dagl_graph_attend_f32", "dagl_ce_workspace_view",
     "dagl_last_impl", "dagl_last_launch_count", "dagl_profile_enable", "dagl_profile_read",
     "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
-    "dagl_ces_heads_forward_f32",
+    "dagl_ces_heads_forward_f32", "dagl_ce_packed_weights_bytes", "dagl_ce_pack_weights_f32",
 ]
 
 
@@ -26,7 +26,8 @@ class DaglCEWeights(C.Structure):
         "g_w", "g_b", "theta_w", "theta_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
         "thr_w", "thr_b", "bias_w", "bias_b")] + [
         ("in_channels", C.c_int32), ("inter_channels", C.c_int32), ("ksize", C.c_int32),
-        ("stride_q", C.c_int32), ("stride_k", C.c_int32), ("softmax_scale", C.c_float)]
+        ("stride_q", C.c_int32), ("stride_k", C.c_int32), ("softmax_scale", C.c_float),
+        ("packed_fc", C.c_void_p)]
 
 
 _lib = None
@@ -53,6 +54,10 @@ def lib() -> C.CDLL:
     L.dagl_ce_host_staging_bytes.argtypes = [i32, i32, i32, i32]
     L.dagl_ce_forward_f32.restype = i32
     L.dagl_ce_forward_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, vp, sz, i32, vp]
+    L.dagl_ce_packed_weights_bytes.restype = sz
+    L.dagl_ce_packed_weights_bytes.argtypes = []
+    L.dagl_ce_pack_weights_f32.restype = i32
+    L.dagl_ce_pack_weights_f32.argtypes = [C.POINTER(DaglCEWeights), vp, sz, vp]
     L.dagl_ces_heads_forward_f32.restype = i32
     L.dagl_ces_heads_forward_f32.argtypes = [C.POINTER(C.POINTER(DaglCEWeights)), i32, vp, vp, i32, i32, i32, vp, sz, i32, vp]
     L.dagl_ce_forward_debug_f32.restype = i32
@@ -75,7 +80,7 @@ def lib() -> C.CDLL:
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32
     L.dagl_profile_read.argtypes = [C.POINTER(C.c_float), i32]
-    if L.dagl_abi_version() != 1:
+    if L.dagl_abi_version() != 2:
         raise RuntimeError("libdagl_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -68,6 +68,9 @@ class CE(nn.Module):
         self.bias_conv = nn.Conv2d(in_channels, 1, kernel_size=ksize, stride=stride_1, padding=0)
         self.last_impl: Optional[str] = None
         self.last_launches: int = 0
+        self.cache_packed_weights = True      # eval mode: pack fc1/fc2 for the tensor cores once, not per call
+        self._packed_buf: Optional[torch.Tensor] = None
+        self._packed_key = None
 
     # -- C-ABI plumbing -------------------------------------------------------
     def _weights(self, device: torch.device) -> Tuple[_lib.DaglCEWeights, list]:
@@ -80,7 +83,10 @@ class CE(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
+        packed = (self._packed_fc(device) if self.cache_packed_weights and not self.training and self.impl != "simt"
+                  else None)
         w = _lib.DaglCEWeights(
+            packed_fc=packed,
             g_w=ptr(self.g.weight), g_b=ptr(self.g.bias),
             theta_w=ptr(self.theta.weight), theta_b=ptr(self.theta.bias),
             fc1_w=ptr(self.fc1[0].weight), fc1_b=ptr(self.fc1[0].bias),
@@ -90,6 +96,24 @@ class CE(nn.Module):
             in_channels=self.in_channels, inter_channels=self.inter_channels, ksize=self.ksize,
             stride_q=self.stride_1, stride_k=self.stride_2, softmax_scale=float(self.softmax_scale))
         return w, keep
+
+    def _packed_fc(self, device: torch.device) -> Optional[int]:
+        """fc1/fc2 packed once for the tensor-core embedding kernel (``dagl_ce_pack_weights_f32``) and reused while the
+        weights are unchanged (eval mode only; keyed on the tensors' storage and in-place version counters, so
+        ``load_state_dict`` / optimiser steps invalidate it)."""
+        w1, w2 = self.fc1[0].weight, self.fc2[0].weight
+        key = (str(device), w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        if self._packed_key != key:
+            L = _lib.lib()
+            buf = torch.empty(L.dagl_ce_packed_weights_bytes(), dtype=torch.uint8, device=device)
+            t1, t2 = w1.detach().contiguous(), w2.detach().contiguous()
+            tmp = _lib.DaglCEWeights(fc1_w=t1.data_ptr(), fc2_w=t2.data_ptr(), inter_channels=self.inter_channels,
+                                     ksize=self.ksize)
+            rc = L.dagl_ce_pack_weights_f32(C.byref(tmp), buf.data_ptr(), buf.numel(),
+                                            torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "dagl_ce_pack_weights_f32")
+            self._packed_buf, self._packed_key = buf, key
+        return self._packed_buf.data_ptr()
 
     def _check_input(self, b: torch.Tensor) -> None:
         if not isinstance(b, torch.Tensor) or b.dim() != 4:

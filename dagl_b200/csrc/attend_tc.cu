@@ -237,7 +237,7 @@ pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsi
 __device__ long long g_tc_trace[1024][24];
 __device__ long long g_tc_tl[4][32][24];   // tc4 timeline: [cluster rank][round - TL_P0][event], cycles since CTA start (cluster 0 only)
 #define TL_P0 100
-#define TL(round, ev) do { const int _r = (round) - TL_P0; if (tl_on && _r >= 0 && _r < 32) g_tc_tl[rank][_r][ev] = clock64() - tr_start; } while (0)
+#define TL(round, ev) do { const int _r = (round) - TL_P0; if (tl_on && _r >= 0 && _r < 32) g_tc_tl[rank][_r][ev] = clock64() - tl_base; } while (0)
 __device__ int g_tc_dbg_mode = 0;      // bit0: skip the S MMAs, bit1: skip the P.V MMAs (timing experiments only)
 #define TRACE_T0() long long _t0 = clock64()
 #define TRACE_ADD(var) (var) += clock64() - _t0
@@ -1171,6 +1171,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
+#ifdef DAGL_TC_TRACE
+  const long long tl_base = clock64();      // common time origin of the cluster's timelines: right after the cluster barrier
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1252,12 +1255,14 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         if ((UN) != rank) mbar_arrive_expect_tx(p_full + ps_, V4_FWD_BYTES);                              \
         { TRACE_T0(); mbar_wait(p_full + ps_, (uint32_t)((PN) >> 1) & 1u); TRACE_ADD(tr_b); }            \
         TL(PN, 8 + 2 * (UN));                                                                             \
-        tc_fence_after();                                                                                 \
+        if (!skip_fence) tc_fence_after();                                                                \
       } while (0)
 #ifdef DAGL_TC_TRACE
       const uint32_t V4_FWD_BYTES = (g_tc_dbg_mode & 4) ? 16u : (uint32_t)P_SLOT_BYTES;
       const bool skip_pv = (g_tc_dbg_mode & 2) != 0;
+      const bool skip_fence = (g_tc_dbg_mode & 64) != 0;
 #else
+      constexpr bool skip_fence = false;
       constexpr uint32_t V4_FWD_BYTES = P_SLOT_BYTES;
       constexpr bool skip_pv = false;
 #endif
@@ -1295,8 +1300,18 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
             mma_f16_ss_a_fill(g_col[0], ad, b0, g_idesc[0], 1u);
             mma_f16_ss_a_lastuse(g_col[1], ad, b1, g_idesc[1], 1u);
           }
+#ifdef DAGL_TC_TRACE
+          if (g_tc_dbg_mode & 32) {                                              // timing experiment: plain arrives instead of tcgen05.commit
+            if (j + 8 < ntiles)
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(p_free_prod[u] + 32 * (p & 1)) : "memory");
+            if ((u & 1) == 1 || j == ntiles - 1) mbar_arrive(t_empty + i_ts);
+          } else {
+#endif
           if (j + 8 < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p & 1));   // slot may be refilled by its producer CTA (+4 barriers)
           if ((u & 1) == 1 || j == ntiles - 1) mma_commit(t_empty + i_ts);
+#ifdef DAGL_TC_TRACE
+          }
+#endif
           if (j == ntiles - 1) mma_commit(pv_last);
 #if !V4_OPT_PREWAIT
           if (j + 1 < ntiles) {
@@ -1372,6 +1387,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
           asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(dst[u] + par * 4 * P_SLOT_BYTES), "r"(src0 + par * 4 * P_SLOT_BYTES), "r"(fwd_bytes),
                          "r"(rbar[u] + par * 32) : "memory");
+        TL(i, 18);
       }
     }
   } else {

@@ -156,7 +156,7 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     if ((rc = launch_kbar(g, kpart, L.kblocks_simt, Kbar, st))) return rc;
   } else {
     if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, K, absmax, base + L.embed,
-                              L.attend - L.embed, st))) return rc;
+                              L.attend - L.embed, w->packed_fc, st))) return rc;
     Kbar = nullptr;      // formed inside the tensor-core launcher from the key-pack column sums
   }
 
@@ -214,6 +214,22 @@ int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_
   }
   call_state().launches = total_launches;
   return 0;
+}
+
+size_t dagl_ce_packed_weights_bytes(void) { return embed_tc_packed_weights_bytes(); }
+
+int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream) {
+  call_state().launches = 0;
+  if (!w || !w->fc1_w || !w->fc2_w || !packed) {
+    call_state().err = "null pointer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  if (w->inter_channels != CI || w->ksize != KS) {
+    call_state().err = "unsupported CE configuration";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  const int rc = launch_pack_fc_weights(w->fc1_w, w->fc2_w, packed, packed_bytes, static_cast<cudaStream_t>(stream));
+  return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
 }
 
 size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {

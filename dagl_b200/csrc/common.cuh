@@ -98,9 +98,11 @@ int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kba
 // tensor-core embeddings (embed_tc.cu): Q, K fp32
 size_t embed_tc_workspace_bytes(const Geom& g);
 int embed_tc_num_tiles(const Geom& g);
+size_t embed_tc_packed_weights_bytes();
+int launch_pack_fc_weights(const float* fc1_w, const float* fc2_w, void* packed, size_t packed_bytes, cudaStream_t st);
 int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                     const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    cudaStream_t st);
+                    const void* prepacked, cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;

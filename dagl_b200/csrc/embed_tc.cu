@@ -288,27 +288,22 @@ static inline size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t embed_tc_workspace_bytes(const Geom& g) {
   const EmbGeom eg = emb_geom(g);
-  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64);
+  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64);   // = maps + embed_tc_packed_weights_bytes()
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
-// Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
-// absmax slot 3 (max |G|) must already be filled.
-int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
-  const EmbGeom eg = emb_geom(g);
-  if (ws_bytes < embed_tc_workspace_bytes(g)) {
-    call_state().err = "embed (tc) workspace too small";
+// packed fc1 | packed fc2 | wmax[2]
+static size_t packed_w_bytes() { return align_up_e((size_t)KK * EB_WTAP_BYTES); }
+size_t embed_tc_packed_weights_bytes() { return 2 * packed_w_bytes() + align_up_e(64); }
+
+int launch_pack_fc_weights(const float* fc1_w, const float* fc2_w, void* packed, size_t packed_bytes, cudaStream_t st) {
+  if (packed_bytes < embed_tc_packed_weights_bytes()) {
+    call_state().err = "packed-weights buffer too small";
     return -3;
   }
-  char* p = static_cast<char*>(ws);
-  uint8_t* ghi = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
-  uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
-  uint8_t* w1 = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)KK * EB_WTAP_BYTES);
-  uint8_t* w2 = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)KK * EB_WTAP_BYTES);
-  unsigned* wmax = reinterpret_cast<unsigned*>(p);
-
+  uint8_t* w1 = static_cast<uint8_t*>(packed);
+  uint8_t* w2 = w1 + packed_w_bytes();
+  unsigned* wmax = reinterpret_cast<unsigned*>(w2 + packed_w_bytes());
   DAGL_CUDA_OK(cudaMemsetAsync(wmax, 0, 2 * sizeof(unsigned), st));
   absmax_flat_kernel<<<64, 256, 0, st>>>(fc1_w, ED * VD, wmax + 0);
   DAGL_LAUNCH_CHECK();
@@ -318,6 +313,30 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   DAGL_LAUNCH_CHECK();
   pack_fc_kernel<<<KK, 256, 0, st>>>(fc2_w, wmax + 1, w2);
   DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
+// absmax slot 3 (max |G|) must already be filled.  `prepacked` (nullable): weights packed by launch_pack_fc_weights.
+int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
+                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
+                    const void* prepacked, cudaStream_t st) {
+  const EmbGeom eg = emb_geom(g);
+  if (ws_bytes < embed_tc_workspace_bytes(g)) {
+    call_state().err = "embed (tc) workspace too small";
+    return -3;
+  }
+  char* p = static_cast<char*>(ws);
+  uint8_t* ghi = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
+  uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
+  const uint8_t* packed = static_cast<const uint8_t*>(prepacked);
+  if (packed == nullptr) {
+    if (int rc = launch_pack_fc_weights(fc1_w, fc2_w, p, embed_tc_packed_weights_bytes(), st)) return rc;
+    packed = reinterpret_cast<const uint8_t*>(p);
+  }
+  const uint8_t* w1 = packed;
+  const uint8_t* w2 = packed + packed_w_bytes();
+  const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
   pack_g_kernel<<<dim3((eg.NPG + 255) / 256, g.B), 256, 0, st>>>(g, eg, G, absmax, ghi, glo);
   DAGL_LAUNCH_CHECK();
 

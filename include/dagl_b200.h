@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DAGL_ABI_VERSION 1
+#define DAGL_ABI_VERSION 2
 
 enum {
   DAGL_OK = 0,
@@ -63,6 +63,8 @@ typedef struct DaglCEWeights {
   int32_t stride_q;         /* must be 4  (stride_1)  */
   int32_t stride_k;         /* must be 1  (stride_2)  */
   float softmax_scale;      /* reference default 10   */
+  const void* packed_fc;    /* optional (may be NULL): fc1/fc2 pre-packed by dagl_ce_pack_weights_f32 for the
+                               tensor-core embedding kernel; saves the per-call weight packing at inference  */
 } DaglCEWeights;
 
 int32_t dagl_abi_version(void);
@@ -78,6 +80,14 @@ int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y,
                             int32_t B, int32_t H, int32_t W,
                             void* workspace, size_t workspace_bytes,
                             int32_t impl, void* stream);
+
+/* Optional weight pre-packing.  The library keeps no state between calls, so by default every forward re-packs
+ * fc1 / fc2 (fp32 [196][784]) into the fp16 hi/lo tensor-core operand images (~25 us).  A caller whose weights
+ * are constant (inference) can do it once: pack into a caller-owned device buffer of
+ * dagl_ce_packed_weights_bytes() and pass it as DaglCEWeights.packed_fc; it must be re-packed whenever fc1_w or
+ * fc2_w change.  Only the tensor-core implementations read it.                                                */
+size_t dagl_ce_packed_weights_bytes(void);
+int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream);
 
 /* The heads of one CES stage (reference CES.forward, dagl.py:114-118: `torch.cat([c_1(x), .., c_4(x)], dim=1)`):
  * head h of `heads[0..n_heads)` runs on the shared input b[B,C,H,W] and writes its 16 channels straight into

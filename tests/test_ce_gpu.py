@@ -365,3 +365,24 @@ def test_stage_entry_equals_cat_of_heads(dev, impl):
     assert got.shape == (2, 64, 22, 27)
     assert torch.equal(got, want)
     assert heads[0].last_impl == impl
+
+
+def test_packed_weight_cache_is_invalidated_by_weight_updates(dev, rand_weights):
+    """eval-mode CE packs fc1/fc2 once (dagl_ce_pack_weights_f32); an in-place weight update must re-pack."""
+    x = torch.randn(1, 64, 24, 20, generator=torch.Generator().manual_seed(4)).to(dev)
+    ce = make_ce(rand_weights, dev, "tc4")
+    with torch.no_grad():
+        y0 = ce(x)
+        assert ce._packed_key is not None
+        key0 = ce._packed_key
+        y0b = ce(x)
+        assert ce._packed_key == key0 and torch.equal(y0, y0b)          # cached, deterministic
+        ce.fc2[0].weight.mul_(1.25)                                      # in-place update bumps the version counter
+        y1 = ce(x)
+        assert ce._packed_key != key0
+    fresh = make_ce({k: (v * 1.25 if k == "fc2.0.weight" else v) for k, v in rand_weights.items()}, dev, "tc4")
+    fresh.cache_packed_weights = False                                   # per-call packing path
+    with torch.no_grad():
+        y2 = fresh(x)
+    assert torch.equal(y1, y2)
+    assert not torch.equal(y0, y1)

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string>
 #include <vector>
 #include "../dagl_b200/csrc/tc_utils.cuh"
 
@@ -422,6 +423,67 @@ static void run_rate_ct(const char* name, long long* dC) {
   printf("P8 %-34s N=%3d : %7.1f cyc/MMA (ideal %5.1f)\n", name, N, (double)mx / iters / 24, N / 2.0);
 }
 
+
+// P9: does tcgen05.mma issue run ahead of execution?  Issue CNT MMAs (N = 112, SS, MN-major sw32 B, A from smem with the
+// collector flags of the P.V loop when COLL != 0), read the clock, commit, read the clock, wait for completion.
+template <int CNT, int COLL>
+__global__ void __launch_bounds__(128) probe_issue(long long* __restrict__ out /*[grid][4]*/) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 32768; i += 128) reinterpret_cast<__half*>(smem)[i] = __float2half(((i * 37) % 17 - 8) * 0.0625f);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  if (warp_id_uniform() == 0 && elect_one()) {
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 32768;
+    constexpr uint32_t idesc = instr_desc(128, 112, FMT_F16, FMT_F16, 0, 1);
+    long long t_issue = 0, t_commit = 0, t_drain = 0, t_wait_done = 0;
+    for (int it = 0; it < 6; ++it) {
+      const long long t0 = clock64();
+#pragma unroll
+      for (int i = 0; i < CNT; ++i) {
+        const uint32_t d = tbase + (i % 3) * 112;
+        const uint64_t bd = smem_desc_ex(sb + (i % 7) * 32, 32, 256, 6, 0);
+        const uint64_t ad = smem_desc(sa + ((i / 2) % 3) * 4096, 2048, 128);
+        if (COLL == 0) mma_f16_ss(d, ad, bd, idesc, 1);
+        else if ((i & 1) == 0) mma_f16_ss_a_fill(d, ad, bd, idesc, 1);
+        else mma_f16_ss_a_lastuse(d, ad, bd, idesc, 1);
+      }
+      const long long t1 = clock64();
+      mma_commit(&bar[it & 1]);
+      const long long t2 = clock64();
+      mbar_wait(&bar[it & 1], (it >> 1) & 1);
+      const long long t3 = clock64();
+      mbar_wait(&bar[it & 1], (it >> 1) & 1);            // already complete: cost of a passing try_wait
+      const long long t4 = clock64();
+      if (it >= 2) { t_issue += t1 - t0; t_commit += t2 - t1; t_drain += t3 - t2; t_wait_done += t4 - t3; }
+    }
+    out[blockIdx.x * 4 + 0] = t_issue / 4; out[blockIdx.x * 4 + 1] = t_commit / 4;
+    out[blockIdx.x * 4 + 2] = t_drain / 4; out[blockIdx.x * 4 + 3] = t_wait_done / 4;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tbase);
+}
+
+template <int CNT, int COLL>
+static void run_issue(long long* dC) {
+  CK(cudaFuncSetAttribute(probe_issue<CNT, COLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  probe_issue<CNT, COLL><<<8, 128, 65536>>>(dC);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("P9 failed: %s\n", cudaGetErrorString(e)); exit(1); }
+  long long h[4];
+  CK(cudaMemcpy(h, dC, sizeof(h), cudaMemcpyDeviceToHost));
+  printf("P9 %2d MMAs (N=112 SS%s): issue %5lld cyc (%5.1f/MMA)  commit %4lld  drain after commit %5lld  passing try_wait %3lld   [exec model %d]\n",
+         CNT, COLL ? ", A collector" : "", h[0], (double)h[0] / CNT, h[1], h[2], h[3], CNT * 58);
+}
+
 static float h2f(__half h) { return __half2float(h); }
 
 int main(int argc, char** argv) {
@@ -543,6 +605,11 @@ int main(int argc, char** argv) {
           if (bad) printf(" first (m=%d,n=%d) got %g exp %g", fm, fn, fg, fe);
           printf("\n");
         }
+  }
+  if (argc > 1 && std::string(argv[1]) == "p9") {
+    run_issue<1, 0>(dC); run_issue<2, 0>(dC); run_issue<4, 0>(dC); run_issue<6, 0>(dC); run_issue<12, 0>(dC);
+    run_issue<24, 0>(dC); run_issue<48, 0>(dC); run_issue<6, 1>(dC); run_issue<24, 1>(dC);
+    return 0;
   }
   // ---- P8 compile-time rate probes ----
   run_rate_ct<48, 0, 0, 1>("S-like  SS Kmajor dep-chain", dC);

@@ -48,16 +48,16 @@ for mode in [int(m) for m in os.environ.get('MODES', '0,1,2,3').split(',')]:
     assert L.dagl_debug_read_tc_timeline(tl.ctypes.data_as(ctypes.c_void_p)) == 0
     names = {0: "sm:s_full", 1: "sm:ld_done", 2: "sm:computed", 3: "sm:p_free", 4: "sm:stored", 5: "sc:k_full", 6: "sc:s_free",
              7: "sc:issued", 8: "pv0:p_full", 9: "pv0:issued", 10: "pv1:p_full", 11: "pv1:issued", 12: "pv2:p_full",
-             13: "pv2:issued", 14: "pv3:p_full", 15: "pv3:issued", 16: "pv:t_full", 17: "fw:p_full", 19: "pr:k_issued", 20: "pr:t_issued"}
-    for rank in (0, 2):
-      print(f"--- timeline, cluster 0 rank {rank}: (round, event) sorted by time, cycles relative to round {100}'s first event")
-      ev = []
-      for r in range(0, 6):
-        for e, nm in names.items():
-          if tl[rank, r, e] > 0: ev.append((int(tl[rank, r, e]), f"r{r}:{nm}"))
-      ev.sort()
-      t0 = ev[0][0]
-      line = []
-      for t, nm in ev:
-        line.append(f"{t - t0:6d} {nm}")
-      for k in range(0, len(line), 4): print("   ".join(f"{x:26s}" for x in line[k:k + 4]))
+             13: "pv2:issued", 14: "pv3:p_full", 15: "pv3:issued", 16: "pv:t_full", 17: "fw:p_full", 18: "fw:issued",
+             19: "kl:issued", 20: "tl:issued"}
+    sel = [int(e) for e in os.environ.get("EVENTS", "3,4,18,8,9,10,11,12,13,14,15").split(",")]
+    print("--- cluster 0, all four ranks on a common clock (cycles since the cluster barrier); rounds 100..103; event = R<rank>:r<round>:<name>")
+    ev = []
+    for rank in range(4):
+      for r in range(0, 4):
+        for e in sel:
+          if tl[rank, r, e] > 0: ev.append((int(tl[rank, r, e]), f"R{rank}:r{r}:{names[e]}"))
+    ev.sort()
+    t0 = ev[0][0]
+    line = [f"{t - t0:6d} {nm}" for t, nm in ev]
+    for k in range(0, len(line), 4): print("   ".join(f"{x:28s}" for x in line[k:k + 4]))
