@@ -98,17 +98,17 @@ class CE(nn.Module):
         return w, keep
 
     def _packed_fc(self, device: torch.device) -> Optional[int]:
-        """fc1/fc2 packed once for the tensor-core embedding kernel (``dagl_ce_pack_weights_f32``) and reused while the
+        """fc1/fc2 and g/theta packed once for the tensor-core kernels (``dagl_ce_pack_weights_f32``) and reused while the
         weights are unchanged (eval mode only; keyed on the tensors' storage and in-place version counters, so
         ``load_state_dict`` / optimiser steps invalidate it)."""
-        w1, w2 = self.fc1[0].weight, self.fc2[0].weight
-        key = (str(device), w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        ws = (self.fc1[0].weight, self.fc2[0].weight, self.g.weight, self.theta.weight)
+        key = (str(device),) + tuple(v for t in ws for v in (t.data_ptr(), t._version))
         if self._packed_key != key:
             L = _lib.lib()
             buf = torch.empty(L.dagl_ce_packed_weights_bytes(), dtype=torch.uint8, device=device)
-            t1, t2 = w1.detach().contiguous(), w2.detach().contiguous()
-            tmp = _lib.DaglCEWeights(fc1_w=t1.data_ptr(), fc2_w=t2.data_ptr(), inter_channels=self.inter_channels,
-                                     ksize=self.ksize)
+            t1, t2, t3, t4 = (t.detach().contiguous() for t in ws)
+            tmp = _lib.DaglCEWeights(fc1_w=t1.data_ptr(), fc2_w=t2.data_ptr(), g_w=t3.data_ptr(), theta_w=t4.data_ptr(),
+                                     in_channels=self.in_channels, inter_channels=self.inter_channels, ksize=self.ksize)
             rc = L.dagl_ce_pack_weights_f32(C.byref(tmp), buf.data_ptr(), buf.numel(),
                                             torch.cuda.current_stream(device).cuda_stream)
             _lib.check(rc, "dagl_ce_pack_weights_f32")

@@ -28,7 +28,7 @@ int prof_end(cudaStream_t st) {
 
 // Workspace carve-up shared by workspace_bytes / forward / workspace_view.
 struct WsLayout {
-  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, embed, attend, total;
+  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, feat, embed, attend, total;
   int kblocks_simt, kblocks_tc;
 };
 
@@ -49,6 +49,7 @@ static WsLayout ws_layout(const Geom& g) {
   L.kpart = take((size_t)g.B * kblocks * ED * f);
   L.Kbar = take((size_t)g.B * ED * f);
   L.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
+  L.feat = take(feature_maps_tc_workspace_bytes(g));
   L.embed = take(embed_tc_workspace_bytes(g));
   L.attend = off;
   const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g);
@@ -148,7 +149,14 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   unsigned* absmax = reinterpret_cast<unsigned*>(base + L.absmax);
 
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
-  if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
+  if (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g)) {
+    if ((rc = launch_feature_maps_tc(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, base + L.feat,
+                                     L.embed - L.feat,
+                                     w->packed_fc ? static_cast<const char*>(w->packed_fc) + embed_tc_packed_weights_bytes() : nullptr,
+                                     st))) return rc;
+  } else {
+    if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
+  }
   if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
   if (impl == DAGL_IMPL_SIMT) {
     if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax, AMAX_Q, st))) return rc;
@@ -216,11 +224,11 @@ int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_
   return 0;
 }
 
-size_t dagl_ce_packed_weights_bytes(void) { return embed_tc_packed_weights_bytes(); }
+size_t dagl_ce_packed_weights_bytes(void) { return embed_tc_packed_weights_bytes() + feature_maps_tc_packed_weights_bytes(); }
 
 int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream) {
   call_state().launches = 0;
-  if (!w || !w->fc1_w || !w->fc2_w || !packed) {
+  if (!w || !w->fc1_w || !w->fc2_w || !w->g_w || !w->theta_w || !packed) {
     call_state().err = "null pointer";
     return DAGL_ERR_INVALID_ARG;
   }
@@ -228,7 +236,14 @@ int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t pa
     call_state().err = "unsupported CE configuration";
     return DAGL_ERR_UNSUPPORTED;
   }
-  const int rc = launch_pack_fc_weights(w->fc1_w, w->fc2_w, packed, packed_bytes, static_cast<cudaStream_t>(stream));
+  if (packed_bytes < dagl_ce_packed_weights_bytes()) {
+    call_state().err = "packed-weights buffer too small";
+    return DAGL_ERR_WORKSPACE;
+  }
+  int rc = launch_pack_fc_weights(w->fc1_w, w->fc2_w, packed, embed_tc_packed_weights_bytes(), static_cast<cudaStream_t>(stream));
+  if (rc == 0)
+    rc = launch_pack_feat_weights(w->in_channels, w->g_w, w->theta_w, static_cast<char*>(packed) + embed_tc_packed_weights_bytes(),
+                                  feature_maps_tc_packed_weights_bytes(), static_cast<cudaStream_t>(stream));
   return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
 }
 

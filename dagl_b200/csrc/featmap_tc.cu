@@ -1,0 +1,331 @@
+// Feature maps on the tensor cores (tcgen05), sm_100a.
+// Reference: b1 = g(b) (Conv2d 64->16, 3x3, pad 1) and b2 = theta(b) (Conv2d 64->16, 1x1), DN_Gray/model/dagl.py:208-209.
+//
+// [G | Theta][p][0..31] = bias + sum_{tap (ky,kx)} sum_{ci} W[.][ci,tap] * bpad[ci][y+ky-1][x+kx-1]
+// is an implicit GEMM with M = pixels, N = 32 (16 g outputs + 16 theta outputs; theta only has the centre tap) and
+// K = 9 taps x 64 channels.  With b repacked channel-last in groups of 16 channels over the zero-padded image and
+// pixels enumerated in padded-flat order (the layout of embed_tc.cu), the A operand of (tap, channel group) for 128
+// consecutive pixels is a pixel-shifted view of a 3-row halo held in smem: 36 "virtual taps" of K = 16 each.
+//
+// G feeds the patch embeddings and through them the neighbour threshold, so it needs fp32 accuracy: b and the
+// weights are rescaled by powers of two and split into fp16 hi + lo; acc = bh.Wh + (bh.Wl + bl.Wh), the cross terms
+// in their own accumulator (fp32 accumulate in TMEM), added in fp32 in the epilogue.
+// The fp32 CUDA-core kernel (prologue.cu) remains for C != 64 and for impl "simt".
+#include <cuda_fp16.h>
+#include <math.h>
+#include "common.cuh"
+#include "tc_utils.cuh"
+
+namespace dagl {
+using namespace tc;
+
+constexpr int FT_M = 128;                           // pixels per CTA
+constexpr int FT_C = 64;                            // input channels handled by this kernel
+constexpr int FT_GROUPS = FT_C / 16;
+constexpr int FT_N = 32;                            // 16 g + 16 theta outputs
+constexpr int FT_SEG_PIX = 144;                     // 128 + 2 (kx) + 7 (alignment) rounded up to 8 ... shares embed_tc's padding (PADK = 3)
+constexpr int FT_SEG_BYTES = FT_SEG_PIX * 32;       // 4608
+constexpr int FT_VTAPS = 9 * FT_GROUPS;             // 36 virtual taps of K = 16
+constexpr int FT_WPART_BYTES = FT_N * 16 * 2;       // 1024: one virtual tap, hi or lo, K-major no-swizzle [2 kc][32 rows][16 B]
+constexpr int FT_WTAP_BYTES = 2 * FT_WPART_BYTES;   // hi | lo
+constexpr int FT_SM_A = 0;                          // [group][hi|lo][ky] segments
+constexpr int FT_SM_W = FT_GROUPS * 2 * 3 * FT_SEG_BYTES;            // 110592 = 108 * 1024
+constexpr int FT_SM_BAR = FT_SM_W + FT_VTAPS * FT_WTAP_BYTES;        // + 73728
+constexpr int FT_SM_TOTAL = FT_SM_BAR + 64;
+constexpr int FT_THREADS = 192;                     // warp 0 loads, warp 1 issues, warps 2-5 epilogue
+static_assert(FT_SM_W % 1024 == 0, "weight image alignment");
+
+struct FtGeom { int Wp, NkP, ntile, NPG; };
+static FtGeom ft_geom(const Geom& g) {
+  FtGeom e;
+  e.Wp = g.W + 2 * PADK;
+  e.NkP = (g.H - 1) * e.Wp + g.W;
+  e.ntile = (e.NkP + FT_M - 1) / FT_M;
+  const int np = (g.H + 2 * PADK) * e.Wp;
+  const int need = FT_M * e.ntile + 2 * PADK * e.Wp + FT_SEG_PIX + 8;
+  e.NPG = ((np > need ? np : need) + 7) & ~7;
+  return e;
+}
+
+__device__ __forceinline__ float pow2_scale_f(unsigned absmax_bits, int target) {
+  const float a = __uint_as_float(absmax_bits);
+  if (!(a > 0.f) || !isfinite(a)) return 1.f;
+  int e;
+  frexpf(a, &e);
+  return ldexpf(1.f, target - e);
+}
+
+// max |b| per image -> bmax[img]
+__global__ void absmax_img_kernel(const float* __restrict__ x, size_t n_per_img, unsigned* __restrict__ bmax) {
+  const int img = blockIdx.y;
+  const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * n_per_img);
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_img / 4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(xi + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(bmax + img, __float_as_uint(m));
+}
+
+// g weight [16][64][3][3], theta weight [16][64] -> per virtual tap (group, tap): [hi|lo][2 k-chunks][32 rows][8 ch] fp16,
+// rows 0..15 = g outputs, rows 16..31 = theta outputs (zero except at the centre tap); wmax[0] = max |w| (float bits).
+__global__ void __launch_bounds__(256)
+pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ th_w, uint8_t* __restrict__ out,
+                  unsigned* __restrict__ wmax) {
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < CI * FT_C * 9; i += 256) m = fmaxf(m, fabsf(__ldg(g_w + i)));
+  for (int i = threadIdx.x; i < CI * FT_C; i += 256) m = fmaxf(m, fabsf(__ldg(th_w + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
+  if (threadIdx.x == 0) *wmax = __float_as_uint(m);
+  const float scale = pow2_scale_f(__float_as_uint(m), 14);
+  for (int o = threadIdx.x; o < FT_VTAPS * 2 * FT_N; o += 256) {          // one 16-byte chunk = 8 channels of one output row
+    const int v = o / (2 * FT_N), kc = (o / FT_N) & 1, e = o % FT_N;
+    const int gq = v / 9, t = v % 9;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ci = gq * 16 + kc * 8 + 2 * j + u;
+        float w = 0.f;
+        if (e < CI) w = __ldg(g_w + ((size_t)e * FT_C + ci) * 9 + t);
+        else if (t == 4) w = __ldg(th_w + (size_t)(e - CI) * FT_C + ci);
+        x[u] = w * scale;
+      }
+      const __half h0 = __float2half_rn(x[0]), h1 = __float2half_rn(x[1]);
+      const __half l0 = __float2half_rn(x[0] - __half2float(h0)), l1 = __float2half_rn(x[1] - __half2float(h1));
+      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    uint8_t* base = out + (size_t)v * FT_WTAP_BYTES + (size_t)(kc * FT_N + e) * 16;
+    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + FT_WPART_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// b [64][H][W] fp32 -> per 16-channel group: zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
+// layout: [img][group][hi|lo][NPG][32 B]
+__global__ void __launch_bounds__(256)
+pack_b_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const unsigned* __restrict__ bmax, uint8_t* __restrict__ bimg) {
+  const int img = blockIdx.z, gq = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= eg.NPG) return;
+  const float scale = pow2_scale_f(bmax[img], 14);
+  const int r = pix / eg.Wp, cc = pix % eg.Wp;
+  const int y = r - PADK, x = cc - PADK;
+  const bool inb = (y >= 0 && y < g.H && x >= 0 && x < g.W);
+  const float* src = b + (((size_t)img * g.C + gq * 16) * g.H + (inb ? y : 0)) * g.W + (inb ? x : 0);
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a0 = 0.f, a1 = 0.f;
+    if (inb) {
+      a0 = __ldg(src + (size_t)(2 * j) * g.Nk) * scale;
+      a1 = __ldg(src + (size_t)(2 * j + 1) * g.Nk) * scale;
+    }
+    const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+    const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  const int sw = (pix >> 2) & 1;
+  uint8_t* base = bimg + ((size_t)(img * FT_GROUPS + gq) * 2) * (size_t)eg.NPG * 32;
+  uint4* dh = reinterpret_cast<uint4*>(base + (size_t)pix * 32);
+  uint4* dl = reinterpret_cast<uint4*>(base + (size_t)eg.NPG * 32 + (size_t)pix * 32);
+  dh[sw] = make_uint4(h[0], h[1], h[2], h[3]);
+  dh[sw ^ 1] = make_uint4(h[4], h[5], h[6], h[7]);
+  dl[sw] = make_uint4(l[0], l[1], l[2], l[3]);
+  dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uint8_t* __restrict__ wpack,
+                  const float* __restrict__ g_b, const float* __restrict__ th_b, const unsigned* __restrict__ bmax,
+                  const unsigned* __restrict__ wmax, float* __restrict__ G, float* __restrict__ Th,
+                  unsigned* __restrict__ absmax /*[B][AMAX_STRIDE]*/) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_SM_BAR);
+  uint64_t* in_full = bars + 0;
+  uint64_t* d_full = bars + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = warp_id_uniform();
+  const int tid = threadIdx.x;
+  const int img = blockIdx.y, tile = blockIdx.x;
+  const int p0 = tile * FT_M;
+
+  if (tid == 0) {
+    mbar_init(in_full, 1);
+    mbar_init(d_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(in_full, FT_GROUPS * 2 * 3 * FT_SEG_BYTES + FT_VTAPS * FT_WTAP_BYTES);
+      bulk_g2s(smem + FT_SM_W, wpack, FT_VTAPS * FT_WTAP_BYTES, in_full);
+      for (int gq = 0; gq < FT_GROUPS; ++gq)
+        for (int part = 0; part < 2; ++part) {
+          const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
+          for (int ky = 0; ky < 3; ++ky) {
+            const int first = (p0 + (ky + 2) * eg.Wp) & ~7;           // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
+            bulk_g2s(smem + FT_SM_A + ((gq * 2 + part) * 3 + ky) * FT_SEG_BYTES, src + (size_t)first * 32, FT_SEG_BYTES, in_full);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(in_full, 0);
+      tc_fence_after();
+      const uint32_t abase = smem_u32(smem + FT_SM_A), wbase = smem_u32(smem + FT_SM_W);
+      constexpr uint32_t id32 = instr_desc(FT_M, 32, FMT_F16, FMT_F16, 0, 0);
+      constexpr uint32_t id16 = instr_desc(FT_M, 16, FMT_F16, FMT_F16, 0, 0);
+      // The centre tap carries the theta outputs (N = 32) and goes first in every group, so that the very first MMA
+      // initialises all 32 accumulator columns; the other taps only touch the 16 g columns.
+      const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+      bool first = true;
+#pragma unroll 1
+      for (int gq = 0; gq < FT_GROUPS; ++gq) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const int t = order[i], ky = t / 3, kx = t % 3;
+          const int off = ((p0 + (ky + 2) * eg.Wp) & 7) + kx + 2;
+          const uint32_t a_hi = abase + ((gq * 2 + 0) * 3 + ky) * FT_SEG_BYTES + off * 32;
+          const uint32_t a_lo = abase + ((gq * 2 + 1) * 3 + ky) * FT_SEG_BYTES + off * 32;
+          // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
+          const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                                 ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+          const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                                 ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+          const uint32_t w_hi = wbase + (gq * 9 + t) * FT_WTAP_BYTES;
+          const uint64_t db_hi = smem_desc(w_hi, FT_N * 16, 128);
+          const uint64_t db_lo = smem_desc(w_hi + FT_WPART_BYTES, FT_N * 16, 128);
+          const uint32_t idesc = (t == 4) ? id32 : id16;
+          const uint32_t acc = first ? 0u : 1u;
+          mma_f16_ss_a_fill(tbase, da_hi, db_hi, idesc, acc);              // bh.Wh  -> main accumulator, columns [0,32)
+          mma_f16_ss_a_lastuse(tbase + 32, da_hi, db_lo, idesc, acc);      // bh.Wl  -> cross accumulator, columns [32,64)
+          mma_f16_ss(tbase + 32, da_lo, db_hi, idesc, 1);                  // bl.Wh
+          first = false;
+        }
+      }
+      mma_commit(d_full);
+    }
+  } else {
+    // epilogue: thread = pixel row
+    const int quad = warp & 3, lane = tid & 31;
+    const int r = quad * 32 + lane;
+    const int p = p0 + r;
+    const int y = p / eg.Wp, x = p % eg.Wp;
+    const bool valid = (p < eg.NkP) && (x < g.W);
+    const float inv = 1.f / (pow2_scale_f(bmax[img], 14) * pow2_scale_f(*wmax, 14));
+    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    mbar_wait(d_full, 0);
+    tc_fence_after();
+    float gmax = 0.f, tmax = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                 // 0: g outputs, 1: theta outputs
+      uint32_t v[16], vc[16];
+      tmem_ld16(trow + half * 16, v);
+      tmem_ld16(trow + 32 + half * 16, vc);
+      tmem_wait_ld();
+      if (valid) {
+        float* dst = (half ? Th : G) + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
+        const float* bias = half ? th_b : g_b;
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+          const float o = (__uint_as_float(v[c]) + __uint_as_float(vc[c])) * inv + __ldg(bias + c);
+          dst[(size_t)c * g.Nk] = o;
+          if (half) tmax = fmaxf(tmax, fabsf(o)); else gmax = fmaxf(gmax, fabsf(o));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    }
+    if (lane == 0 && absmax != nullptr) {
+      atomicMax(absmax + img * AMAX_STRIDE + AMAX_THETA, __float_as_uint(tmax));
+      atomicMax(absmax + img * AMAX_STRIDE + AMAX_G, __float_as_uint(gmax));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tbase);
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static inline size_t align_up_f(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool feature_maps_tc_supported(const Geom& g) { return g.C == FT_C; }
+
+size_t feature_maps_tc_workspace_bytes(const Geom& g) {
+  if (!feature_maps_tc_supported(g)) return 0;
+  const FtGeom eg = ft_geom(g);
+  return align_up_f((size_t)g.B * FT_GROUPS * 2 * eg.NPG * 32) + align_up_f((size_t)g.B * sizeof(unsigned)) +
+         align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES) + align_up_f(64);
+}
+
+// packed g/theta weights | wmax (one unsigned)
+size_t feature_maps_tc_packed_weights_bytes() { return align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES) + align_up_f(64); }
+
+int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* packed, size_t packed_bytes, cudaStream_t st) {
+  if (C != FT_C) return 0;                                   // fp32 CUDA-core feature kernel: nothing to pack
+  if (packed_bytes < feature_maps_tc_packed_weights_bytes()) {
+    call_state().err = "packed-weights buffer too small";
+    return -3;
+  }
+  uint8_t* wpack = static_cast<uint8_t*>(packed);
+  unsigned* wmax = reinterpret_cast<unsigned*>(wpack + align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES));
+  pack_featw_kernel<<<1, 256, 0, st>>>(g_w, th_w, wpack, wmax);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// `prepacked` (nullable): weights packed by launch_pack_feat_weights.
+int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
+                           const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
+                           const void* prepacked, cudaStream_t st) {
+  const FtGeom eg = ft_geom(g);
+  if (!feature_maps_tc_supported(g) || ws_bytes < feature_maps_tc_workspace_bytes(g)) {
+    call_state().err = "feature maps (tc): unsupported channel count or workspace too small";
+    return -3;
+  }
+  char* p = static_cast<char*>(ws);
+  uint8_t* bimg = reinterpret_cast<uint8_t*>(p); p += align_up_f((size_t)g.B * FT_GROUPS * 2 * eg.NPG * 32);
+  unsigned* bmax = reinterpret_cast<unsigned*>(p); p += align_up_f((size_t)g.B * sizeof(unsigned));
+  const uint8_t* wpack = static_cast<const uint8_t*>(prepacked);
+  if (wpack == nullptr) {
+    if (int rc = launch_pack_feat_weights(g.C, g_w, th_w, p, feature_maps_tc_packed_weights_bytes(), st)) return rc;
+    wpack = reinterpret_cast<const uint8_t*>(p);
+  }
+  const unsigned* wmax = reinterpret_cast<const unsigned*>(wpack + align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES));
+
+  DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)g.B * sizeof(unsigned), st));
+  const size_t n_img = (size_t)g.C * g.Nk;
+  absmax_img_kernel<<<dim3(128, g.B), 256, 0, st>>>(b, n_img, bmax);
+  DAGL_LAUNCH_CHECK();
+  pack_b_kernel<<<dim3((eg.NPG + 255) / 256, FT_GROUPS, g.B), 256, 0, st>>>(g, eg, b, bmax, bimg);
+  DAGL_LAUNCH_CHECK();
+  DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
+  featmap_tc_kernel<<<dim3(eg.ntile, g.B), FT_THREADS, FT_SM_TOTAL, st>>>(g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax);
+  DAGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dagl

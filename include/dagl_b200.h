@@ -63,8 +63,8 @@ typedef struct DaglCEWeights {
   int32_t stride_q;         /* must be 4  (stride_1)  */
   int32_t stride_k;         /* must be 1  (stride_2)  */
   float softmax_scale;      /* reference default 10   */
-  const void* packed_fc;    /* optional (may be NULL): fc1/fc2 pre-packed by dagl_ce_pack_weights_f32 for the
-                               tensor-core embedding kernel; saves the per-call weight packing at inference  */
+  const void* packed_fc;    /* optional (may be NULL): fc1/fc2 and g/theta pre-packed by dagl_ce_pack_weights_f32
+                               for the tensor-core kernels; saves the per-call weight packing at inference   */
 } DaglCEWeights;
 
 int32_t dagl_abi_version(void);
@@ -82,10 +82,10 @@ int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y,
                             int32_t impl, void* stream);
 
 /* Optional weight pre-packing.  The library keeps no state between calls, so by default every forward re-packs
- * fc1 / fc2 (fp32 [196][784]) into the fp16 hi/lo tensor-core operand images (~25 us).  A caller whose weights
- * are constant (inference) can do it once: pack into a caller-owned device buffer of
- * dagl_ce_packed_weights_bytes() and pass it as DaglCEWeights.packed_fc; it must be re-packed whenever fc1_w or
- * fc2_w change.  Only the tensor-core implementations read it.                                                */
+ * fc1 / fc2 (fp32 [196][784]) and g / theta into the fp16 hi/lo tensor-core operand images (~40 us).  A caller
+ * whose weights are constant (inference) can do it once: pack into a caller-owned device buffer of
+ * dagl_ce_packed_weights_bytes() and pass it as DaglCEWeights.packed_fc; it must be re-packed whenever fc1_w,
+ * fc2_w, g_w or theta_w change (w->in_channels must be set).  Only the tensor-core implementations read it.   */
 size_t dagl_ce_packed_weights_bytes(void);
 int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream);
 
