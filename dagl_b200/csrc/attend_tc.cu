@@ -581,43 +581,43 @@ attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_
 // so ref_q = exponent(1.004 * smax_q) bounds every term.  No online maximum, no accumulator rescale,
 // and key-split partials merge by plain sums.
 // =============================================================================================
-constexpr int RM_TILES = 2;                                 // key tiles per pre-pass step
 constexpr int RM_QT = 2;                                    // query tiles per CTA (each K tile is fetched once for both)
-constexpr int RM_STAGE_BYTES = RM_TILES * K_HALF_BYTES;     // 39936
-constexpr int RM_SM_Q = 0;
-constexpr int RM_SM_K = RM_QT * Q_HALF_BYTES;               // 106496 = 104 * 1024
-constexpr int RM_KSTAGES = 3;
-constexpr int RM_SM_BAR = RM_SM_K + RM_KSTAGES * RM_STAGE_BYTES;
+constexpr int RM_KSTAGES = 4;
+constexpr int RM_SM_K = 0;                                  // ring of Kh tiles (19968 B each)
+constexpr int RM_SM_BAR = RM_SM_K + RM_KSTAGES * K_HALF_BYTES;
 constexpr int RM_SM_TOTAL = RM_SM_BAR + 128;
 constexpr int RM_THREADS = 192;
-constexpr int RM_DCOLS = RM_QT * RM_TILES * TC_BN;          // 192 accumulator columns per TMEM buffer
-static_assert(RM_SM_K % 1024 == 0, "pre-pass smem alignment");
+constexpr int RM_QCOL = 0;                                  // Qh of the two query tiles: 2 x 104 TMEM columns
+constexpr int RM_DCOL0 = RM_QT * (TC_EP / 2);               // 208: two accumulator buffers of RM_QT x 48 columns
+constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 
 // smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits.
-// The pre-pass is bound by the L2 -> SM traffic of the K tiles, so a CTA serves two query tiles per K fetch.
+// The query tiles live in TMEM (A operand of the MMAs, TS form: 27.7 instead of ~51 cycles per N = 48 MMA) and a CTA
+// serves two query tiles per K fetch (the pre-pass would otherwise be bound by the L2 -> SM traffic of the K tiles).
+//   TMEM: Qh(q0) [0,104) | Qh(q1) [104,208) | D0 [208,304) | D1 [304,400)
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
                  int qt_base, int qt_end, unsigned* __restrict__ smax) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [3]
-  uint64_t* k_empty = bars + 4;   // [3]
-  uint64_t* d_full = bars + 7;    // [2]
-  uint64_t* d_empty = bars + 9;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* q_ready = bars + 0;   // 128 arrivals: the query tiles are in TMEM
+  uint64_t* k_full = bars + 1;    // [4]
+  uint64_t* k_empty = bars + 5;   // [4]
+  uint64_t* d_full = bars + 9;    // [2]
+  uint64_t* d_empty = bars + 11;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const int qt0 = qt_base + blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
   const int nq_here = min(RM_QT, qt_end - qt0);
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
-  const int nsteps = (t_end - t_begin + RM_TILES - 1) / RM_TILES;
+  const int nsteps = t_end - t_begin;                       // one key tile per step
 
   if (tid == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
     for (int i = 0; i < RM_KSTAGES; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -628,49 +628,32 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, (uint32_t)nq_here * Q_HALF_BYTES);
-      for (int qi = 0; qi < nq_here; ++qi)
-        bulk_g2s(smem + RM_SM_Q + qi * Q_HALF_BYTES, Qp + ((size_t)img * tg.nqt + qt0 + qi) * Q_TILE_BYTES, Q_HALF_BYTES, q_full);
-      for (int st = 0; st < nsteps; ++st) {
+      const uint8_t* ksrc = Kp + ((size_t)img * tg.NT + t_begin) * K_TILE_BYTES;
+      for (int st = 0; st < nsteps; ++st, ksrc += K_TILE_BYTES) {
         const int s = st % RM_KSTAGES;
         mbar_wait(k_empty + s, ((uint32_t)(st / RM_KSTAGES) & 1u) ^ 1u);
-        const int t0 = t_begin + st * RM_TILES;
-        const int nt = min(RM_TILES, t_end - t0);
-        mbar_arrive_expect_tx(k_full + s, (uint32_t)nt * K_HALF_BYTES);
-        for (int i = 0; i < nt; ++i)
-          bulk_g2s(smem + RM_SM_K + s * RM_STAGE_BYTES + i * K_HALF_BYTES,
-                   Kp + ((size_t)img * tg.NT + t0 + i) * K_TILE_BYTES, K_HALF_BYTES, k_full + s);
+        mbar_arrive_expect_tx(k_full + s, K_HALF_BYTES);
+        bulk_g2s(smem + RM_SM_K + s * K_HALF_BYTES, ksrc, K_HALF_BYTES, k_full + s);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
-      const uint64_t dq0 = smem_desc(smem_u32(smem + RM_SM_Q), (TC_BM / 8) * 128, 128);
-      const uint64_t dq1 = smem_desc(smem_u32(smem + RM_SM_Q + Q_HALF_BYTES), (TC_BM / 8) * 128, 128);
-      mbar_wait(q_full, 0);
+      const bool two_q = nq_here > 1;
+      mbar_wait(q_ready, 0);
       tc_fence_after();
       for (int st = 0; st < nsteps; ++st) {
         const int s = st % RM_KSTAGES, db = st & 1;
         mbar_wait(k_full + s, (uint32_t)(st / RM_KSTAGES) & 1u);
         mbar_wait(d_empty + db, ((uint32_t)(st >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
-        const uint32_t kb = smem_u32(smem + RM_SM_K + s * RM_STAGE_BYTES);
-        // single-thread issue: keep the descriptor arithmetic out of the loop (fully unrolled, constants folded)
-        const uint64_t dk0 = smem_desc(kb, (TC_BN / 8) * 128, 128);
-        const uint64_t dk1 = smem_desc(kb + K_HALF_BYTES, (TC_BN / 8) * 128, 128);
-        const uint32_t d0 = tbase + db * RM_DCOLS;
-        const bool two_k = nt > 1, two_q = nq_here > 1;
+        const uint64_t dk = smem_desc(smem_u32(smem + RM_SM_K + s * K_HALF_BYTES), (TC_BN / 8) * 128, 128);
+        const uint32_t d0 = tbase + RM_DCOL0 + db * RM_DCOLS;
 #pragma unroll
         for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-          const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
           const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-          mma_f16_ss_a_fill(d0, dq0 + qo, dk0 + ko, idS, ks > 0);                        // Qh slab read once ...
-          if (two_k) mma_f16_ss_a_lastuse(d0 + TC_BN, dq0 + qo, dk1 + ko, idS, ks > 0);  // ... re-used for the 2nd key tile
-          if (two_q) {
-            mma_f16_ss_a_fill(d0 + 2 * TC_BN, dq1 + qo, dk0 + ko, idS, ks > 0);
-            if (two_k) mma_f16_ss_a_lastuse(d0 + 3 * TC_BN, dq1 + qo, dk1 + ko, idS, ks > 0);
-          }
+          mma_f16_ts(d0, tbase + RM_QCOL + ks * 8, dk + ko, idS, ks > 0);
+          if (two_q) mma_f16_ts(d0 + TC_BN, tbase + RM_QCOL + TC_EP / 2 + ks * 8, dk + ko, idS, ks > 0);
         }
         mma_commit(k_empty + s);
         mma_commit(d_full + db);
@@ -678,31 +661,51 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     }
   } else {
     const int quad = warp & 3, lane = tid & 31;
+    const int row = quad * 32 + lane;
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    // ---- query tiles (hi parts) -> TMEM: lane = row, column j = elements (2j, 2j+1) ----
+#pragma unroll 1
+    for (int qi = 0; qi < nq_here; ++qi) {
+      const uint8_t* src = Qp + ((size_t)img * tg.nqt + qt0 + qi) * Q_TILE_BYTES + row * 16;
+#pragma unroll 1
+      for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
+        const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
+        const uint32_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        tmem_st8(trow + RM_QCOL + qi * (TC_EP / 2) + ks * 8, v);
+      }
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(q_ready);
     float m[RM_QT] = {0.f, 0.f};
     for (int st = 0; st < nsteps; ++st) {
       const int db = st & 1;
       mbar_wait(d_full + db, (uint32_t)(st >> 1) & 1u);
       tc_fence_after();
-      const int nt = min(RM_TILES, t_end - (t_begin + st * RM_TILES));
 #pragma unroll
       for (int qi = 0; qi < RM_QT; ++qi) {
         if (qi >= nq_here) break;
-        for (int c0 = 0; c0 < nt * TC_BN; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(trow + db * RM_DCOLS + qi * RM_TILES * TC_BN + c0, v);
-          tmem_wait_ld();
+        uint32_t v[48];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) m[qi] = fmaxf(m[qi], __uint_as_float(v[i]));
+        for (int c0 = 0; c0 < TC_BN; c0 += 16) {
+          uint32_t t16[16];
+          tmem_ld16(trow + RM_DCOL0 + db * RM_DCOLS + qi * TC_BN + c0, t16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c0 + i] = t16[i];
         }
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < TC_BN; ++i) m[qi] = fmaxf(m[qi], __uint_as_float(v[i]));
       }
       tc_fence_before();
-      mbar_arrive(d_empty + db);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + db);
     }
 #pragma unroll
     for (int qi = 0; qi < RM_QT; ++qi)
       if (qi < nq_here)
-        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + quad * 32 + lane, __float_as_uint(m[qi]));
+        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row, __float_as_uint(m[qi]));
   }
   tc_fence_before();
   __syncthreads();
@@ -1740,7 +1743,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     const int nqg = (qt_end - qt_begin + RM_QT - 1) / RM_QT;
     int pre_split = 148 / (nqg * g.B);
     if (pre_split < 1) pre_split = 1;
-    const int max_split = (tg.NT + RM_TILES - 1) / RM_TILES;
+    const int max_split = tg.NT;
     if (pre_split > max_split) pre_split = max_split;
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
     rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, qt_begin, qt_end, smax);
