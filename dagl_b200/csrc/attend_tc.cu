@@ -1661,6 +1661,26 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
 
 size_t attend_tc_workspace_bytes(const Geom& g) { return tc_ws(g, tc_geom(g)).total; }
 
+void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, float** colsum) {
+  const TcWs w = tc_ws(g, tc_geom(g));
+  char* base = static_cast<char*>(attend_ws);
+  *ktiles = reinterpret_cast<uint8_t*>(base + w.Kp);
+  *colsum = reinterpret_cast<float*>(base + w.colsum);
+}
+
+// validity bits of the 48 key slots of every tile (dummy slots of the padded-flat enumeration are 0)
+__global__ void tilemask_kernel(Geom g, TcGeom tg, unsigned long long* __restrict__ tilemask) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= tg.NT) return;
+  unsigned long long m = 0ull;
+  int kp = t * TC_BN, x = kp % tg.Wp;
+  for (int r = 0; r < TC_BN; ++r, ++kp) {
+    if (kp < tg.NkP && x < g.W) m |= 1ull << r;
+    if (++x == tg.Wp) x = 0;
+  }
+  for (int img = 0; img < g.B; ++img) tilemask[(size_t)img * tg.NT + t] = m;
+}
+
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, int variant, cudaStream_t st) {
   const TcGeom tg = tc_geom(g);
   TcWs w = tc_ws(g, tg);
@@ -1717,13 +1737,20 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     const float* Kbar = a.Kbar;
     float* colsum = nullptr;
     if (Kbar == nullptr) colsum = reinterpret_cast<float*>(base + w.colsum);
-    auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
-    const size_t smem_k = (size_t)TC_BN * ED * 4;
-    kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr, colsum);
-    DAGL_LAUNCH_CHECK();
+    int kblocks = tg.NT;
+    if (a.k_packed) {                                   // the embedding kernel wrote Kp and the column sums already
+      tilemask_kernel<<<(tg.NT + 127) / 128, 128, 0, st>>>(g, tg, tilemask);
+      DAGL_LAUNCH_CHECK();
+      kblocks = a.kblocks;
+    } else {
+      auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
+      const size_t smem_k = (size_t)TC_BN * ED * 4;
+      kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr, colsum);
+      DAGL_LAUNCH_CHECK();
+    }
     if (Kbar == nullptr) {
       float* kb = a.kbar_out ? a.kbar_out : reinterpret_cast<float*>(base + w.kbar);
-      if (int rc = launch_kbar(g, colsum, tg.NT, kb, st)) return rc;
+      if (int rc = launch_kbar(g, colsum, kblocks, kb, st)) return rc;
       Kbar = kb;
     }
     auto kq = pack_tiles_kernel<TC_BM, 0, 16>;

@@ -148,6 +148,7 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   float* Kbar = reinterpret_cast<float*>(base + L.Kbar);
   unsigned* absmax = reinterpret_cast<unsigned*>(base + L.absmax);
 
+  bool k_packed = false;
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
   if (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g)) {
     if ((rc = launch_feature_maps_tc(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, base + L.feat,
@@ -163,15 +164,22 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax, AMAX_K, st))) return rc;
     if ((rc = launch_kbar(g, kpart, L.kblocks_simt, Kbar, st))) return rc;
   } else {
-    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, K, absmax, base + L.embed,
-                              L.attend - L.embed, w->packed_fc, st))) return rc;
-    Kbar = nullptr;      // formed inside the tensor-core launcher from the key-pack column sums
+    // the key embeddings go straight into the graph kernel's fp16 key tiles (+ column sums for Kbar); the fp32 K array is
+    // only materialised for the debug entry (parity tests read it through dagl_ce_workspace_view)
+    uint8_t* ktiles; float* colsum;
+    attend_tc_key_buffers(g, base + L.attend, &ktiles, &colsum);
+    const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
+    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, debug ? K : nullptr, absmax, base + L.embed,
+                              L.attend - L.embed, w->packed_fc, ktiles, colsum, st))) return rc;
+    Kbar = nullptr;      // formed inside the tensor-core launcher from the key column sums
+    k_packed = true;
   }
 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
+  a.k_packed = k_packed; a.kblocks = L.kblocks_tc;
   a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
   a.rows_out = rows_out; a.qt_begin = qt_begin; a.qt_end = qt_end;
   return run_attend(g, a, impl, absmax, st);
@@ -228,7 +236,7 @@ size_t dagl_ce_packed_weights_bytes(void) { return embed_tc_packed_weights_bytes
 
 int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream) {
   call_state().launches = 0;
-  if (!w || !w->fc1_w || !w->fc2_w || !w->g_w || !w->theta_w || !packed) {
+  if (!w || !w->fc1_w || !w->fc2_w || !w->fc1_b || !w->fc2_b || !w->g_w || !w->theta_w || !packed) {
     call_state().err = "null pointer";
     return DAGL_ERR_INVALID_ARG;
   }
@@ -240,7 +248,8 @@ int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t pa
     call_state().err = "packed-weights buffer too small";
     return DAGL_ERR_WORKSPACE;
   }
-  int rc = launch_pack_fc_weights(w->fc1_w, w->fc2_w, packed, embed_tc_packed_weights_bytes(), static_cast<cudaStream_t>(stream));
+  int rc = launch_pack_fc_weights(w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, packed, embed_tc_packed_weights_bytes(),
+                                  static_cast<cudaStream_t>(stream));
   if (rc == 0)
     rc = launch_pack_feat_weights(w->in_channels, w->g_w, w->theta_w, static_cast<char*>(packed) + embed_tc_packed_weights_bytes(),
                                   feature_maps_tc_packed_weights_bytes(), static_cast<cudaStream_t>(stream));

@@ -106,10 +106,11 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
                            const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
                            const void* prepacked, cudaStream_t st);
 size_t embed_tc_packed_weights_bytes();
-int launch_pack_fc_weights(const float* fc1_w, const float* fc2_w, void* packed, size_t packed_bytes, cudaStream_t st);
+int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, void* packed,
+                           size_t packed_bytes, cudaStream_t st);
 int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                     const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    const void* prepacked, cudaStream_t st);
+                    const void* prepacked, uint8_t* ktiles, float* colsum, cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
@@ -121,7 +122,13 @@ struct AttendArgs {
   // rows_out is set the merged rows [B][Nq][49][16] are written there and the fold is left to the caller
   int qt_begin = 0, qt_end = 0;
   float* rows_out = nullptr;
+  // keys already packed into the tensor-core tiles (and their column sums formed) by the embedding kernel: K is unused,
+  // `kblocks` = number of column-sum partials per image
+  bool k_packed = false;
+  int kblocks = 0;
 };
+// where the tensor-core graph kernel expects its packed key tiles / column-sum partials inside its workspace
+void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, float** colsum);
 size_t merge_fold_scratch_bytes(const Geom& g);      // Omerged [B][Nq][784]
 int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
                      int shift_major, cudaStream_t st);

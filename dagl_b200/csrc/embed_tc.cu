@@ -49,11 +49,13 @@ static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
 struct EmbGeom {
   int Wp, NkP, ntile, NPG;
 };
+constexpr int EB_KTILE = 48;                       // key-tile size of the graph kernel (attend_tc.cu TC_BN)
 static EmbGeom emb_geom(const Geom& g) {
   EmbGeom e;
-  e.Wp = g.W + 2 * PADK;
+  e.Wp = (g.W + 2 * PADK + 7) & ~7;                // the padded-flat key enumeration of attend_tc.cu (tc_geom)
   e.NkP = (g.H - 1) * e.Wp + g.W;
-  e.ntile = (e.NkP + EB_M - 1) / EB_M;
+  const int slots = ((e.NkP + EB_KTILE - 1) / EB_KTILE) * EB_KTILE;     // every slot of every 48-key tile gets written
+  e.ntile = (slots + EB_M - 1) / EB_M;
   int np = (g.H + 2 * PADK) * e.Wp;
   int need = EB_M * e.ntile + 2 * PADK * e.Wp + EB_SEG_PIX + 8;
   e.NPG = ((np > need ? np : need) + 7) & ~7;
@@ -145,7 +147,9 @@ __global__ void __launch_bounds__(EB_THREADS, 2)
 embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __restrict__ ghi,
                 const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
                 const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
-                float* __restrict__ out, unsigned* __restrict__ absmax_out) {
+                float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
+                uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
+                float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of this CTA's rows*/) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
   uint64_t* g_full = bars + 0;
@@ -250,6 +254,15 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
     }
     const float inv = 1.f / (pow2_scale_e(absmax_in[img * 4 + 3], 14) * pow2_scale_e(*wmax, 14));
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    const bool fused = (mode == 0) && (ktiles != nullptr);
+    // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
+    // (launch_embed_tc), so no pass over K is needed to find its maximum
+    const float kscale = fused ? pow2_scale_e(absmax_in[img * 4 + 1], 14) : 1.f;
+    const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
+    const int kt = p / EB_KTILE, kr = p % EB_KTILE;                          // key tile / row of this pixel slot
+    uint8_t* ktile = fused && kt < ntile_k ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * EB_KTILE * EB_N * 2) : nullptr;
+    constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
+    float* csum_s = reinterpret_cast<float*>(smem + EB_SM_G);                // the G halo is dead once d_full fires: [4 warps][112]
     float vmax = 0.f;
     mbar_wait(d_full, 0);
     tc_fence_after();
@@ -265,18 +278,61 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
       for (int i = 0; i < 16; ++i) {
         const int e = eb + i;
         const float b = (e < ED) ? __ldg(bias + e) : 0.f;
-        f[i] = valid ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
+        f[i] = (valid && e < ED) ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
         vmax = fmaxf(vmax, f[i]);
       }
-      if (valid) {
+      if (valid && out != nullptr) {
         float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
         const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
         for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
       }
+      if (fused) {
+        if (ktile != nullptr) {                                  // dummy slots (x >= W, p >= NkP) get zero rows
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = f[h8 * 8 + 2 * j] * kscale, x1 = f[h8 * 8 + 2 * j + 1] * kscale;
+              const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+              const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+              hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const int kc = eb / 8 + h8;                          // 16-byte chunk column of the K-major no-swizzle tile
+            const uint32_t off = (uint32_t)(kc * (EB_KTILE / 8) * 128 + (kr / 8) * 128 + (kr % 8) * 16);
+            *reinterpret_cast<uint4*>(ktile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(ktile + K_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        // column sums over this warp's 32 rows, then over the 4 warps below (Kbar = mean_k K).  Transposing butterfly:
+        // every step halves the columns a lane carries and doubles the rows they cover (8+4+2+1+1 = 16 shuffles instead
+        // of 16 x 5); fixed order, so the result is deterministic.  Lane l ends with column (l >> 1) & 15.
+        {
+          float a8[8], a4[4], a2[2];
+          const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a8[i] = (u16 ? f[8 + i] : f[i]) + __shfl_xor_sync(0xffffffffu, u16 ? f[i] : f[8 + i], 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a4[i] = (u8 ? a8[4 + i] : a8[i]) + __shfl_xor_sync(0xffffffffu, u8 ? a8[i] : a8[4 + i], 8);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a2[i] = (u4 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, u4 ? a4[i] : a4[2 + i], 4);
+          float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+          if ((lane & 1) == 0) csum_s[quad * EB_N0 + c16 * 16 + (lane >> 1)] = a1;
+        }
+      }
+    }
+    if (fused) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps
+      const int c = quad * 32 + lane;
+      if (c < ncols && e0 + c < ED)
+        colsum[((size_t)img * gridDim.x + tile) * ED + e0 + c] =
+            ((csum_s[c] + csum_s[EB_N0 + c]) + csum_s[2 * EB_N0 + c]) + csum_s[3 * EB_N0 + c];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
+    if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
   }
   tc_fence_before();
   __syncthreads();
@@ -292,11 +348,46 @@ size_t embed_tc_workspace_bytes(const Geom& g) {
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
-// packed fc1 | packed fc2 | wmax[2]
+// meta[2*which + 0] = max_e sum_j |w[e][j]|, meta[2*which + 1] = max_e |bias[e]|   (which = blockIdx.x: 0 fc1, 1 fc2)
+// -> a-priori bound  |fc(x)|_inf <= max|x| * meta[0] + meta[1]  used as the fp16 scale of the fused key pack
+__global__ void __launch_bounds__(256)
+fc_meta_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+               const float* __restrict__ b2, float* __restrict__ meta) {
+  __shared__ float red[2][8];
+  const float* w = blockIdx.x ? w2 : w1;
+  const float* bb = blockIdx.x ? b2 : b1;
+  float l1 = 0.f, bm = 0.f;
+  for (int e = threadIdx.x >> 5; e < ED; e += 8) {                 // one warp per output row
+    float t = 0.f;
+    for (int j = threadIdx.x & 31; j < VD; j += 32) t += fabsf(__ldg(w + (size_t)e * VD + j));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    l1 = fmaxf(l1, t);
+    bm = fmaxf(bm, fabsf(__ldg(bb + e)));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = l1; red[1][threadIdx.x >> 5] = bm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { l1 = fmaxf(l1, red[0][k]); bm = fmaxf(bm, red[1][k]); }
+    meta[2 * blockIdx.x + 0] = l1 * 1.0001f;                          // margin for the rounding of the sums
+    meta[2 * blockIdx.x + 1] = bm;
+  }
+}
+
+// absmax[img][slot 1] <- bound on max K = max|G| * l1(fc2) + max|b2|  (float bits; K >= 0)
+__global__ void kbound_kernel(unsigned* __restrict__ absmax, const float* __restrict__ meta, int B) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= B) return;
+  const float gmax = __uint_as_float(absmax[img * 4 + 3]);
+  absmax[img * 4 + 1] = __float_as_uint(gmax * meta[2] + meta[3]);
+}
+
+// packed fc1 | packed fc2 | wmax[2], meta[4] (fc_meta_kernel)
 static size_t packed_w_bytes() { return align_up_e((size_t)KK * EB_WTAP_BYTES); }
 size_t embed_tc_packed_weights_bytes() { return 2 * packed_w_bytes() + align_up_e(64); }
 
-int launch_pack_fc_weights(const float* fc1_w, const float* fc2_w, void* packed, size_t packed_bytes, cudaStream_t st) {
+int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, void* packed,
+                           size_t packed_bytes, cudaStream_t st) {
   if (packed_bytes < embed_tc_packed_weights_bytes()) {
     call_state().err = "packed-weights buffer too small";
     return -3;
@@ -313,14 +404,19 @@ int launch_pack_fc_weights(const float* fc1_w, const float* fc2_w, void* packed,
   DAGL_LAUNCH_CHECK();
   pack_fc_kernel<<<KK, 256, 0, st>>>(fc2_w, wmax + 1, w2);
   DAGL_LAUNCH_CHECK();
+  fc_meta_kernel<<<2, 256, 0, st>>>(fc1_w, fc1_b, fc2_w, fc2_b, reinterpret_cast<float*>(wmax + 2));
+  DAGL_LAUNCH_CHECK();
   return 0;
 }
 
 // Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
 // absmax slot 3 (max |G|) must already be filled.  `prepacked` (nullable): weights packed by launch_pack_fc_weights.
+// With `ktiles` (and `colsum`) the key launch writes the graph kernel's fp16 hi|lo key tiles and the per-CTA column sums
+// directly (no fp32 K round trip through HBM, no separate pack pass); absmax slot 1 then holds an a-priori bound on K
+// (the fp16 scale) instead of the measured maximum, and K (fp32) is only written when `K` is non-null.
 int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
                     const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    const void* prepacked, cudaStream_t st) {
+                    const void* prepacked, uint8_t* ktiles, float* colsum, cudaStream_t st) {
   const EmbGeom eg = emb_geom(g);
   if (ws_bytes < embed_tc_workspace_bytes(g)) {
     call_state().err = "embed (tc) workspace too small";
@@ -331,7 +427,7 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
   const uint8_t* packed = static_cast<const uint8_t*>(prepacked);
   if (packed == nullptr) {
-    if (int rc = launch_pack_fc_weights(fc1_w, fc2_w, p, embed_tc_packed_weights_bytes(), st)) return rc;
+    if (int rc = launch_pack_fc_weights(fc1_w, fc1_b, fc2_w, fc2_b, p, embed_tc_packed_weights_bytes(), st)) return rc;
     packed = reinterpret_cast<const uint8_t*>(p);
   }
   const uint8_t* w1 = packed;
@@ -343,9 +439,15 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   const int oy = PADK - g.qpad_top, ox = PADK - g.qpad_left;
   dim3 grid(eg.ntile, 2, g.B);
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q, absmax);
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q, absmax,
+                                                         nullptr, nullptr);
   DAGL_LAUNCH_CHECK();
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K, absmax);
+  if (ktiles != nullptr) {
+    kbound_kernel<<<(g.B + 63) / 64, 64, 0, st>>>(absmax, reinterpret_cast<const float*>(wmax + 2), g.B);
+    DAGL_LAUNCH_CHECK();
+  }
+  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K, absmax,
+                                                         ktiles, colsum);
   DAGL_LAUNCH_CHECK();
   return 0;
 }

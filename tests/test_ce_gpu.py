@@ -142,8 +142,8 @@ def test_prologue_intermediates(dev, rand_weights, impl):
     x = g["x0"]                                  # (2,64,30,41)
     ce = make_ce(rand_weights, dev, impl)
     with torch.no_grad():
-        ce(x.to(dev))
-    torch.cuda.synchronize()
+        ce.forward_debug(x.to(dev))              # the debug entry also materialises the fp32 K array (the product path
+    torch.cuda.synchronize()                     # writes the key embeddings straight into the fp16 key tiles)
     inter = {k: v.cpu() for k, v in ce.intermediates(tuple(x.shape)).items()}
     _, aux = O.ce_forward(rand_weights, x, return_aux=True)
     for name, ref in [("G", aux["G"]), ("theta", aux["theta"]), ("gamma", aux["gamma"]),
@@ -386,3 +386,19 @@ def test_packed_weight_cache_is_invalidated_by_weight_updates(dev, rand_weights)
         y2 = fresh(x)
     assert torch.equal(y1, y2)
     assert not torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("impl", ["tc", "tc4"])
+def test_fused_key_pack_equals_debug_path(dev, rand_weights, impl):
+    """Product path (key embeddings written directly as fp16 key tiles, scale from the a-priori bound) and debug path
+    (same, plus the fp32 K array) give the same output bit for bit; and both agree with the split entry that packs K
+    from fp32 with the measured maximum up to the usual tolerance."""
+    g = load_npz("ce_ragged.npz")
+    x = g["x0"].to(dev)                          # (2,64,30,41)
+    ce = make_ce(rand_weights, dev, impl)
+    with torch.no_grad():
+        y_prod = ce(x)
+        y_dbg, _, _ = ce.forward_debug(x)
+    assert torch.equal(y_prod, y_dbg)
+    yref = g["y0"]
+    assert rel_err(y_prod.cpu(), yref) <= REL_TOL
