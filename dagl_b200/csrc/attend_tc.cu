@@ -205,10 +205,19 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
 // segment that starts at a multiple of 8 pixels lands on a 256-byte aligned smem address.
 __global__ void __launch_bounds__(256)
 pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsigned* __restrict__ absmax,
-                  uint8_t* __restrict__ thp) {
+                  uint8_t* __restrict__ thp, unsigned long long* __restrict__ tilemask /*nullable*/) {
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   if (pix >= tg.NP) return;
+  if (tilemask != nullptr && pix < tg.NT) {            // validity bits of the 48 key slots of tile `pix` (NT < NP)
+    unsigned long long m = 0ull;
+    int kp = pix * TC_BN, x = kp % tg.Wp;
+    for (int r = 0; r < TC_BN; ++r, ++kp) {
+      if (kp < tg.NkP && x < g.W) m |= 1ull << r;
+      if (++x == tg.Wp) x = 0;
+    }
+    tilemask[(size_t)img * tg.NT + pix] = m;
+  }
   const float scale = pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
   const int r = pix / tg.Wp, cc = pix % tg.Wp;
   const int y = r - PADK, x = cc - PADK;
@@ -1668,18 +1677,6 @@ void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, flo
   *colsum = reinterpret_cast<float*>(base + w.colsum);
 }
 
-// validity bits of the 48 key slots of every tile (dummy slots of the padded-flat enumeration are 0)
-__global__ void tilemask_kernel(Geom g, TcGeom tg, unsigned long long* __restrict__ tilemask) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= tg.NT) return;
-  unsigned long long m = 0ull;
-  int kp = t * TC_BN, x = kp % tg.Wp;
-  for (int r = 0; r < TC_BN; ++r, ++kp) {
-    if (kp < tg.NkP && x < g.W) m |= 1ull << r;
-    if (++x == tg.Wp) x = 0;
-  }
-  for (int img = 0; img < g.B; ++img) tilemask[(size_t)img * tg.NT + t] = m;
-}
 
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, int variant, cudaStream_t st) {
   const TcGeom tg = tc_geom(g);
@@ -1738,10 +1735,8 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     float* colsum = nullptr;
     if (Kbar == nullptr) colsum = reinterpret_cast<float*>(base + w.colsum);
     int kblocks = tg.NT;
-    if (a.k_packed) {                                   // the embedding kernel wrote Kp and the column sums already
-      tilemask_kernel<<<(tg.NT + 127) / 128, 128, 0, st>>>(g, tg, tilemask);
-      DAGL_LAUNCH_CHECK();
-      kblocks = a.kblocks;
+    if (a.k_packed) {                                   // the embedding kernel wrote Kp and the column sums already;
+      kblocks = a.kblocks;                              // the tile validity masks come from pack_theta_kernel below
     } else {
       auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
       const size_t smem_k = (size_t)TC_BN * ED * 4;
@@ -1757,7 +1752,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     const size_t smem = (size_t)16 * ED * 4;
     kq<<<dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thrA, thrB, nullptr);
     DAGL_LAUNCH_CHECK();
-    pack_theta_kernel<<<dim3((tg.NP + 255) / 256, g.B), 256, 0, st>>>(g, tg, a.theta, absmax, Thp);
+    pack_theta_kernel<<<dim3((tg.NP + 255) / 256, g.B), 256, 0, st>>>(g, tg, a.theta, absmax, Thp, a.k_packed ? tilemask : nullptr);
     DAGL_LAUNCH_CHECK();
   }
 

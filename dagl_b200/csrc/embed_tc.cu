@@ -110,10 +110,13 @@ pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, u
 
 // G [16][H][W] fp32 -> zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
 __global__ void __launch_bounds__(256)
-pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* __restrict__ absmax,
-              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo) {
+pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restrict__ absmax,
+              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, const float* __restrict__ kmeta /*nullable*/) {
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
+  // fused key pack: absmax slot 1 <- a-priori bound on max K = max|G| * l1(fc2) + max|b2| (float bits; K >= 0), the
+  // fp16 scale of the key tiles; written here because this kernel precedes both embedding launches
+  if (kmeta != nullptr && pix == 0) absmax[img * 4 + 1] = __float_as_uint(__uint_as_float(absmax[img * 4 + 3]) * kmeta[2] + kmeta[3]);
   if (pix >= eg.NPG) return;
   const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
   const int r = pix / eg.Wp, cc = pix % eg.Wp;
@@ -374,14 +377,6 @@ fc_meta_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const
   }
 }
 
-// absmax[img][slot 1] <- bound on max K = max|G| * l1(fc2) + max|b2|  (float bits; K >= 0)
-__global__ void kbound_kernel(unsigned* __restrict__ absmax, const float* __restrict__ meta, int B) {
-  const int img = blockIdx.x * blockDim.x + threadIdx.x;
-  if (img >= B) return;
-  const float gmax = __uint_as_float(absmax[img * 4 + 3]);
-  absmax[img * 4 + 1] = __float_as_uint(gmax * meta[2] + meta[3]);
-}
-
 // packed fc1 | packed fc2 | wmax[2], meta[4] (fc_meta_kernel)
 static size_t packed_w_bytes() { return align_up_e((size_t)KK * EB_WTAP_BYTES); }
 size_t embed_tc_packed_weights_bytes() { return 2 * packed_w_bytes() + align_up_e(64); }
@@ -433,7 +428,8 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   const uint8_t* w1 = packed;
   const uint8_t* w2 = packed + packed_w_bytes();
   const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
-  pack_g_kernel<<<dim3((eg.NPG + 255) / 256, g.B), 256, 0, st>>>(g, eg, G, absmax, ghi, glo);
+  pack_g_kernel<<<dim3((eg.NPG + 255) / 256, g.B), 256, 0, st>>>(g, eg, G, absmax, ghi, glo,
+                                                                 ktiles ? reinterpret_cast<const float*>(wmax + 2) : nullptr);
   DAGL_LAUNCH_CHECK();
 
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
@@ -442,10 +438,6 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q, absmax,
                                                          nullptr, nullptr);
   DAGL_LAUNCH_CHECK();
-  if (ktiles != nullptr) {
-    kbound_kernel<<<(g.B + 63) / 64, 64, 0, st>>>(absmax, reinterpret_cast<const float*>(wmax + 2), g.B);
-    DAGL_LAUNCH_CHECK();
-  }
   embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K, absmax,
                                                          ktiles, colsum);
   DAGL_LAUNCH_CHECK();

@@ -112,11 +112,11 @@ int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const f
 
 // ---------------------------------------------------------------------------
 // gamma = thr_conv(pad4(b)), beta = bias_conv(pad4(b))     (dagl.py:213-215)
-// CTA = 32 consecutive queries (lanes) x 8 channel groups (warps); the SAME padding is a predicate, not a
+// CTA = 32 consecutive queries (lanes) x 16 channel groups (warps); the SAME padding is a predicate, not a
 // copy; both 7x7 filters are staged in smem and read as warp-uniform broadcasts.  The channel-group
 // partials are summed in a fixed order (deterministic).
 // ---------------------------------------------------------------------------
-constexpr int GB_GROUPS = 8;
+constexpr int GB_GROUPS = 16;
 
 __global__ void __launch_bounds__(32 * GB_GROUPS)
 gamma_beta_kernel(Geom g, const float* __restrict__ b, const float* __restrict__ thr_w,
@@ -137,7 +137,7 @@ gamma_beta_kernel(Geom g, const float* __restrict__ b, const float* __restrict__
   bool rok[KS], cok[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) { rok[k] = live && (y0 + k >= 0) && (y0 + k < g.H); cok[k] = (x0 + k >= 0) && (x0 + k < g.W); }
-  float a0 = 0.f, a1 = 0.f;
+  float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};              // two chains per output: the FMA latency is the bound
   for (int ci = grp; ci < g.C; ci += GB_GROUPS) {
     const float* bc = bi + (size_t)ci * g.Nk + y0 * g.W + x0;
     const float2* wc = w_s + ci * KK;
@@ -147,11 +147,11 @@ gamma_beta_kernel(Geom g, const float* __restrict__ b, const float* __restrict__
       for (int kx = 0; kx < KS; ++kx) {
         const float v = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
         const float2 w = wc[ky * KS + kx];
-        a0 = fmaf(v, w.x, a0);
-        a1 = fmaf(v, w.y, a1);
+        a0[(ky * KS + kx) & 1] = fmaf(v, w.x, a0[(ky * KS + kx) & 1]);
+        a1[(ky * KS + kx) & 1] = fmaf(v, w.y, a1[(ky * KS + kx) & 1]);
       }
   }
-  red[grp * 32 + lane] = make_float2(a0, a1);
+  red[grp * 32 + lane] = make_float2(a0[0] + a0[1], a1[0] + a1[1]);
   __syncthreads();
   if (grp == 0 && live) {
     float s0 = 0.f, s1 = 0.f;
