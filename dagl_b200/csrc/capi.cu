@@ -304,7 +304,7 @@ int32_t dagl_ce_forward_rows_f32(const DaglCEWeights* w, const float* b, float* 
     call_state().err = "bad query-tile range";
     return DAGL_ERR_INVALID_ARG;
   }
-  return forward_impl(w, b, nullptr, B, H, W, workspace, workspace_bytes, DAGL_IMPL_TC, static_cast<cudaStream_t>(stream),
+  return forward_impl(w, b, nullptr, B, H, W, workspace, workspace_bytes, DAGL_IMPL_AUTO, static_cast<cudaStream_t>(stream),
                       nullptr, nullptr, rows, q_tile_begin, q_tile_end);
 }
 
