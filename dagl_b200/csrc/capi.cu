@@ -12,15 +12,22 @@ CallState& call_state() {
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+void prof_mark(cudaStream_t st) {
+  CallState& s = call_state();
+  if (s.prof_on != 2 || s.prof_n >= PROF_RING) return;
+  if (s.prof_n == 0) cudaEventRecord(s.prof_start[0], st);       // origin: right after the first launch
+  cudaEventRecord(s.prof_stop[s.prof_n++], st);
+}
+
 int prof_begin(cudaStream_t st) {
   CallState& s = call_state();
-  if (!s.prof_on || s.prof_n >= PROF_RING) return 0;
+  if (s.prof_on != 1 || s.prof_n >= PROF_RING) return 0;
   DAGL_CUDA_OK(cudaEventRecord(s.prof_start[s.prof_n], st));
   return 0;
 }
 int prof_end(cudaStream_t st) {
   CallState& s = call_state();
-  if (!s.prof_on || s.prof_n >= PROF_RING) return 0;
+  if (s.prof_on != 1 || s.prof_n >= PROF_RING) return 0;
   DAGL_CUDA_OK(cudaEventRecord(s.prof_stop[s.prof_n], st));
   s.prof_n++;
   return 0;
@@ -355,7 +362,7 @@ int32_t dagl_profile_enable(int32_t on) {
     }
     s.prof_created = true;
   }
-  s.prof_on = on != 0;
+  s.prof_on = on;
   s.prof_n = 0;
   return 0;
 }
@@ -366,7 +373,10 @@ int32_t dagl_profile_read(float* ms, int32_t max) {
   int n = s.prof_n < max ? s.prof_n : max;
   for (int i = 0; i < n; ++i) {
     DAGL_CUDA_OK(cudaEventSynchronize(s.prof_stop[i]));
-    DAGL_CUDA_OK(cudaEventElapsedTime(&ms[i], s.prof_start[i], s.prof_stop[i]));
+    if (s.prof_on == 2)       // time since the previous mark (mark 0: since the origin recorded with it, ~0)
+      DAGL_CUDA_OK(cudaEventElapsedTime(&ms[i], i == 0 ? s.prof_start[0] : s.prof_stop[i - 1], s.prof_stop[i]));
+    else
+      DAGL_CUDA_OK(cudaEventElapsedTime(&ms[i], s.prof_start[i], s.prof_stop[i]));
   }
   s.prof_n = 0;
   return n;

@@ -50,7 +50,7 @@ struct CallState {
   int launches = 0;
   const char* impl = "none";
   // optional event ring around the dominant kernel (dagl_profile_*)
-  bool prof_on = false;
+  int prof_on = 0;                    // 0 off, 1 dominant kernel only, 2 one mark per launch
   int prof_n = 0;
   cudaEvent_t prof_start[PROF_RING];
   cudaEvent_t prof_stop[PROF_RING];
@@ -59,6 +59,7 @@ struct CallState {
 // record helpers: no-ops unless profiling is enabled on this thread
 int prof_begin(cudaStream_t st);
 int prof_end(cudaStream_t st);
+void prof_mark(cudaStream_t st);      // prof_on == 2: one event after every launch (per-launch timeline of a forward)
 CallState& call_state();
 
 #define DAGL_CUDA_OK(expr)                                                           \
@@ -70,10 +71,12 @@ CallState& call_state();
     }                                                                                \
   } while (0)
 
+// after every kernel launch (a stream variable `st` is in scope in every launcher)
 #define DAGL_LAUNCH_CHECK()                   \
   do {                                        \
     ::dagl::call_state().launches++;          \
     DAGL_CUDA_OK(cudaGetLastError());         \
+    ::dagl::prof_mark(st);                    \
   } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -37,7 +37,10 @@ constexpr int EB_WTAP0_BYTES = 2 * EB_N0 * 32;     // 7168: one tap of output ha
 constexpr int EB_WTAP1_BYTES = 2 * EB_N1 * 32;     // 6144
 constexpr int EB_WHALF1_OFF = KK * EB_WTAP0_BYTES; // start of output half 1 in the packed array
 constexpr int EB_WSTAGE_BYTES = EB_WTAP0_BYTES;
-constexpr int EB_WSTAGES = 5;
+#ifndef EB_WSTAGES_N
+#define EB_WSTAGES_N 5
+#endif
+constexpr int EB_WSTAGES = EB_WSTAGES_N;
 constexpr int EB_SM_G = 0;
 constexpr int EB_SM_W = EB_G_BYTES;                                  // 64512 = 63 * 1024
 constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;    // 100352

@@ -163,7 +163,9 @@ int32_t dagl_last_launch_count(void);
  * forward with a pair of CUDA events recorded on the caller's stream (a ring
  * of 256 pairs).  dagl_profile_read() synchronises on the recorded events and
  * returns up to `max` kernel durations in milliseconds, oldest first, and
- * resets the ring.  Returns the number written, <0 on error.                 */
+ * resets the ring.  Returns the number written, <0 on error.
+ * on = 2: development aid — one event after EVERY kernel launch of a forward; read() then returns the time between
+ * consecutive launches' completions (entry 0 is ~0), i.e. a warm, in-pipeline per-launch timeline.             */
 int32_t dagl_profile_enable(int32_t on);
 int32_t dagl_profile_read(float* ms, int32_t max);
 

@@ -1,0 +1,38 @@
+"""Warm, in-pipeline per-launch timeline of one CE.forward (dagl_profile_enable(2): an event after every launch).
+ncu's launch list is cold-cache and serialised; this one keeps L2 state and back-to-back launches (development aid)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dagl_b200
+from dagl_b200 import _lib
+from oracle import ce_oracle as O
+
+NAMES_TC = ["absmax_img", "pack_b", "featmap_tc", "gamma_beta", "pack_g", "embed_tc(Q)", "embed_tc(K)", "kbar", "pack_tiles(Q)",
+            "pack_theta", "rowmax_tc", "attend_tc4", "merge_coef", "fold_partials"]
+dev = torch.device("cuda:0")
+H = W = int(os.environ.get("HW", "256"))
+B = int(os.environ.get("B", "1"))
+params = O.init_ce_params(1000)
+x = torch.randn(B, 64, H, W, generator=torch.Generator().manual_seed(2000)).to(dev)
+ce = dagl_b200.CE(in_channels=64, impl=os.environ.get("IMPL", "auto")); ce.load_state_dict(params); ce = ce.to(dev).eval()
+L = _lib.lib()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+with torch.no_grad():
+    for _ in range(3): ce(x)
+    acc = None
+    reps = 10
+    for _ in range(reps):
+        flush.zero_()
+        L.dagl_profile_enable(2)
+        ce(x)
+        buf = (ctypes.c_float * 256)()
+        n = L.dagl_profile_read(buf, 256)
+        L.dagl_profile_enable(0)
+        v = [buf[i] * 1e3 for i in range(n)]
+        acc = v if acc is None else [a + b for a, b in zip(acc, v)]
+names = NAMES_TC if len(acc) == len(NAMES_TC) else [f"launch {i}" for i in range(len(acc))]
+tot = 0.0
+for nm, t in zip(names, acc):
+    print(f"{nm:16s} {t / reps:8.1f} us")
+    tot += t / reps
+print(f"{'TOTAL':16s} {tot:8.1f} us   ({B}x64x{H}x{W}, impl {ce.last_impl}, L2 flushed before each forward, mean of {reps})")
