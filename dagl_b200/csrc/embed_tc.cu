@@ -37,17 +37,21 @@ constexpr int EB_WTAP0_BYTES = 2 * EB_N0 * 32;     // 7168: one tap of output ha
 constexpr int EB_WTAP1_BYTES = 2 * EB_N1 * 32;     // 6144
 constexpr int EB_WHALF1_OFF = KK * EB_WTAP0_BYTES; // start of output half 1 in the packed array
 constexpr int EB_WSTAGE_BYTES = EB_WTAP0_BYTES;
-#ifndef EB_WSTAGES_N
-#define EB_WSTAGES_N 5
-#endif
-constexpr int EB_WSTAGES = EB_WSTAGES_N;
-constexpr int EB_SM_G = 0;
-constexpr int EB_SM_W = EB_G_BYTES;                                  // 64512 = 63 * 1024
-constexpr int EB_SM_BAR = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;    // 100352
-constexpr int EB_SM_TOTAL = EB_SM_BAR + 128;
-constexpr int EB_THREADS = 192;
-constexpr int EB_TMEM_COLS = 256;                  // per CTA: main (hi.hi) accumulator at column 0, cross-term accumulator at 128
+constexpr int EB_WSTAGES = KS;                     // 7 = one row of taps: tap (ky, kx) of EVERY item uses stage kx (a compile-time
+                                                   // constant in the unrolled issue loop) and every stage completes 7 phases per item.
+                                                   // (14 stages measured no faster: the kernel is bound by the L2 -> SM stream of the
+                                                   // weight taps, 343 KB per 128-pixel item, not by its latency.)
+__host__ __device__ constexpr int eb_stage_uses(int) { return KS; }
+constexpr int EB_SM_G = 0;                                           // two halo stages
+constexpr int EB_SM_W = 2 * EB_G_BYTES;                              // 129024 = 126 * 1024
+constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-sum exchange [4][112] floats
+constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
+constexpr int EB_SM_TOTAL = EB_SM_BAR + 512;             // 8 + 2 * 14 mbarriers + the TMEM base
+constexpr int EB_THREADS = 224;                    // warp 0 weight taps, 1 MMA issuer, 2-5 epilogue, 6 G halos
+constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
+constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
 static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
+static_assert(EB_SM_TOTAL <= 232448, "embed kernel exceeds the 227 KB dynamic shared memory limit");
 
 struct EmbGeom {
   int Wp, NkP, ntile, NPG;
@@ -147,41 +151,65 @@ pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restr
   dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
-// mode 0: keys (every pixel) -> out[y*W+x][196], column sums for Kbar, absmax slot 1
+// mode 0: keys (every pixel) -> out[y*W+x][196] and/or the fp16 key tiles + column sums for Kbar, absmax slot 1
 // mode 1: queries (pixels (4qy+oy, 4qx+ox)) -> out[qy*nqx+qx][196], absmax slot 0
-__global__ void __launch_bounds__(EB_THREADS, 2)
+//
+// Persistent kernel: one CTA per SM walks the work items (image, 128-pixel tile, output half) with a stride of the grid.
+// The G halo and the TMEM accumulators are double buffered, the weight taps stream through one ring that runs across
+// items, so the tensor pipe goes from the last tap of an item straight to the first tap of the next while the epilogue
+// warps drain the previous accumulator (before: two CTAs per SM whose load / MMA / epilogue phases ran in lock step).
+// Work item w -> (image, tile, output half).  Keys: every tile.  Queries: only the tiles that intersect a query row
+// (image row oy + 4 qy), enumerated per query row so that the active items spread evenly over the persistent CTAs
+// (a tile that intersects two query rows of a very narrow image is simply computed twice, with identical results).
+__host__ __device__ inline int embed_tiles_per_query_row(const Geom& g) { return (g.W + EB_M - 1) / EB_M + 1; }
+__host__ __device__ inline int embed_num_items(const Geom& g, const EmbGeom& eg, int mode) {
+  return mode == 0 ? g.B * 2 * eg.ntile : g.B * 2 * g.nqy * embed_tiles_per_query_row(g);
+}
+__device__ __forceinline__ bool embed_item(const Geom& g, const EmbGeom& eg, int mode, int oy, int w, int& img, int& tile, int& eh) {
+  eh = w & 1;
+  if (mode == 0) {
+    img = (w >> 1) / eg.ntile;
+    tile = (w >> 1) % eg.ntile;
+    return true;
+  }
+  const int tpr = embed_tiles_per_query_row(g);
+  const int per_img = g.nqy * tpr;
+  img = (w >> 1) / per_img;
+  const int r = (w >> 1) % per_img;
+  const int y = oy + 4 * (r / tpr);
+  if (y >= g.H) return false;
+  const int p_first = y * eg.Wp;
+  tile = p_first / EB_M + r % tpr;
+  return tile <= (p_first + g.W - 1) / EB_M;
+}
+
+__global__ void __launch_bounds__(EB_THREADS, 1)
 embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __restrict__ ghi,
                 const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
                 const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
                 float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
                 uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
-                float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of this CTA's rows*/) {
+                float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
-  uint64_t* g_full = bars + 0;
-  uint64_t* w_full = bars + 1;                 // [EB_WSTAGES]
-  uint64_t* w_empty = bars + 1 + EB_WSTAGES;   // [EB_WSTAGES]
-  uint64_t* d_full = bars + 1 + 2 * EB_WSTAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 + 2 * EB_WSTAGES);
+  uint64_t* g_full = bars + 0;                   // [2]
+  uint64_t* g_empty = bars + 2;                  // [2]
+  uint64_t* d_full = bars + 4;                   // [2]
+  uint64_t* d_empty = bars + 6;                  // [2] 4 arrivals (one per epilogue warp)
+  uint64_t* w_full = bars + 8;                   // [EB_WSTAGES]
+  uint64_t* w_empty = bars + 8 + EB_WSTAGES;     // [EB_WSTAGES]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * EB_WSTAGES);
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int img = blockIdx.z, tile = blockIdx.x, eh = blockIdx.y;          // eh: which part of the 208 outputs
-  const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
-  const int p0 = tile * EB_M;
-
-  // query mode: skip tiles whose rows hold no query centre
-  if (mode == 1) {
-    const int y_first = p0 / eg.Wp, y_last = min((p0 + EB_M - 1) / eg.Wp, g.H - 1);
-    bool any = false;
-    for (int y = y_first; y <= y_last; ++y) any |= (y >= oy) && (((y - oy) & 3) == 0);
-    if (!any) return;
-  }
+  const int nwork = embed_num_items(g, eg, mode);
 
   if (tid == 0) {
-    mbar_init(g_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(g_full + i, 1); mbar_init(g_empty + i, 1);
+      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4);
+    }
     for (int i = 0; i < EB_WSTAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    mbar_init(d_full, 1);
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<EB_TMEM_COLS>(tmem_ptr);
@@ -191,130 +219,175 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
   const uint32_t tbase = *tmem_ptr;
 
   if (warp == 0) {
+    // ===================== producer: weight taps (one ring that runs across items) =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(g_full, EB_G_BYTES);
-      for (int part = 0; part < 2; ++part) {
-        const uint8_t* src = (part ? glo : ghi) + (size_t)img * eg.NPG * 32;
-        for (int ky = 0; ky < KS; ++ky) {
-          const int first = (p0 + ky * eg.Wp) & ~7;
-          bulk_g2s(smem + EB_SM_G + (part * KS + ky) * EB_SEG_BYTES, src + (size_t)first * 32, EB_SEG_BYTES, g_full);
+      int it = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int img, tile, eh;
+        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
+        const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
+        for (int t = 0; t < KK; ++t) {
+          const int s = t % EB_WSTAGES;
+          const uint32_t use = (uint32_t)(it * eb_stage_uses(s) + t / EB_WSTAGES);      // how often stage s was filled before
+          mbar_wait(w_empty + s, (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(w_full + s, tap_bytes);
+          bulk_g2s(smem + EB_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
         }
+        ++it;
       }
-      const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
-      const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
-      for (int t = 0; t < KK; ++t) {
-        const int s = t % EB_WSTAGES;
-        const uint32_t ph = (uint32_t)(t / EB_WSTAGES) & 1u;
-        mbar_wait(w_empty + s, ph ^ 1u);
-        mbar_arrive_expect_tx(w_full + s, tap_bytes);
-        bulk_g2s(smem + EB_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
+    }
+  } else if (warp == 6) {
+    // ===================== producer: G halos (2 stages, one item ahead of the MMAs) =====================
+    if (elect_one()) {
+      int it = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int img, tile, eh;
+        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        const int p0 = tile * EB_M, hs = it & 1;
+        mbar_wait(g_empty + hs, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(g_full + hs, EB_G_BYTES);
+        for (int part = 0; part < 2; ++part) {
+          const uint8_t* src = (part ? glo : ghi) + (size_t)img * eg.NPG * 32;
+          for (int ky = 0; ky < KS; ++ky) {
+            const int first = (p0 + ky * eg.Wp) & ~7;
+            bulk_g2s(smem + EB_SM_G + hs * EB_G_BYTES + (part * KS + ky) * EB_SEG_BYTES, src + (size_t)first * 32,
+                     EB_SEG_BYTES, g_full + hs);
+          }
+        }
+        ++it;
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (elect_one()) {
-      const uint32_t idesc = instr_desc(EB_M, (uint32_t)ncols, FMT_F16, FMT_F16, 0, 0);
-      mbar_wait(g_full, 0);
-      tc_fence_after();
-      const uint32_t gbase = smem_u32(smem + EB_SM_G);
-      for (int t = 0; t < KK; ++t) {
-        const int s = t % EB_WSTAGES;
-        mbar_wait(w_full + s, (uint32_t)(t / EB_WSTAGES) & 1u);
+      int it = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int img, tile, eh;
+        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        const int p0 = tile * EB_M, hs = it & 1, ab = it & 1;
+        const int ncols = eh ? EB_N1 : EB_N0;
+        const uint32_t idesc = instr_desc(EB_M, (uint32_t)ncols, FMT_F16, FMT_F16, 0, 0);
+        const uint32_t d_main = tbase + ab * EB_ACC_COLS, d_cross = d_main + EB_N0;
+        mbar_wait(g_full + hs, (uint32_t)(it >> 1) & 1u);
+        mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
-        const int ky = t / KS, kx = t % KS;
-        const int off = ((p0 + ky * eg.Wp) & 7) + kx;
+        // Single-thread issue: the 49 taps are fully unrolled with every descriptor a pre-computed base plus an
+        // immediate (a runtime-indexed loop costs ~90 cycles per MMA in descriptor arithmetic and uniform-register
+        // moves and left the tensor pipe idle more than half of the time).
+        const uint32_t gbase = smem_u32(smem + EB_SM_G + hs * EB_G_BYTES);
         // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
-        const uint32_t a_hi = gbase + ky * EB_SEG_BYTES + off * 32;
-        const uint32_t a_lo = a_hi + KS * EB_SEG_BYTES;
-        const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
-                               ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-        const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
-                               ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-        const uint32_t w_hi = smem_u32(smem + EB_SM_W + s * EB_WSTAGE_BYTES);                  // this CTA's output half only
-        const uint64_t db_hi = smem_desc(w_hi, (ncols / 8) * 128, 128);
-        const uint64_t db_lo = smem_desc(w_hi + ncols * 32, (ncols / 8) * 128, 128);
-        // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
-        // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
-        // the epilogue adds the two in round-to-nearest fp32.
-        mma_f16_ss_a_fill(tbase, da_hi, db_hi, idesc, t > 0);                // Gh.Wh
-        mma_f16_ss_a_lastuse(tbase + 128, da_hi, db_lo, idesc, t > 0);       // Gh.Wl
-        mma_f16_ss(tbase + 128, da_lo, db_hi, idesc, 1);                     // Gl.Wh
-        mma_commit(w_empty + s);
+        constexpr uint64_t a_bits = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+        uint32_t a_row[KS];                                       // (start address >> 4) of tap (ky, kx = 0), hi part
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) a_row[ky] = (gbase + ky * EB_SEG_BYTES + (((p0 + ky * eg.Wp) & 7) << 5)) >> 4;
+        // B: K-major no swizzle, this item's output half: LBO = (ncols / 8) * 128, SBO = 128
+        const uint64_t b_bits = ((uint64_t)(((uint32_t)(ncols / 8) * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        const uint32_t w_row = smem_u32(smem + EB_SM_W) >> 4;
+        const uint32_t w_lo = (uint32_t)(ncols * 32) >> 4;        // lo part follows the hi part
+        const uint32_t par0 = (uint32_t)(it * eb_stage_uses(0));
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+          const int ky = t / KS, kx = t % KS, st = t % EB_WSTAGES;    // compile-time after unrolling
+          mbar_wait(w_full + st, (par0 + t / EB_WSTAGES) & 1u);
+          tc_fence_after();
+          const uint64_t da_hi = a_bits | (uint64_t)((a_row[ky] + kx * 2) & 0x3FFF);
+          const uint64_t da_lo = a_bits | (uint64_t)((a_row[ky] + kx * 2 + ((KS * EB_SEG_BYTES) >> 4)) & 0x3FFF);
+          const uint64_t db_hi = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4)) & 0x3FFF);
+          const uint64_t db_lo = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4) + w_lo) & 0x3FFF);
+          // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
+          // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
+          // the epilogue adds the two in round-to-nearest fp32.
+          mma_f16_ss_a_fill(d_main, da_hi, db_hi, idesc, t > 0);               // Gh.Wh
+          mma_f16_ss_a_lastuse(d_cross, da_hi, db_lo, idesc, t > 0);           // Gh.Wl
+          mma_f16_ss(d_cross, da_lo, db_hi, idesc, 1);                         // Gl.Wh
+          mma_commit(w_empty + st);
+        }
+        mma_commit(d_full + ab);
+        mma_commit(g_empty + hs);
+        ++it;
       }
-      mma_commit(d_full);
     }
   } else {
-    // epilogue: thread = pixel row
+    // ===================== epilogue (warps 2-5): thread = pixel row =====================
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
-    const int p = p0 + r;
-    const int y = p / eg.Wp, x = p % eg.Wp;
-    bool valid = (p < eg.NkP) && (x < g.W);
-    size_t orow = 0;
-    if (mode == 0) {
-      orow = (size_t)img * g.Nk + (size_t)y * g.W + x;
-    } else {
-      valid = valid && (y >= oy) && (x >= ox) && (((y - oy) & 3) == 0) && (((x - ox) & 3) == 0);
-      const int qy = (y - oy) >> 2, qx = (x - ox) >> 2;
-      valid = valid && (qy < g.nqy) && (qx < g.nqx);
-      orow = (size_t)img * g.Nq + (size_t)qy * g.nqx + qx;
-    }
-    const float inv = 1.f / (pow2_scale_e(absmax_in[img * 4 + 3], 14) * pow2_scale_e(*wmax, 14));
-    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
+    const uint32_t trow0 = tbase + ((uint32_t)(quad * 32) << 16);
     const bool fused = (mode == 0) && (ktiles != nullptr);
-    // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
-    // (launch_embed_tc), so no pass over K is needed to find its maximum
-    const float kscale = fused ? pow2_scale_e(absmax_in[img * 4 + 1], 14) : 1.f;
     const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
-    const int kt = p / EB_KTILE, kr = p % EB_KTILE;                          // key tile / row of this pixel slot
-    uint8_t* ktile = fused && kt < ntile_k ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * EB_KTILE * EB_N * 2) : nullptr;
     constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
-    float* csum_s = reinterpret_cast<float*>(smem + EB_SM_G);                // the G halo is dead once d_full fires: [4 warps][112]
-    float vmax = 0.f;
-    mbar_wait(d_full, 0);
-    tc_fence_after();
+    float* csum_s = reinterpret_cast<float*>(smem + EB_SM_CSUM);             // [4 warps][112]
+    const float winv = 1.f / pow2_scale_e(*wmax, 14);
+    int it = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      int img, tile, eh;
+      if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+      const int ab = it & 1;
+      const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
+      const int p = tile * EB_M + r;
+      const int y = p / eg.Wp, x = p % eg.Wp;
+      bool valid = (p < eg.NkP) && (x < g.W);
+      size_t orow = 0;
+      if (mode == 0) {
+        orow = (size_t)img * g.Nk + (size_t)y * g.W + x;
+      } else {
+        valid = valid && (y >= oy) && (x >= ox) && (((y - oy) & 3) == 0) && (((x - ox) & 3) == 0);
+        const int qy = (y - oy) >> 2, qx = (x - ox) >> 2;
+        valid = valid && (qy < g.nqy) && (qx < g.nqx);
+        orow = (size_t)img * g.Nq + (size_t)qy * g.nqx + qx;
+      }
+      const float inv = winv / pow2_scale_e(absmax_in[img * 4 + 3], 14);
+      // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
+      // (pack_g_kernel), so no pass over K is needed to find its maximum
+      const float kscale = fused ? pow2_scale_e(absmax_in[img * 4 + 1], 14) : 1.f;
+      const int kt = p / EB_KTILE, kr = p % EB_KTILE;                        // key tile / row of this pixel slot
+      uint8_t* ktile = fused && kt < ntile_k ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * K_HALF) : nullptr;
+      const uint32_t trow = trow0 + ab * EB_ACC_COLS;
+      float vmax = 0.f;
+      mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c16 = 0; c16 < ncols / 16; ++c16) {
-      uint32_t v[16], vc[16];
-      tmem_ld16(trow + c16 * 16, v);
-      tmem_ld16(trow + 128 + c16 * 16, vc);
-      tmem_wait_ld();
-      const int eb = e0 + c16 * 16;
-      float f[16];
+      for (int c16 = 0; c16 < ncols / 16; ++c16) {
+        uint32_t v[16], vc[16];
+        tmem_ld16(trow + c16 * 16, v);
+        tmem_ld16(trow + EB_N0 + c16 * 16, vc);
+        tmem_wait_ld();
+        const int eb = e0 + c16 * 16;
+        float f[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int e = eb + i;
-        const float b = (e < ED) ? __ldg(bias + e) : 0.f;
-        f[i] = (valid && e < ED) ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
-        vmax = fmaxf(vmax, f[i]);
-      }
-      if (valid && out != nullptr) {
-        float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
-        const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
-        for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-      }
-      if (fused) {
-        if (ktile != nullptr) {                                  // dummy slots (x >= W, p >= NkP) get zero rows
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = f[h8 * 8 + 2 * j] * kscale, x1 = f[h8 * 8 + 2 * j + 1] * kscale;
-              const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-              const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-              hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-            }
-            const int kc = eb / 8 + h8;                          // 16-byte chunk column of the K-major no-swizzle tile
-            const uint32_t off = (uint32_t)(kc * (EB_KTILE / 8) * 128 + (kr / 8) * 128 + (kr % 8) * 16);
-            *reinterpret_cast<uint4*>(ktile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(ktile + K_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
+        for (int i = 0; i < 16; ++i) {
+          const int e = eb + i;
+          const float b = (e < ED) ? __ldg(bias + e) : 0.f;
+          f[i] = (valid && e < ED) ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
+          vmax = fmaxf(vmax, f[i]);
         }
-        // column sums over this warp's 32 rows, then over the 4 warps below (Kbar = mean_k K).  Transposing butterfly:
-        // every step halves the columns a lane carries and doubles the rows they cover (8+4+2+1+1 = 16 shuffles instead
-        // of 16 x 5); fixed order, so the result is deterministic.  Lane l ends with column (l >> 1) & 15.
-        {
+        if (valid && out != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
+          const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
+          for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        }
+        if (fused) {
+          if (ktile != nullptr) {                                  // dummy slots (x >= W, p >= NkP) get zero rows
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x0 = f[h8 * 8 + 2 * j] * kscale, x1 = f[h8 * 8 + 2 * j + 1] * kscale;
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              const int kc = eb / 8 + h8;                          // 16-byte chunk column of the K-major no-swizzle tile
+              const uint32_t off = (uint32_t)(kc * (EB_KTILE / 8) * 128 + (kr / 8) * 128 + (kr % 8) * 16);
+              *reinterpret_cast<uint4*>(ktile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(ktile + K_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+          // column sums over this warp's 32 rows, then over the 4 warps below (Kbar = mean_k K).  Transposing butterfly:
+          // every step halves the columns a lane carries and doubles the rows they cover (8+4+2+1+1 = 16 shuffles instead
+          // of 16 x 5); fixed order, so the result is deterministic.  Lane l ends with column (l >> 1) & 15.
           float a8[8], a4[4], a2[2];
           const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
 #pragma unroll
@@ -328,17 +401,22 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
           if ((lane & 1) == 0) csum_s[quad * EB_N0 + c16 * 16 + (lane >> 1)] = a1;
         }
       }
-    }
-    if (fused) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps
-      const int c = quad * 32 + lane;
-      if (c < ncols && e0 + c < ED)
-        colsum[((size_t)img * gridDim.x + tile) * ED + e0 + c] =
-            ((csum_s[c] + csum_s[EB_N0 + c]) + csum_s[2 * EB_N0 + c]) + csum_s[3 * EB_N0 + c];
-    }
+      // this accumulator may be overwritten by the MMAs of the item after next
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + ab);
+      if (fused) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps: csum_s complete
+        if (r < ncols && e0 + r < ED)
+          colsum[((size_t)img * eg.ntile + tile) * ED + e0 + r] =
+              ((csum_s[r] + csum_s[EB_N0 + r]) + csum_s[2 * EB_N0 + r]) + csum_s[3 * EB_N0 + r];
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // ... and read before the next item overwrites it
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
+      ++it;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -437,12 +515,15 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
 
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   const int oy = PADK - g.qpad_top, ox = PADK - g.qpad_left;
-  dim3 grid(eg.ntile, 2, g.B);
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax, wmax + 0, Q, absmax,
-                                                         nullptr, nullptr);
+  int dev = 0, sms = 148;
+  DAGL_CUDA_OK(cudaGetDevice(&dev));
+  DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nwork_q = embed_num_items(g, eg, 1), nwork_k = embed_num_items(g, eg, 0);   // persistent: one CTA per SM
+  embed_tc_kernel<<<nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax,
+                                                                                 wmax + 0, Q, absmax, nullptr, nullptr);
   DAGL_LAUNCH_CHECK();
-  embed_tc_kernel<<<grid, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax, wmax + 1, K, absmax,
-                                                         ktiles, colsum);
+  embed_tc_kernel<<<nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax,
+                                                                                 wmax + 1, K, absmax, ktiles, colsum);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
