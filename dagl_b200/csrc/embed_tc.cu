@@ -37,6 +37,8 @@ constexpr int EB_WTAP0_BYTES = 2 * EB_N0 * 32;     // 7168: one tap of output ha
 constexpr int EB_WTAP1_BYTES = 2 * EB_N1 * 32;     // 6144
 constexpr int EB_WHALF1_OFF = KK * EB_WTAP0_BYTES; // start of output half 1 in the packed array
 constexpr int EB_WSTAGE_BYTES = EB_WTAP0_BYTES;
+constexpr int EB_QA_BYTES = 2 * EB_M * 16 * 2;     // 8192: one tap of a 128-query patch tile, hi | lo, [2 k-chunks][128 rows][16 B]
+constexpr int EB_QSTAGE_BYTES = EB_QA_BYTES + EB_WSTAGE_BYTES;   // query launch: the A operand streams with the weights
 constexpr int EB_WSTAGES = KS;                     // 7 = one row of taps: tap (ky, kx) of EVERY item uses stage kx (a compile-time
                                                    // constant in the unrolled issue loop) and every stage completes 7 phases per item.
                                                    // (14 stages measured no faster: the kernel is bound by the L2 -> SM stream of the
@@ -46,7 +48,8 @@ constexpr int EB_SM_G = 0;                                           // two halo
 constexpr int EB_SM_W = 2 * EB_G_BYTES;                              // 129024 = 126 * 1024
 constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-sum exchange [4][112] floats
 constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
-constexpr int EB_SM_TOTAL = EB_SM_BAR + 512;             // 8 + 2 * 14 mbarriers + the TMEM base
+constexpr int EB_SM_TOTAL = EB_SM_BAR + 512;
+constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 512;   // query launch             // 8 + 2 * 14 mbarriers + the TMEM base
 constexpr int EB_THREADS = 224;                    // warp 0 weight taps, 1 MMA issuer, 2-5 epilogue, 6 G halos
 constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
 constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
@@ -54,7 +57,7 @@ static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
 static_assert(EB_SM_TOTAL <= 232448, "embed kernel exceeds the 227 KB dynamic shared memory limit");
 
 struct EmbGeom {
-  int Wp, NkP, ntile, NPG;
+  int Wp, NkP, ntile, NPG, nqt;
 };
 constexpr int EB_KTILE = 48;                       // key-tile size of the graph kernel (attend_tc.cu TC_BN)
 static EmbGeom emb_geom(const Geom& g) {
@@ -66,6 +69,7 @@ static EmbGeom emb_geom(const Geom& g) {
   int np = (g.H + 2 * PADK) * e.Wp;
   int need = EB_M * e.ntile + 2 * PADK * e.Wp + EB_SEG_PIX + 8;
   e.NPG = ((np > need ? np : need) + 7) & ~7;
+  e.nqt = (g.Nq + EB_M - 1) / EB_M;
   return e;
 }
 
@@ -151,47 +155,38 @@ pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restr
   dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
-// mode 0: keys (every pixel) -> out[y*W+x][196] and/or the fp16 key tiles + column sums for Kbar, absmax slot 1
-// mode 1: queries (pixels (4qy+oy, 4qx+ox)) -> out[qy*nqx+qx][196], absmax slot 0
+// QG = false: keys (every pixel) -> out[y*W+x][196] and/or the fp16 key tiles + column sums for Kbar, absmax slot 1
+// QG = true : queries -> out[q][196], absmax slot 0; the A operand is the gathered patch image (pack_qpatch_kernel)
 //
 // Persistent kernel: one CTA per SM walks the work items (image, 128-pixel tile, output half) with a stride of the grid.
 // The G halo and the TMEM accumulators are double buffered, the weight taps stream through one ring that runs across
 // items, so the tensor pipe goes from the last tap of an item straight to the first tap of the next while the epilogue
 // warps drain the previous accumulator (before: two CTAs per SM whose load / MMA / epilogue phases ran in lock step).
-// Work item w -> (image, tile, output half).  Keys: every tile.  Queries: only the tiles that intersect a query row
-// (image row oy + 4 qy), enumerated per query row so that the active items spread evenly over the persistent CTAs
-// (a tile that intersects two query rows of a very narrow image is simply computed twice, with identical results).
-__host__ __device__ inline int embed_tiles_per_query_row(const Geom& g) { return (g.W + EB_M - 1) / EB_M + 1; }
-__host__ __device__ inline int embed_num_items(const Geom& g, const EmbGeom& eg, int mode) {
-  return mode == 0 ? g.B * 2 * eg.ntile : g.B * 2 * g.nqy * embed_tiles_per_query_row(g);
-}
-__device__ __forceinline__ bool embed_item(const Geom& g, const EmbGeom& eg, int mode, int oy, int w, int& img, int& tile, int& eh) {
+// Work item w -> (image, tile, output half).  Keys: tile = 128 consecutive padded-flat pixel slots.  Queries: tile = 128
+// consecutive queries of the gathered patch image (pack_qpatch_kernel).
+template <bool QG>
+__device__ __forceinline__ void embed_item(const Geom& g, const EmbGeom& eg, int w, int& img, int& tile, int& eh) {
+  const int per_img = QG ? eg.nqt : eg.ntile;
   eh = w & 1;
-  if (mode == 0) {
-    img = (w >> 1) / eg.ntile;
-    tile = (w >> 1) % eg.ntile;
-    return true;
-  }
-  const int tpr = embed_tiles_per_query_row(g);
-  const int per_img = g.nqy * tpr;
   img = (w >> 1) / per_img;
-  const int r = (w >> 1) % per_img;
-  const int y = oy + 4 * (r / tpr);
-  if (y >= g.H) return false;
-  const int p_first = y * eg.Wp;
-  tile = p_first / EB_M + r % tpr;
-  return tile <= (p_first + g.W - 1) / EB_M;
+  tile = (w >> 1) % per_img;
 }
 
+template <bool QG>
 __global__ void __launch_bounds__(EB_THREADS, 1)
-embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __restrict__ ghi,
+embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the gathered query-patch image*/,
                 const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
                 const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
                 float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
                 uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
                 float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EB_SM_BAR);
+  constexpr int STAGE = QG ? EB_QSTAGE_BYTES : EB_WSTAGE_BYTES;      // QG: [A hi 4 KB | A lo 4 KB | weight tap]
+  constexpr int W_OFF = QG ? EB_QA_BYTES : 0;
+  constexpr int SM_W = QG ? 0 : EB_SM_W;                             // queries: no halo stages
+  constexpr int SM_CSUM = SM_W + EB_WSTAGES * STAGE;
+  constexpr int SM_BAR = SM_CSUM + 4 * EB_N0 * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* g_full = bars + 0;                   // [2]
   uint64_t* g_empty = bars + 2;                  // [2]
   uint64_t* d_full = bars + 4;                   // [2]
@@ -202,7 +197,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int nwork = embed_num_items(g, eg, mode);
+  const int nwork = g.B * 2 * (QG ? eg.nqt : eg.ntile);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -224,26 +219,28 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
       int it = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         int img, tile, eh;
-        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        embed_item<QG>(g, eg, w, img, tile, eh);
         const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
         const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
+        const uint8_t* asrc = QG ? ghi + ((size_t)img * eg.nqt + tile) * (size_t)(KK * EB_QA_BYTES) : nullptr;
         for (int t = 0; t < KK; ++t) {
           const int s = t % EB_WSTAGES;
           const uint32_t use = (uint32_t)(it * eb_stage_uses(s) + t / EB_WSTAGES);      // how often stage s was filled before
           mbar_wait(w_empty + s, (use & 1u) ^ 1u);
-          mbar_arrive_expect_tx(w_full + s, tap_bytes);
-          bulk_g2s(smem + EB_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
+          mbar_arrive_expect_tx(w_full + s, tap_bytes + (QG ? EB_QA_BYTES : 0));
+          if (QG) bulk_g2s(smem + SM_W + s * STAGE, asrc + (size_t)t * EB_QA_BYTES, EB_QA_BYTES, w_full + s);
+          bulk_g2s(smem + SM_W + s * STAGE + W_OFF, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
         }
         ++it;
       }
     }
   } else if (warp == 6) {
-    // ===================== producer: G halos (2 stages, one item ahead of the MMAs) =====================
-    if (elect_one()) {
+    // ===================== producer: G halos (2 stages, one item ahead of the MMAs); keys only =====================
+    if (!QG && elect_one()) {
       int it = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         int img, tile, eh;
-        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        embed_item<QG>(g, eg, w, img, tile, eh);
         const int p0 = tile * EB_M, hs = it & 1;
         mbar_wait(g_empty + hs, ((uint32_t)(it >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(g_full + hs, EB_G_BYTES);
@@ -264,12 +261,12 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
       int it = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         int img, tile, eh;
-        if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+        embed_item<QG>(g, eg, w, img, tile, eh);
         const int p0 = tile * EB_M, hs = it & 1, ab = it & 1;
         const int ncols = eh ? EB_N1 : EB_N0;
         const uint32_t idesc = instr_desc(EB_M, (uint32_t)ncols, FMT_F16, FMT_F16, 0, 0);
         const uint32_t d_main = tbase + ab * EB_ACC_COLS, d_cross = d_main + EB_N0;
-        mbar_wait(g_full + hs, (uint32_t)(it >> 1) & 1u);
+        if (!QG) mbar_wait(g_full + hs, (uint32_t)(it >> 1) & 1u);
         mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator
         tc_fence_after();
         // Single-thread issue: the 49 taps are fully unrolled with every descriptor a pre-computed base plus an
@@ -277,13 +274,15 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
         // moves and left the tensor pipe idle more than half of the time).
         const uint32_t gbase = smem_u32(smem + EB_SM_G + hs * EB_G_BYTES);
         // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
-        constexpr uint64_t a_bits = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+        // (queries: the gathered patches arrive with the weight tap: K-major no swizzle, LBO 2048 between the two k-chunks)
+        constexpr uint64_t a_bits = QG ? (((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46))
+                                       : (((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61));
         uint32_t a_row[KS];                                       // (start address >> 4) of tap (ky, kx = 0), hi part
 #pragma unroll
-        for (int ky = 0; ky < KS; ++ky) a_row[ky] = (gbase + ky * EB_SEG_BYTES + (((p0 + ky * eg.Wp) & 7) << 5)) >> 4;
+        for (int ky = 0; ky < KS; ++ky) a_row[ky] = QG ? 0u : (gbase + ky * EB_SEG_BYTES + (((p0 + ky * eg.Wp) & 7) << 5)) >> 4;
         // B: K-major no swizzle, this item's output half: LBO = (ncols / 8) * 128, SBO = 128
         const uint64_t b_bits = ((uint64_t)(((uint32_t)(ncols / 8) * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-        const uint32_t w_row = smem_u32(smem + EB_SM_W) >> 4;
+        const uint32_t w_row = smem_u32(smem + SM_W) >> 4;
         const uint32_t w_lo = (uint32_t)(ncols * 32) >> 4;        // lo part follows the hi part
         const uint32_t par0 = (uint32_t)(it * eb_stage_uses(0));
 #pragma unroll
@@ -291,10 +290,11 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
           const int ky = t / KS, kx = t % KS, st = t % EB_WSTAGES;    // compile-time after unrolling
           mbar_wait(w_full + st, (par0 + t / EB_WSTAGES) & 1u);
           tc_fence_after();
-          const uint64_t da_hi = a_bits | (uint64_t)((a_row[ky] + kx * 2) & 0x3FFF);
-          const uint64_t da_lo = a_bits | (uint64_t)((a_row[ky] + kx * 2 + ((KS * EB_SEG_BYTES) >> 4)) & 0x3FFF);
-          const uint64_t db_hi = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4)) & 0x3FFF);
-          const uint64_t db_lo = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4) + w_lo) & 0x3FFF);
+          const uint32_t a_hi = QG ? w_row + st * (STAGE >> 4) : a_row[ky] + kx * 2;
+          const uint64_t da_hi = a_bits | (uint64_t)(a_hi & 0x3FFF);
+          const uint64_t da_lo = a_bits | (uint64_t)((a_hi + (QG ? (EB_QA_BYTES / 2) >> 4 : (KS * EB_SEG_BYTES) >> 4)) & 0x3FFF);
+          const uint64_t db_hi = b_bits | (uint64_t)((w_row + st * (STAGE >> 4) + (W_OFF >> 4)) & 0x3FFF);
+          const uint64_t db_lo = b_bits | (uint64_t)((w_row + st * (STAGE >> 4) + (W_OFF >> 4) + w_lo) & 0x3FFF);
           // Tensor-core fp32 accumulation truncates relative to the running sum: the two cross terms
           // (~2^-11 of the result) get their own accumulator so that the main chain has 49 steps, not 147;
           // the epilogue adds the two in round-to-nearest fp32.
@@ -304,7 +304,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
           mma_commit(w_empty + st);
         }
         mma_commit(d_full + ab);
-        mma_commit(g_empty + hs);
+        if (!QG) mma_commit(g_empty + hs);
         ++it;
       }
     }
@@ -313,28 +313,27 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
     const uint32_t trow0 = tbase + ((uint32_t)(quad * 32) << 16);
-    const bool fused = (mode == 0) && (ktiles != nullptr);
+    const bool fused = !QG && (ktiles != nullptr);
     const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
     constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
-    float* csum_s = reinterpret_cast<float*>(smem + EB_SM_CSUM);             // [4 warps][112]
+    float* csum_s = reinterpret_cast<float*>(smem + SM_CSUM);             // [4 warps][112]
     const float winv = 1.f / pow2_scale_e(*wmax, 14);
     int it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       int img, tile, eh;
-      if (!embed_item(g, eg, mode, oy, w, img, tile, eh)) continue;
+      embed_item<QG>(g, eg, w, img, tile, eh);
       const int ab = it & 1;
       const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
       const int p = tile * EB_M + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
-      bool valid = (p < eg.NkP) && (x < g.W);
-      size_t orow = 0;
-      if (mode == 0) {
+      bool valid;
+      size_t orow;
+      if (!QG) {
+        valid = (p < eg.NkP) && (x < g.W);
         orow = (size_t)img * g.Nk + (size_t)y * g.W + x;
       } else {
-        valid = valid && (y >= oy) && (x >= ox) && (((y - oy) & 3) == 0) && (((x - ox) & 3) == 0);
-        const int qy = (y - oy) >> 2, qx = (x - ox) >> 2;
-        valid = valid && (qy < g.nqy) && (qx < g.nqx);
-        orow = (size_t)img * g.Nq + (size_t)qy * g.nqx + qx;
+        valid = p < g.Nq;                                              // row = query
+        orow = (size_t)img * g.Nq + p;
       }
       const float inv = winv / pow2_scale_e(absmax_in[img * 4 + 3], 14);
       // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
@@ -414,7 +413,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (mode == 0 ? 1 : 0), __float_as_uint(vmax));
+      if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (QG ? 0 : 1), __float_as_uint(vmax));
       ++it;
     }
   }
@@ -423,12 +422,50 @@ embed_tc_kernel(Geom g, EmbGeom eg, int mode, int oy, int ox, const uint8_t* __r
   if (warp == 1) tmem_dealloc<EB_TMEM_COLS>(tbase);
 }
 
+// Query patches gathered for the query embedding GEMM: for every 128-query tile and tap (ky,kx) the 16-channel vectors of
+// the queries' patch pixel (4qy - top + ky, 4qx - left + kx) of G, fp16 hi | lo, laid out as the K-major no-swizzle UMMA
+// A operand [tap][hi|lo][2 k-chunks][128 rows][8 ch].  Queries are 1/16 of the pixels, so this (0.4 MB per tile) is cheap,
+// unlike unfolding the keys; it turns the query embedding (fc1 on the stride-4 unfold, dagl.py:216-221,248) into a dense
+// [Nq x 784] x [784 x 196] GEMM instead of a 7x7 convolution evaluated at every pixel of the query rows.
+__global__ void __launch_bounds__(256)
+pack_qpatch_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* __restrict__ absmax,
+                   uint8_t* __restrict__ qimg) {
+  const int qt = blockIdx.x / KS, ky = blockIdx.x % KS, img = blockIdx.y;      // one CTA per (query tile, tap row)
+  const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
+  uint8_t* tile = qimg + ((size_t)img * eg.nqt + qt) * (size_t)(KK * EB_QA_BYTES);
+  const float* Gi = G + (size_t)img * CI * g.Nk;
+  for (int o = threadIdx.x; o < KS * 2 * EB_M; o += 256) {              // one 16-byte chunk: 8 channels of (tap, k-chunk, row)
+    const int row = o % EB_M, kc = (o / EB_M) & 1, t = ky * KS + o / (2 * EB_M);
+    const int q = qt * EB_M + row;
+    const int qy = q / g.nqx, qx = q % g.nqx;
+    const int y = qy * SQ - g.qpad_top + t / KS, x = qx * SQ - g.qpad_left + t % KS;
+    const bool inb = (q < g.Nq) && y >= 0 && y < g.H && x >= 0 && x < g.W;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f, b = 0.f;
+      if (inb) {
+        a = __ldg(Gi + (size_t)(kc * 8 + 2 * j) * g.Nk + (size_t)y * g.W + x) * scale;
+        b = __ldg(Gi + (size_t)(kc * 8 + 2 * j + 1) * g.Nk + (size_t)y * g.W + x) * scale;
+      }
+      const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
+      const __half l0 = __float2half_rn(a - __half2float(h0)), l1 = __float2half_rn(b - __half2float(h1));
+      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    uint8_t* dst = tile + (size_t)t * EB_QA_BYTES + (size_t)(kc * EB_M + row) * 16;     // [kc][row] chunk order
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + EB_QA_BYTES / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------
 static inline size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t embed_tc_workspace_bytes(const Geom& g) {
   const EmbGeom eg = emb_geom(g);
-  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64);   // = maps + embed_tc_packed_weights_bytes()
+  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64) +   // maps + packed weights
+         align_up_e((size_t)g.B * eg.nqt * KK * EB_QA_BYTES);                                                         // query patch tiles
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
@@ -513,17 +550,22 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
                                                                  ktiles ? reinterpret_cast<const float*>(wmax + 2) : nullptr);
   DAGL_LAUNCH_CHECK();
 
-  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
-  const int oy = PADK - g.qpad_top, ox = PADK - g.qpad_left;
+  uint8_t* qimg = reinterpret_cast<uint8_t*>(p) + embed_tc_packed_weights_bytes();       // after the (possibly unused) weight slot
   int dev = 0, sms = 148;
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int nwork_q = embed_num_items(g, eg, 1), nwork_k = embed_num_items(g, eg, 0);   // persistent: one CTA per SM
-  embed_tc_kernel<<<nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 1, oy, ox, ghi, glo, w1, fc1_b, absmax,
-                                                                                 wmax + 0, Q, absmax, nullptr, nullptr);
+  // queries: gather the patches, then a dense GEMM against fc1
+  pack_qpatch_kernel<<<dim3(eg.nqt * KS, g.B), 256, 0, st>>>(g, eg, G, absmax, qimg);
   DAGL_LAUNCH_CHECK();
-  embed_tc_kernel<<<nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, 0, 0, 0, ghi, glo, w2, fc2_b, absmax,
-                                                                                 wmax + 1, K, absmax, ktiles, colsum);
+  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMQ_TOTAL));
+  const int nwork_q = g.B * 2 * eg.nqt, nwork_k = g.B * 2 * eg.ntile;                     // persistent: one CTA per SM
+  embed_tc_kernel<true><<<nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st>>>(g, eg, qimg, nullptr, w1, fc1_b, absmax,
+                                                                                        wmax + 0, Q, absmax, nullptr, nullptr);
+  DAGL_LAUNCH_CHECK();
+  // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given
+  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
+  embed_tc_kernel<false><<<nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, ghi, glo, w2, fc2_b, absmax,
+                                                                                        wmax + 1, K, absmax, ktiles, colsum);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
