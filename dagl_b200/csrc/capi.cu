@@ -158,14 +158,15 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   bool k_packed = false;
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
   if (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g)) {
+    const GammaBetaArgs gb{w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta};       // computed inside the b-repack launch
     if ((rc = launch_feature_maps_tc(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, base + L.feat,
                                      L.embed - L.feat,
                                      w->packed_fc ? static_cast<const char*>(w->packed_fc) + embed_tc_packed_weights_bytes() : nullptr,
-                                     st))) return rc;
+                                     &gb, st))) return rc;
   } else {
     if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
+    if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
   }
-  if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
   if (impl == DAGL_IMPL_SIMT) {
     if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax, AMAX_Q, st))) return rc;
     if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax, AMAX_K, st))) return rc;

@@ -14,6 +14,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include "common.cuh"
+#include "prologue.cuh"
 #include "tc_utils.cuh"
 
 namespace dagl {
@@ -115,10 +116,23 @@ pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ th_w,
 
 // b [64][H][W] fp32 -> per 16-channel group: zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
 // layout: [img][group][hi|lo][NPG][32 B]
-__global__ void __launch_bounds__(256)
-pack_b_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const unsigned* __restrict__ bmax, uint8_t* __restrict__ bimg) {
-  const int img = blockIdx.z, gq = blockIdx.y;
-  const int pix = blockIdx.x * 256 + threadIdx.x;
+// The same launch also computes gamma / beta (dagl.py:213-215) in its first `n_gb` CTAs: the two parts only share the
+// input, the gamma/beta part is latency-bound (19 us on its own) and hides behind the bandwidth-bound repack.
+__global__ void __launch_bounds__(GB_THREADS)
+pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const unsigned* __restrict__ bmax,
+                         uint8_t* __restrict__ bimg, int n_gb, const float* __restrict__ thr_w, const float* __restrict__ thr_b,
+                         const float* __restrict__ bias_w, const float* __restrict__ bias_b, float* __restrict__ gamma,
+                         float* __restrict__ beta) {
+  extern __shared__ float gb_smem[];
+  if ((int)blockIdx.x < n_gb) {                           // block-uniform branch
+    const int qblocks = (g.Nq + 31) / 32;
+    gamma_beta_body(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta, gb_smem, blockIdx.x % qblocks, blockIdx.x / qblocks);
+    return;
+  }
+  const int pblocks = (eg.NPG + GB_THREADS - 1) / GB_THREADS;
+  const int pb = blockIdx.x - n_gb;
+  const int img = pb / (pblocks * FT_GROUPS), gq = (pb / pblocks) % FT_GROUPS;
+  const int pix = (pb % pblocks) * GB_THREADS + threadIdx.x;
   if (pix >= eg.NPG) return;
   const float scale = pow2_scale_f(bmax[img], 14);
   const int r = pix / eg.Wp, cc = pix % eg.Wp;
@@ -297,10 +311,11 @@ int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* p
   return 0;
 }
 
-// `prepacked` (nullable): weights packed by launch_pack_feat_weights.
+// `prepacked` (nullable): weights packed by launch_pack_feat_weights.  `gb` (nullable): also compute gamma / beta, inside
+// the launch that repacks b.
 int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
                            const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
-                           const void* prepacked, cudaStream_t st) {
+                           const void* prepacked, const GammaBetaArgs* gb, cudaStream_t st) {
   const FtGeom eg = ft_geom(g);
   if (!feature_maps_tc_supported(g) || ws_bytes < feature_maps_tc_workspace_bytes(g)) {
     call_state().err = "feature maps (tc): unsupported channel count or workspace too small";
@@ -320,8 +335,18 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
   const size_t n_img = (size_t)g.C * g.Nk;
   absmax_img_kernel<<<dim3(128, g.B), 256, 0, st>>>(b, n_img, bmax);
   DAGL_LAUNCH_CHECK();
-  pack_b_kernel<<<dim3((eg.NPG + 255) / 256, FT_GROUPS, g.B), 256, 0, st>>>(g, eg, b, bmax, bimg);
-  DAGL_LAUNCH_CHECK();
+  {
+    const int n_gb = gb ? ((g.Nq + 31) / 32) * g.B : 0;
+    const int n_pack = ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * g.B;
+    const size_t smem = gamma_beta_smem_bytes(g.C);
+    if (smem > 48 * 1024)
+      DAGL_CUDA_OK(cudaFuncSetAttribute(pack_b_gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pack_b_gamma_beta_kernel<<<n_gb + n_pack, GB_THREADS, smem, st>>>(g, eg, b, bmax, bimg, n_gb, gb ? gb->thr_w : nullptr,
+                                                                      gb ? gb->thr_b : nullptr, gb ? gb->bias_w : nullptr,
+                                                                      gb ? gb->bias_b : nullptr, gb ? gb->gamma : nullptr,
+                                                                      gb ? gb->beta : nullptr);
+    DAGL_LAUNCH_CHECK();
+  }
   DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
   featmap_tc_kernel<<<dim3(eg.ntile, g.B), FT_THREADS, FT_SM_TOTAL, st>>>(g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax);
   DAGL_LAUNCH_CHECK();

@@ -5,6 +5,7 @@
 // written to HBM here: fc1/fc2 applied to unfolded patches are evaluated as
 // implicit-GEMM 7x7 convolutions that gather straight from the 16-channel map G.
 #include "common.cuh"
+#include "prologue.cuh"
 
 namespace dagl {
 
@@ -116,59 +117,21 @@ int launch_feature_maps(const Geom& g, const float* b, const float* g_w, const f
 // copy; both 7x7 filters are staged in smem and read as warp-uniform broadcasts.  The channel-group
 // partials are summed in a fixed order (deterministic).
 // ---------------------------------------------------------------------------
-constexpr int GB_GROUPS = 16;
-
-__global__ void __launch_bounds__(32 * GB_GROUPS)
+__global__ void __launch_bounds__(GB_THREADS)
 gamma_beta_kernel(Geom g, const float* __restrict__ b, const float* __restrict__ thr_w,
                   const float* __restrict__ thr_b, const float* __restrict__ bias_w,
                   const float* __restrict__ bias_b, float* __restrict__ gamma, float* __restrict__ beta) {
   extern __shared__ float smem[];
-  float2* w_s = reinterpret_cast<float2*>(smem);                      // [C*49] (thr, bias)
-  float2* red = reinterpret_cast<float2*>(smem) + g.C * KK;           // [GB_GROUPS][32]
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const int img = blockIdx.y;
-  for (int i = threadIdx.x; i < g.C * KK; i += 32 * GB_GROUPS) w_s[i] = make_float2(__ldg(thr_w + i), __ldg(bias_w + i));
-  __syncthreads();
-  const int q = blockIdx.x * 32 + lane;
-  const bool live = q < g.Nq;
-  const int qy = live ? q / g.nqx : 0, qx = live ? q % g.nqx : 0;
-  const int y0 = qy * SQ - g.qpad_top, x0 = qx * SQ - g.qpad_left;
-  const float* bi = b + (size_t)img * g.C * g.Nk;
-  bool rok[KS], cok[KS];
-#pragma unroll
-  for (int k = 0; k < KS; ++k) { rok[k] = live && (y0 + k >= 0) && (y0 + k < g.H); cok[k] = (x0 + k >= 0) && (x0 + k < g.W); }
-  float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};              // two chains per output: the FMA latency is the bound
-  for (int ci = grp; ci < g.C; ci += GB_GROUPS) {
-    const float* bc = bi + (size_t)ci * g.Nk + y0 * g.W + x0;
-    const float2* wc = w_s + ci * KK;
-#pragma unroll
-    for (int ky = 0; ky < KS; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const float v = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
-        const float2 w = wc[ky * KS + kx];
-        a0[(ky * KS + kx) & 1] = fmaf(v, w.x, a0[(ky * KS + kx) & 1]);
-        a1[(ky * KS + kx) & 1] = fmaf(v, w.y, a1[(ky * KS + kx) & 1]);
-      }
-  }
-  red[grp * 32 + lane] = make_float2(a0[0] + a0[1], a1[0] + a1[1]);
-  __syncthreads();
-  if (grp == 0 && live) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < GB_GROUPS; ++k) { const float2 r = red[k * 32 + lane]; s0 += r.x; s1 += r.y; }
-    gamma[(size_t)img * g.Nq + q] = s0 + thr_b[0];
-    beta[(size_t)img * g.Nq + q] = s1 + bias_b[0];
-  }
+  gamma_beta_body(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta, smem, blockIdx.x, blockIdx.y);
 }
 
 int launch_gamma_beta(const Geom& g, const float* b, const float* thr_w, const float* thr_b,
                       const float* bias_w, const float* bias_b, float* gamma, float* beta, cudaStream_t st) {
-  const size_t smem = (size_t)(g.C * KK + GB_GROUPS * 32) * sizeof(float2);
+  const size_t smem = gamma_beta_smem_bytes(g.C);
   if (smem > 48 * 1024)
     DAGL_CUDA_OK(cudaFuncSetAttribute(gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.Nq + 31) / 32, g.B);
-  gamma_beta_kernel<<<grid, 32 * GB_GROUPS, smem, st>>>(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta);
+  gamma_beta_kernel<<<grid, GB_THREADS, smem, st>>>(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta);
   DAGL_LAUNCH_CHECK();
   return 0;
 }

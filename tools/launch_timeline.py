@@ -7,7 +7,7 @@ import dagl_b200
 from dagl_b200 import _lib
 from oracle import ce_oracle as O
 
-NAMES_TC = ["absmax_img", "pack_b", "featmap_tc", "gamma_beta", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar", "pack_tiles(Q)",
+NAMES_TC = ["absmax_img", "pack_b+gamma_beta", "featmap_tc", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar", "pack_tiles(Q)",
             "pack_theta", "rowmax_tc", "attend_tc4", "merge_coef", "fold_partials"]
 dev = torch.device("cuda:0")
 H = W = int(os.environ.get("HW", "256"))
