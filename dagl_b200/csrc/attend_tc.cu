@@ -118,6 +118,7 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
                   uint8_t* __restrict__ tiles, unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ Kbar, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float* __restrict__ thrA, float* __restrict__ thrB, float* __restrict__ colsum_partial) {
+  pdl_prologue();
   extern __shared__ __align__(16) float rows_s[];            // [RPB][196]
   constexpr int BPT = ROWS / RPB;                            // blocks per tile
   const int t = blockIdx.x / BPT, r0 = (blockIdx.x % BPT) * RPB, img = blockIdx.y, tid = threadIdx.x;
@@ -206,6 +207,7 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
 __global__ void __launch_bounds__(256)
 pack_theta_kernel(Geom g, TcGeom tg, const float* __restrict__ theta, const unsigned* __restrict__ absmax,
                   uint8_t* __restrict__ thp, unsigned long long* __restrict__ tilemask /*nullable*/) {
+  pdl_prologue();
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   if (pix >= tg.NP) return;
@@ -607,6 +609,7 @@ constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
                  int qt_base, int qt_end, unsigned* __restrict__ smax) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
   uint64_t* q_ready = bars + 0;   // 128 arrivals: the query tiles are in TMEM
@@ -740,6 +743,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_BAR);
   uint64_t* q_full = bars + 0;
@@ -1135,6 +1139,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][4][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
   uint64_t* q_ready = bars + 0;   // query tile resident in TMEM (128 arrivals)
@@ -1601,6 +1606,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 // coef[b][s][q] = 1 / sum_{s,h} l   (fixed-reference partials merge by plain sums)
 __global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int nparts, int q_begin, int q_end,
                                         const float* __restrict__ lpart, float* __restrict__ coef) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Nq) return;
   const int img = i / Nq, q = i % Nq;
@@ -1750,9 +1756,9 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     }
     auto kq = pack_tiles_kernel<TC_BM, 0, 16>;
     const size_t smem = (size_t)16 * ED * 4;
-    kq<<<dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st>>>(g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thrA, thrB, nullptr);
+    DAGL_CUDA_OK(launch_pdl(kq, dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st, g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thrA, thrB, nullptr));
     DAGL_LAUNCH_CHECK();
-    pack_theta_kernel<<<dim3((tg.NP + 255) / 256, g.B), 256, 0, st>>>(g, tg, a.theta, absmax, Thp, a.k_packed ? tilemask : nullptr);
+    DAGL_CUDA_OK(launch_pdl(pack_theta_kernel, dim3((tg.NP + 255) / 256, g.B), 256, 0, st, g, tg, a.theta, absmax, Thp, a.k_packed ? tilemask : nullptr));
     DAGL_LAUNCH_CHECK();
   }
 
@@ -1768,25 +1774,25 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     const int max_split = tg.NT;
     if (pre_split > max_split) pre_split = max_split;
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-    rowmax_tc_kernel<<<dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st>>>(tg, Qp, Kp, pre_split, qt_begin, qt_end, smax);
+    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin, qt_end, smax));
     DAGL_LAUNCH_CHECK();
     if (int rc = prof_begin(st)) return rc;
     if (variant == 4) {
       DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
-      attend_tc4_kernel<<<grid, V4_THREADS, S4_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+      DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
                                                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
-                                                           a.nnz);
+                                                           a.nnz));
     } else {
       DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
-      attend_tc2_kernel<<<grid, TC2_THREADS, S2_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
+      DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
                                                             sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
-                                                            a.nnz);
+                                                            a.nnz));
     }
     DAGL_LAUNCH_CHECK();
     if (int rc = prof_end(st)) return rc;
     const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
     const int nq_total = g.B * g.Nq;
-    merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef);
+    DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef));
     DAGL_LAUNCH_CHECK();
     if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
       return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);

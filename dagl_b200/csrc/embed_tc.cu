@@ -123,6 +123,7 @@ pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, u
 __global__ void __launch_bounds__(256)
 pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restrict__ absmax,
               uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, const float* __restrict__ kmeta /*nullable*/) {
+  pdl_prologue();
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   // fused key pack: absmax slot 1 <- a-priori bound on max K = max|G| * l1(fc2) + max|b2| (float bits; K >= 0), the
@@ -180,6 +181,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
                 float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
                 uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
                 float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int STAGE = QG ? EB_QSTAGE_BYTES : EB_WSTAGE_BYTES;      // QG: [A hi 4 KB | A lo 4 KB | weight tap]
   constexpr int W_OFF = QG ? EB_QA_BYTES : 0;
@@ -430,6 +432,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
 __global__ void __launch_bounds__(256)
 pack_qpatch_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* __restrict__ absmax,
                    uint8_t* __restrict__ qimg) {
+  pdl_prologue();
   const int qt = blockIdx.x / KS, ky = blockIdx.x % KS, img = blockIdx.y;      // one CTA per (query tile, tap row)
   const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
   uint8_t* tile = qimg + ((size_t)img * eg.nqt + qt) * (size_t)(KK * EB_QA_BYTES);
@@ -546,8 +549,8 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   const uint8_t* w1 = packed;
   const uint8_t* w2 = packed + packed_w_bytes();
   const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
-  pack_g_kernel<<<dim3((eg.NPG + 255) / 256, g.B), 256, 0, st>>>(g, eg, G, absmax, ghi, glo,
-                                                                 ktiles ? reinterpret_cast<const float*>(wmax + 2) : nullptr);
+  DAGL_CUDA_OK(launch_pdl(pack_g_kernel, dim3((eg.NPG + 255) / 256, g.B), 256, 0, st, g, eg, G, absmax, ghi, glo,
+                                                                 ktiles ? reinterpret_cast<const float*>(wmax + 2) : nullptr));
   DAGL_LAUNCH_CHECK();
 
   uint8_t* qimg = reinterpret_cast<uint8_t*>(p) + embed_tc_packed_weights_bytes();       // after the (possibly unused) weight slot
@@ -555,17 +558,17 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // queries: gather the patches, then a dense GEMM against fc1
-  pack_qpatch_kernel<<<dim3(eg.nqt * KS, g.B), 256, 0, st>>>(g, eg, G, absmax, qimg);
+  DAGL_CUDA_OK(launch_pdl(pack_qpatch_kernel, dim3(eg.nqt * KS, g.B), 256, 0, st, g, eg, G, absmax, qimg));
   DAGL_LAUNCH_CHECK();
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMQ_TOTAL));
   const int nwork_q = g.B * 2 * eg.nqt, nwork_k = g.B * 2 * eg.ntile;                     // persistent: one CTA per SM
-  embed_tc_kernel<true><<<nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st>>>(g, eg, qimg, nullptr, w1, fc1_b, absmax,
-                                                                                        wmax + 0, Q, absmax, nullptr, nullptr);
+  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, fc1_b, absmax,
+                                                                                        wmax + 0, Q, absmax, nullptr, nullptr));
   DAGL_LAUNCH_CHECK();
   // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
-  embed_tc_kernel<false><<<nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st>>>(g, eg, ghi, glo, w2, fc2_b, absmax,
-                                                                                        wmax + 1, K, absmax, ktiles, colsum);
+  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<false>, nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st, g, eg, ghi, glo, w2, fc2_b, absmax,
+                                                                                        wmax + 1, K, absmax, ktiles, colsum));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

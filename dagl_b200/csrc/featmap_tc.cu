@@ -58,6 +58,7 @@ __device__ __forceinline__ float pow2_scale_f(unsigned absmax_bits, int target) 
 
 // max |b| per image -> bmax[img]
 __global__ void absmax_img_kernel(const float* __restrict__ x, size_t n_per_img, unsigned* __restrict__ bmax) {
+  pdl_prologue();
   const int img = blockIdx.y;
   const float4* xi = reinterpret_cast<const float4*>(x + (size_t)img * n_per_img);
   float m = 0.f;
@@ -123,6 +124,7 @@ pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const u
                          uint8_t* __restrict__ bimg, int n_gb, const float* __restrict__ thr_w, const float* __restrict__ thr_b,
                          const float* __restrict__ bias_w, const float* __restrict__ bias_b, float* __restrict__ gamma,
                          float* __restrict__ beta) {
+  pdl_prologue();
   extern __shared__ float gb_smem[];
   if ((int)blockIdx.x < n_gb) {                           // block-uniform branch
     const int qblocks = (g.Nq + 31) / 32;
@@ -167,6 +169,7 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
                   const float* __restrict__ g_b, const float* __restrict__ th_b, const unsigned* __restrict__ bmax,
                   const unsigned* __restrict__ wmax, float* __restrict__ G, float* __restrict__ Th,
                   unsigned* __restrict__ absmax /*[B][AMAX_STRIDE]*/) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_SM_BAR);
   uint64_t* in_full = bars + 0;
@@ -333,7 +336,7 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
 
   DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)g.B * sizeof(unsigned), st));
   const size_t n_img = (size_t)g.C * g.Nk;
-  absmax_img_kernel<<<dim3(128, g.B), 256, 0, st>>>(b, n_img, bmax);
+  DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, g.B), 256, 0, st, b, n_img, bmax));
   DAGL_LAUNCH_CHECK();
   {
     const int n_gb = gb ? ((g.Nq + 31) / 32) * g.B : 0;
@@ -341,14 +344,14 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
     const size_t smem = gamma_beta_smem_bytes(g.C);
     if (smem > 48 * 1024)
       DAGL_CUDA_OK(cudaFuncSetAttribute(pack_b_gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pack_b_gamma_beta_kernel<<<n_gb + n_pack, GB_THREADS, smem, st>>>(g, eg, b, bmax, bimg, n_gb, gb ? gb->thr_w : nullptr,
+    DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, smem, st, g, eg, b, bmax, bimg, n_gb, gb ? gb->thr_w : nullptr,
                                                                       gb ? gb->thr_b : nullptr, gb ? gb->bias_w : nullptr,
                                                                       gb ? gb->bias_b : nullptr, gb ? gb->gamma : nullptr,
-                                                                      gb ? gb->beta : nullptr);
+                                                                      gb ? gb->beta : nullptr));
     DAGL_LAUNCH_CHECK();
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
-  featmap_tc_kernel<<<dim3(eg.ntile, g.B), FT_THREADS, FT_SM_TOTAL, st>>>(g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax);
+  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(eg.ntile, g.B), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

@@ -79,6 +79,7 @@ __global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ O
 __global__ void __launch_bounds__(256)
 fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const float* __restrict__ coef,
                      float* __restrict__ y) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = g.B * 4 * g.Nk;
   if (i >= total) return;
@@ -106,7 +107,7 @@ fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const 
 
 int launch_fold_partials(const Geom& g, int nsplit, const float* Opart, const float* coef, float* y, cudaStream_t st) {
   const int total = g.B * 4 * g.Nk;
-  fold_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, nsplit, Opart, coef, y);
+  DAGL_CUDA_OK(launch_pdl(fold_partials_kernel, (total + 255) / 256, 256, 0, st, g, nsplit, Opart, coef, y));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

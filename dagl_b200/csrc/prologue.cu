@@ -266,6 +266,7 @@ int launch_embed(const Geom& g, const float* G, const float* fc_w, const float* 
 // fp64 chains per column, then a fixed tree), so the result is deterministic.  grid = (7, B): 32 columns
 // per block, 1024 threads.
 __global__ void __launch_bounds__(1024) kbar_kernel(const float* __restrict__ partial, int nblk, int Nk, float* __restrict__ Kbar) {
+  pdl_prologue();
   __shared__ double acc_s[32][33];
   const int img = blockIdx.y;
   const int chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(1024) kbar_kernel(const float* __restrict__ pa
 }
 
 int launch_kbar(const Geom& g, const float* colsum_partial, int nblk, float* Kbar, cudaStream_t st) {
-  kbar_kernel<<<dim3((ED + 31) / 32, g.B), 1024, 0, st>>>(colsum_partial, nblk, g.Nk, Kbar);
+  DAGL_CUDA_OK(launch_pdl(kbar_kernel, dim3((ED + 31) / 32, g.B), 1024, 0, st, colsum_partial, nblk, g.Nk, Kbar));
   DAGL_LAUNCH_CHECK();
   return 0;
 }
