@@ -50,7 +50,7 @@ constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-s
 constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
 constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + EB_N * 4;   // mbarriers + TMEM base (384 B), then the bias vector
 constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + EB_N * 4;   // query launch
-constexpr int EB_THREADS = 256;                    // warps 0, 7 weight taps (even / odd), 1 MMA issuer, 2-5 epilogue, 6 G halos
+constexpr int EB_THREADS = 384;                    // warps 0, 7 weight taps (even / odd), 1 MMA issuer, 2-5 + 8-11 epilogue, 6 G halos
 constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
 constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
 static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
@@ -192,7 +192,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
   uint64_t* g_full = bars + 0;                   // [2]
   uint64_t* g_empty = bars + 2;                  // [2]
   uint64_t* d_full = bars + 4;                   // [2]
-  uint64_t* d_empty = bars + 6;                  // [2] 4 arrivals (one per epilogue warp)
+  uint64_t* d_empty = bars + 6;                  // [2] 8 arrivals (one per epilogue warp)
   uint64_t* w_full = bars + 8;                   // [EB_WSTAGES]
   uint64_t* w_empty = bars + 8 + EB_WSTAGES;     // [EB_WSTAGES]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * EB_WSTAGES);
@@ -204,7 +204,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(g_full + i, 1); mbar_init(g_empty + i, 1);
-      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4);
+      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 8);
     }
     for (int i = 0; i < EB_WSTAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     mbar_init_fence();
@@ -316,7 +316,9 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
       }
     }
   } else {
-    // ===================== epilogue (warps 2-5): thread = pixel row =====================
+    // ===================== epilogue (warps 2-5 and 8-11): thread = pixel row; the two warps of a TMEM lane quadrant
+    // take alternate pairs of 16-column chunks =====================
+    const int egrp = warp >= 8 ? 1 : 0;
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
     const uint32_t trow0 = tbase + ((uint32_t)(quad * 32) << 16);
@@ -405,7 +407,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
       // two chunks per TMEM round trip: the epilogue is one warp per scheduler, so the load latency is otherwise exposed
       const int nch = ncols / 16;
 #pragma unroll 1
-      for (int c16 = 0; c16 < nch; c16 += 2) {
+      for (int c16 = 2 * egrp; c16 < nch; c16 += 4) {
         uint32_t v0[16], w0[16], v1[16], w1[16];
         const bool two = c16 + 1 < nch;
         tmem_ld16(trow + c16 * 16, v0);
@@ -423,11 +425,11 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty + ab);
       if (fused) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");              // the four epilogue warps: csum_s complete
-        if (r < ncols && e0 + r < ED)
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // the eight epilogue warps: csum_s complete
+        if (egrp == 0 && r < ncols && e0 + r < ED)
           colsum[((size_t)img * eg.ntile + tile) * ED + e0 + r] =
               ((csum_s[r] + csum_s[EB_N0 + r]) + csum_s[2 * EB_N0 + r]) + csum_s[3 * EB_N0 + r];
-        asm volatile("bar.sync 1, 128;" ::: "memory");              // ... and read before the next item overwrites it
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // ... and read before the next item overwrites it
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
