@@ -67,7 +67,7 @@ static EmbGeom emb_geom(const Geom& g) {
   const int slots = ((e.NkP + EB_KTILE - 1) / EB_KTILE) * EB_KTILE;     // every slot of every 48-key tile gets written
   e.ntile = (slots + EB_M - 1) / EB_M;
   int np = (g.H + 2 * PADK) * e.Wp;
-  int need = EB_M * (e.ntile + 1) + 2 * PADK * e.Wp + EB_SEG_PIX + 8;      // + one dummy tile: keys are processed in tile pairs
+  const int need = EB_M * e.ntile + 2 * PADK * e.Wp + EB_SEG_PIX + 8;
   e.NPG = ((np > need ? np : need) + 7) & ~7;
   e.nqt = (g.Nq + EB_M - 1) / EB_M;
   return e;
@@ -442,266 +442,6 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
   if (warp == 1) tmem_dealloc<EB_TMEM_COLS>(tbase);
 }
 
-// =============================================================================================================================
-// Key embedding kernel: like embed_tc_kernel<false>, but an item is a PAIR of adjacent 128-pixel tiles that share every weight
-// tap (6 MMAs per tap instead of 3): the kernel is bound by the L2 -> SM stream of the packed fc2 weights (343 KB per pass), so
-// one pass now serves 256 pixels.  Both halos and both accumulator sets (2 x 224 TMEM columns) are live at once; the halos of the
-// next pair load while the two epilogue warp groups (one per tile) drain the accumulators.
-//   warps: 0, 11 weight taps (even / odd) | 1 MMA issuer | 2-5 epilogue of tile 0 | 6-9 epilogue of tile 1 | 10 halos
-// =============================================================================================================================
-constexpr int EK_THREADS = 384;
-constexpr int EK_SM_G = 0;                                            // halo of tile 0, halo of tile 1
-constexpr int EK_SM_W = 2 * EB_G_BYTES;
-constexpr int EK_SM_CSUM = EK_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;    // [2 tiles][4 warps][112] floats
-constexpr int EK_SM_BAR = EK_SM_CSUM + 2 * 4 * EB_N0 * 4;
-constexpr int EK_SM_TOTAL = EK_SM_BAR + 512;
-static_assert(EK_SM_TOTAL <= 232448, "key embedding kernel exceeds the 227 KB dynamic shared memory limit");
-
-__global__ void __launch_bounds__(EK_THREADS, 1)
-embed_keys_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi, const uint8_t* __restrict__ glo,
-                     const uint8_t* __restrict__ wp, const float* __restrict__ bias,
-                     const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|, slot 1 = K bound when fused*/,
-                     const unsigned* __restrict__ wmax, float* __restrict__ out /*nullable: fp32 K [B][Nk][196]*/,
-                     unsigned* __restrict__ absmax_out,
-                     uint8_t* __restrict__ ktiles /*nullable: fp16 hi|lo key tiles of the graph kernel*/,
-                     float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
-  pdl_prologue();
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + EK_SM_BAR);
-  uint64_t* g_full = bars + 0;                   // [2] halo of tile 0 / 1 of the pair
-  uint64_t* g_empty = bars + 2;                  // [2]
-  uint64_t* d_full = bars + 4;                   // both accumulator sets complete
-  uint64_t* d_empty = bars + 5;                  // 8 arrivals (one per epilogue warp)
-  uint64_t* w_full = bars + 6;                   // [EB_WSTAGES]
-  uint64_t* w_empty = bars + 6 + EB_WSTAGES;     // [EB_WSTAGES]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6 + 2 * EB_WSTAGES);
-
-  const int warp = warp_id_uniform();
-  const int tid = threadIdx.x;
-  const int npairs = (eg.ntile + 1) >> 1;
-  const int nwork = g.B * 2 * npairs;
-
-  if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(g_full + i, 1); mbar_init(g_empty + i, 1); }
-    mbar_init(d_full, 1);
-    mbar_init(d_empty, 8);
-    for (int i = 0; i < EB_WSTAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    mbar_init_fence();
-  }
-  if (warp == 1) tmem_alloc<EB_TMEM_COLS>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tmem_ptr;
-
-  if (warp == 0 || warp == 11) {
-    // ===================== producers: weight taps (one ring that runs across items) =====================
-    // A single thread issues a tap (try_wait + expect_tx + bulk copy) every ~300 cycles, about what the tap's six MMAs
-    // take, so two warps share the taps (even / odd); every stage still sees its fills in order.
-    if (elect_one()) {
-      int it = 0;
-      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-        const int eh = w & 1;
-        const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
-        const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
-        for (int t = (warp == 0 ? 0 : 1); t < KK; t += 2) {
-          const int s = t % EB_WSTAGES;
-          const uint32_t use = (uint32_t)(it * eb_stage_uses(s) + t / EB_WSTAGES);      // how often stage s was filled before
-          mbar_wait(w_empty + s, (use & 1u) ^ 1u);
-#ifdef EK_DBG_NO_W
-          mbar_arrive_expect_tx(w_full + s, 16);
-          bulk_g2s(smem + EK_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, 16, w_full + s);
-#else
-          mbar_arrive_expect_tx(w_full + s, tap_bytes);
-          bulk_g2s(smem + EK_SM_W + s * EB_WSTAGE_BYTES, wsrc + (size_t)t * tap_bytes, tap_bytes, w_full + s);
-#endif
-        }
-      }
-    }
-  } else if (warp == 10) {
-    // ===================== producer: the two G halos of a pair =====================
-    if (elect_one()) {
-      int it = 0;
-      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-        const int img = (w >> 1) / npairs, pr = (w >> 1) % npairs;
-        for (int tp = 0; tp < 2; ++tp) {
-          const int p0 = (2 * pr + tp) * EB_M;
-          mbar_wait(g_empty + tp, ((uint32_t)it & 1u) ^ 1u);
-#ifdef EK_DBG_NO_G
-          mbar_arrive_expect_tx(g_full + tp, 16);
-          bulk_g2s(smem + EK_SM_G + tp * EB_G_BYTES, ghi, 16, g_full + tp);
-          continue;
-#endif
-          mbar_arrive_expect_tx(g_full + tp, EB_G_BYTES);
-          for (int part = 0; part < 2; ++part) {
-            const uint8_t* src = (part ? glo : ghi) + (size_t)img * eg.NPG * 32;
-            for (int ky = 0; ky < KS; ++ky) {
-              const int first = (p0 + ky * eg.Wp) & ~7;
-              bulk_g2s(smem + EK_SM_G + tp * EB_G_BYTES + (part * KS + ky) * EB_SEG_BYTES, src + (size_t)first * 32,
-                       EB_SEG_BYTES, g_full + tp);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      int it = 0;
-      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-        const int eh = w & 1, pr = (w >> 1) % npairs;
-        const int ncols = eh ? EB_N1 : EB_N0;
-        const uint32_t idesc = instr_desc(EB_M, (uint32_t)ncols, FMT_F16, FMT_F16, 0, 0);
-        mbar_wait(g_full + 0, (uint32_t)it & 1u);
-        mbar_wait(g_full + 1, (uint32_t)it & 1u);
-        mbar_wait(d_empty, ((uint32_t)it & 1u) ^ 1u);                    // both epilogue groups have drained the accumulators
-        tc_fence_after();
-        // single-thread issue: fully unrolled, every descriptor a pre-computed base plus an immediate
-        constexpr uint64_t a_bits = ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-        uint32_t a_row[2][KS];                                    // (start address >> 4) of tap (ky, kx = 0), hi part, per tile
-#pragma unroll
-        for (int tp = 0; tp < 2; ++tp) {
-          const int p0 = (2 * pr + tp) * EB_M;
-          const uint32_t gbase = smem_u32(smem + EK_SM_G + tp * EB_G_BYTES);
-#pragma unroll
-          for (int ky = 0; ky < KS; ++ky) a_row[tp][ky] = (gbase + ky * EB_SEG_BYTES + (((p0 + ky * eg.Wp) & 7) << 5)) >> 4;
-        }
-        const uint64_t b_bits = ((uint64_t)(((uint32_t)(ncols / 8) * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-        const uint32_t w_row = smem_u32(smem + EK_SM_W) >> 4;
-        const uint32_t w_lo = (uint32_t)(ncols * 32) >> 4;        // lo part follows the hi part
-        const uint32_t par0 = (uint32_t)(it * eb_stage_uses(0));
-#pragma unroll
-        for (int t = 0; t < KK; ++t) {
-          const int ky = t / KS, kx = t % KS, st = t % EB_WSTAGES;    // compile-time after unrolling
-          mbar_wait(w_full + st, (par0 + t / EB_WSTAGES) & 1u);
-          tc_fence_after();
-          const uint64_t db_hi = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4)) & 0x3FFF);
-          const uint64_t db_lo = b_bits | (uint64_t)((w_row + st * (EB_WSTAGE_BYTES >> 4) + w_lo) & 0x3FFF);
-#pragma unroll
-          for (int tp = 0; tp < 2; ++tp) {
-            const uint32_t d_main = tbase + tp * EB_ACC_COLS, d_cross = d_main + EB_N0;
-            const uint64_t da_hi = a_bits | (uint64_t)((a_row[tp][ky] + kx * 2) & 0x3FFF);
-            const uint64_t da_lo = a_bits | (uint64_t)((a_row[tp][ky] + kx * 2 + ((KS * EB_SEG_BYTES) >> 4)) & 0x3FFF);
-            // the two cross terms (~2^-11 of the result) get their own accumulator (see embed_tc_kernel)
-#ifndef EK_DBG_NO_MMA
-            mma_f16_ss_a_fill(d_main, da_hi, db_hi, idesc, t > 0);               // Gh.Wh
-            mma_f16_ss_a_lastuse(d_cross, da_hi, db_lo, idesc, t > 0);           // Gh.Wl
-            mma_f16_ss(d_cross, da_lo, db_hi, idesc, 1);                         // Gl.Wh
-#endif
-          }
-          mma_commit(w_empty + st);
-        }
-        mma_commit(d_full);
-        mma_commit(g_empty + 0);
-        mma_commit(g_empty + 1);
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 2-5: tile 0, warps 6-9: tile 1): thread = pixel row =====================
-    const int tp = (warp - 2) >> 2;
-    const int quad = warp & 3, lane = tid & 31;
-    const int r = quad * 32 + lane;
-    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16) + tp * EB_ACC_COLS;
-    const bool fused = ktiles != nullptr;
-    const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
-    constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
-    float* csum_s = reinterpret_cast<float*>(smem + EK_SM_CSUM) + tp * 4 * EB_N0;   // [4 warps][112]
-    const float winv = 1.f / pow2_scale_e(*wmax, 14);
-    int it = 0;
-    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-      const int eh = w & 1, img = (w >> 1) / npairs, tile = 2 * ((w >> 1) % npairs) + tp;
-      const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
-      const int p = tile * EB_M + r;
-      const int y = p / eg.Wp, x = p % eg.Wp;
-      const bool valid = (p < eg.NkP) && (x < g.W);
-      const size_t orow = (size_t)img * g.Nk + (size_t)y * g.W + x;
-      const float inv = winv / pow2_scale_e(absmax_in[img * 4 + 3], 14);
-      // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
-      // (pack_g_kernel), so no pass over K is needed to find its maximum
-      const float kscale = fused ? pow2_scale_e(absmax_in[img * 4 + 1], 14) : 1.f;
-      const int kt = p / EB_KTILE, kr = p % EB_KTILE;                        // key tile / row of this pixel slot
-      uint8_t* ktile = fused && kt < ntile_k ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * K_HALF) : nullptr;
-      float vmax = 0.f;
-      mbar_wait(d_full, (uint32_t)it & 1u);
-      tc_fence_after();
-#pragma unroll 1
-#ifdef EK_DBG_NO_EPI
-      for (int c16 = 0; c16 < 0; ++c16) {
-#else
-      for (int c16 = 0; c16 < ncols / 16; ++c16) {
-#endif
-        uint32_t v[16], vc[16];
-        tmem_ld16(trow + c16 * 16, v);
-        tmem_ld16(trow + EB_N0 + c16 * 16, vc);
-        tmem_wait_ld();
-        const int eb = e0 + c16 * 16;
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int e = eb + i;
-          const float b = (e < ED) ? __ldg(bias + e) : 0.f;
-          f[i] = (valid && e < ED) ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + b, 0.f) : 0.f;
-          vmax = fmaxf(vmax, f[i]);
-        }
-        if (valid && out != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
-          const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
-          for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        }
-        if (fused) {
-          if (ktile != nullptr) {                                  // dummy slots (x >= W, p >= NkP) get zero rows
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x0 = f[h8 * 8 + 2 * j] * kscale, x1 = f[h8 * 8 + 2 * j + 1] * kscale;
-                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-                hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-              }
-              const int kc = eb / 8 + h8;                          // 16-byte chunk column of the K-major no-swizzle tile
-              const uint32_t off = (uint32_t)(kc * (EB_KTILE / 8) * 128 + (kr / 8) * 128 + (kr % 8) * 16);
-              *reinterpret_cast<uint4*>(ktile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(ktile + K_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-          // column sums over this warp's 32 rows (transposing butterfly: 16 shuffles, fixed order), then over the 4 warps
-          float a8[8], a4[4], a2[2];
-          const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a8[i] = (u16 ? f[8 + i] : f[i]) + __shfl_xor_sync(0xffffffffu, u16 ? f[i] : f[8 + i], 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a4[i] = (u8 ? a8[4 + i] : a8[i]) + __shfl_xor_sync(0xffffffffu, u8 ? a8[i] : a8[4 + i], 8);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) a2[i] = (u4 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, u4 ? a4[i] : a4[2 + i], 4);
-          float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 2);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-          if ((lane & 1) == 0) csum_s[quad * EB_N0 + c16 * 16 + (lane >> 1)] = a1;
-        }
-      }
-      // the accumulators may be overwritten by the MMAs of the next pair
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty);
-      if (fused) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + tp) : "memory");      // this tile's four epilogue warps: csum_s complete
-        if (r < ncols && e0 + r < ED && tile < eg.ntile)
-          colsum[((size_t)img * eg.ntile + tile) * ED + e0 + r] =
-              ((csum_s[r] + csum_s[EB_N0 + r]) + csum_s[2 * EB_N0 + r]) + csum_s[3 * EB_N0 + r];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + tp) : "memory");      // ... and read before the next item overwrites it
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + 1, __float_as_uint(vmax));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<EB_TMEM_COLS>(tbase);
-}
-
 // Query patches gathered for the query embedding GEMM: for every 128-query tile and tap (ky,kx) the 16-channel vectors of
 // the queries' patch pixel (4qy - top + ky, 4qx - left + kx) of G, fp16 hi | lo, laid out as the K-major no-swizzle UMMA
 // A operand [tap][hi|lo][2 k-chunks][128 rows][8 ch].  Queries are 1/16 of the pixels, so this (0.4 MB per tile) is cheap,
@@ -843,9 +583,9 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, fc1_b, absmax,
                                                                                         wmax + 0, Q, absmax, nullptr, nullptr));
   DAGL_LAUNCH_CHECK();
-  // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given.
-  // (embed_keys_tc_kernel, the two-tiles-per-weight-pass variant, measured the same 87 us: with a single accumulator set per
-  // tile its MMA phase and its epilogue run back to back; kept for reference, see DESIGN.md.)
+  // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given
+  // (a two-tiles-per-weight-pass variant measured no faster: with one accumulator set per tile its MMA phase and its
+  // epilogue run back to back)
   const int nwork_k = g.B * 2 * eg.ntile;
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<false>, nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st, g, eg, ghi, glo, w2,

@@ -164,6 +164,10 @@ pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const u
   dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
+// Persistent: one CTA per SM walks the (image, 128-pixel tile) items; the packed weights (72 KB) are loaded ONCE per CTA
+// (they were 40 % of the smem fill of a one-tile CTA, and the kernel is bound by that L2 -> SM traffic), the halo is
+// single-buffered and the two 64-column accumulator sets alternate so that the epilogue of a tile overlaps the halo load
+// and the MMAs of the next.
 __global__ void __launch_bounds__(FT_THREADS, 1)
 featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uint8_t* __restrict__ wpack,
                   const float* __restrict__ g_b, const float* __restrict__ th_b, const unsigned* __restrict__ bmax,
@@ -172,118 +176,151 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_SM_BAR);
-  uint64_t* in_full = bars + 0;
-  uint64_t* d_full = bars + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* w_full = bars + 0;      // weights resident
+  uint64_t* a_full = bars + 1;      // halo of the current item
+  uint64_t* a_empty = bars + 2;     // its MMAs have completed
+  uint64_t* d_full = bars + 3;      // [2]
+  uint64_t* d_empty = bars + 5;     // [2] 4 arrivals (one per epilogue warp)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int img = blockIdx.y, tile = blockIdx.x;
-  const int p0 = tile * FT_M;
+  const int nwork = g.B * eg.ntile;
 
   if (tid == 0) {
-    mbar_init(in_full, 1);
-    mbar_init(d_full, 1);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
     mbar_init_fence();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_ptr);
+  if (warp == 1) tmem_alloc<128>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
 
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(in_full, FT_GROUPS * 2 * 3 * FT_SEG_BYTES + FT_VTAPS * FT_WTAP_BYTES);
-      bulk_g2s(smem + FT_SM_W, wpack, FT_VTAPS * FT_WTAP_BYTES, in_full);
-      for (int gq = 0; gq < FT_GROUPS; ++gq)
-        for (int part = 0; part < 2; ++part) {
-          const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
-          for (int ky = 0; ky < 3; ++ky) {
-            const int first = (p0 + (ky + 2) * eg.Wp) & ~7;           // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
-            bulk_g2s(smem + FT_SM_A + ((gq * 2 + part) * 3 + ky) * FT_SEG_BYTES, src + (size_t)first * 32, FT_SEG_BYTES, in_full);
-          }
-        }
+    // ===================== producer: one bulk copy per lane (24 halo segments; lane 24: the weights, once) ==========
+    const int lane = tid & 31;
+    if (lane == FT_GROUPS * 2 * 3) {
+      mbar_arrive_expect_tx(w_full, FT_VTAPS * FT_WTAP_BYTES);
+      bulk_g2s(smem + FT_SM_W, wpack, FT_VTAPS * FT_WTAP_BYTES, w_full);
+    }
+    int it = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+      const int img = w / eg.ntile, p0 = (w % eg.ntile) * FT_M;
+      if (lane == 0) {
+        mbar_wait(a_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(a_full, FT_GROUPS * 2 * 3 * FT_SEG_BYTES);
+      }
+      __syncwarp();
+      if (lane < FT_GROUPS * 2 * 3) {
+        const int gq = lane / 6, part = (lane / 3) & 1, ky = lane % 3;
+        const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
+        const int first = (p0 + (ky + 2) * eg.Wp) & ~7;                 // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
+        bulk_g2s(smem + FT_SM_A + ((gq * 2 + part) * 3 + ky) * FT_SEG_BYTES, src + (size_t)first * 32, FT_SEG_BYTES, a_full);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (elect_one()) {
-      mbar_wait(in_full, 0);
-      tc_fence_after();
       const uint32_t abase = smem_u32(smem + FT_SM_A), wbase = smem_u32(smem + FT_SM_W);
       constexpr uint32_t id32 = instr_desc(FT_M, 32, FMT_F16, FMT_F16, 0, 0);
       constexpr uint32_t id16 = instr_desc(FT_M, 16, FMT_F16, FMT_F16, 0, 0);
-      // The centre tap carries the theta outputs (N = 32) and goes first in every group, so that the very first MMA
-      // initialises all 32 accumulator columns; the other taps only touch the 16 g columns.
-      const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
-      bool first = true;
+      mbar_wait(w_full, 0);
+      int it = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+        const int p0 = (w % eg.ntile) * FT_M, ab = it & 1;
+        const uint32_t d_main = tbase + ab * 64, d_cross = d_main + 32;
+        mbar_wait(a_full, (uint32_t)it & 1u);
+        mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        // The centre tap carries the theta outputs (N = 32) and goes first in every group, so that the very first MMA
+        // initialises all 32 accumulator columns; the other taps only touch the 16 g columns.
+        const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+        bool first = true;
 #pragma unroll 1
-      for (int gq = 0; gq < FT_GROUPS; ++gq) {
+        for (int gq = 0; gq < FT_GROUPS; ++gq) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const int t = order[i], ky = t / 3, kx = t % 3;
-          const int off = ((p0 + (ky + 2) * eg.Wp) & 7) + kx + 2;
-          const uint32_t a_hi = abase + ((gq * 2 + 0) * 3 + ky) * FT_SEG_BYTES + off * 32;
-          const uint32_t a_lo = abase + ((gq * 2 + 1) * 3 + ky) * FT_SEG_BYTES + off * 32;
-          // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
-          const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
-                                 ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-          const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
-                                 ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-          const uint32_t w_hi = wbase + (gq * 9 + t) * FT_WTAP_BYTES;
-          const uint64_t db_hi = smem_desc(w_hi, FT_N * 16, 128);
-          const uint64_t db_lo = smem_desc(w_hi + FT_WPART_BYTES, FT_N * 16, 128);
-          const uint32_t idesc = (t == 4) ? id32 : id16;
-          const uint32_t acc = first ? 0u : 1u;
-          mma_f16_ss_a_fill(tbase, da_hi, db_hi, idesc, acc);              // bh.Wh  -> main accumulator, columns [0,32)
-          mma_f16_ss_a_lastuse(tbase + 32, da_hi, db_lo, idesc, acc);      // bh.Wl  -> cross accumulator, columns [32,64)
-          mma_f16_ss(tbase + 32, da_lo, db_hi, idesc, 1);                  // bl.Wh
-          first = false;
+          for (int i = 0; i < 9; ++i) {
+            const int t = order[i], ky = t / 3, kx = t % 3;
+            const int off = ((p0 + (ky + 2) * eg.Wp) & 7) + kx + 2;
+            const uint32_t a_hi = abase + ((gq * 2 + 0) * 3 + ky) * FT_SEG_BYTES + off * 32;
+            const uint32_t a_lo = abase + ((gq * 2 + 1) * 3 + ky) * FT_SEG_BYTES + off * 32;
+            // A: K-major SWIZZLE_32B, rows (pixels) 32 B apart, 8-row groups 256 B apart
+            const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                                   ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+            const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+                                   ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+            const uint32_t w_hi = wbase + (gq * 9 + t) * FT_WTAP_BYTES;
+            const uint64_t db_hi = smem_desc(w_hi, FT_N * 16, 128);
+            const uint64_t db_lo = smem_desc(w_hi + FT_WPART_BYTES, FT_N * 16, 128);
+            const uint32_t idesc = (t == 4) ? id32 : id16;
+            const uint32_t acc = first ? 0u : 1u;
+            mma_f16_ss_a_fill(d_main, da_hi, db_hi, idesc, acc);             // bh.Wh  -> main accumulator
+            mma_f16_ss_a_lastuse(d_cross, da_hi, db_lo, idesc, acc);         // bh.Wl  -> cross accumulator
+            mma_f16_ss(d_cross, da_lo, db_hi, idesc, 1);                     // bl.Wh
+            first = false;
+          }
         }
+        mma_commit(d_full + ab);
+        mma_commit(a_empty);
       }
-      mma_commit(d_full);
     }
   } else {
-    // epilogue: thread = pixel row
+    // ===================== epilogue: thread = pixel row =====================
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
-    const int p = p0 + r;
-    const int y = p / eg.Wp, x = p % eg.Wp;
-    const bool valid = (p < eg.NkP) && (x < g.W);
-    const float inv = 1.f / (pow2_scale_f(bmax[img], 14) * pow2_scale_f(*wmax, 14));
-    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
-    mbar_wait(d_full, 0);
-    tc_fence_after();
-    float gmax = 0.f, tmax = 0.f;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {                 // 0: g outputs, 1: theta outputs
-      uint32_t v[16], vc[16];
-      tmem_ld16(trow + half * 16, v);
-      tmem_ld16(trow + 32 + half * 16, vc);
+    const float winv = 1.f / pow2_scale_f(*wmax, 14);
+    int it = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+      const int img = w / eg.ntile, ab = it & 1;
+      const int p = (w % eg.ntile) * FT_M + r;
+      const int y = p / eg.Wp, x = p % eg.Wp;
+      const bool valid = (p < eg.NkP) && (x < g.W);
+      const float inv = winv / pow2_scale_f(bmax[img], 14);
+      const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16) + ab * 64;
+      mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v[2][16], vc[2][16];
+      tmem_ld16(trow, v[0]);
+      tmem_ld16(trow + 16, v[1]);
+      tmem_ld16(trow + 32, vc[0]);
+      tmem_ld16(trow + 48, vc[1]);
       tmem_wait_ld();
-      if (valid) {
-        float* dst = (half ? Th : G) + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
-        const float* bias = half ? th_b : g_b;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty + ab);          // the accumulator set is in registers now
+      float gmax = 0.f, tmax = 0.f;
 #pragma unroll
-        for (int c = 0; c < CI; ++c) {
-          const float o = (__uint_as_float(v[c]) + __uint_as_float(vc[c])) * inv + __ldg(bias + c);
-          dst[(size_t)c * g.Nk] = o;
-          if (half) tmax = fmaxf(tmax, fabsf(o)); else gmax = fmaxf(gmax, fabsf(o));
+      for (int half = 0; half < 2; ++half) {                 // 0: g outputs, 1: theta outputs
+        if (valid) {
+          float* dst = (half ? Th : G) + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
+          const float* bias = half ? th_b : g_b;
+#pragma unroll
+          for (int c = 0; c < CI; ++c) {
+            const float o = (__uint_as_float(v[half][c]) + __uint_as_float(vc[half][c])) * inv + __ldg(bias + c);
+            dst[(size_t)c * g.Nk] = o;
+            if (half) tmax = fmaxf(tmax, fabsf(o)); else gmax = fmaxf(gmax, fabsf(o));
+          }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-      gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    }
-    if (lane == 0 && absmax != nullptr) {
-      atomicMax(absmax + img * AMAX_STRIDE + AMAX_THETA, __float_as_uint(tmax));
-      atomicMax(absmax + img * AMAX_STRIDE + AMAX_G, __float_as_uint(gmax));
+      for (int o = 16; o > 0; o >>= 1) {
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+      }
+      if (lane == 0 && absmax != nullptr) {
+        atomicMax(absmax + img * AMAX_STRIDE + AMAX_THETA, __float_as_uint(tmax));
+        atomicMax(absmax + img * AMAX_STRIDE + AMAX_G, __float_as_uint(gmax));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tbase);
+  if (warp == 1) tmem_dealloc<128>(tbase);
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -351,7 +388,11 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
     DAGL_LAUNCH_CHECK();
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
-  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(eg.ntile, g.B), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax));
+  int dev = 0, sms = 148;
+  DAGL_CUDA_OK(cudaGetDevice(&dev));
+  DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nwork = g.B * eg.ntile;
+  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(nwork < sms ? nwork : sms), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax));
   DAGL_LAUNCH_CHECK();
   return 0;
 }
