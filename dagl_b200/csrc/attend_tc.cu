@@ -599,13 +599,14 @@ constexpr int RM_SM_BAR = RM_SM_K + RM_KSTAGES * K_HALF_BYTES;
 constexpr int RM_SM_TOTAL = RM_SM_BAR + 128;
 constexpr int RM_THREADS = 192;
 constexpr int RM_QCOL = 0;                                  // Qh of the two query tiles: 2 x 104 TMEM columns
-constexpr int RM_DCOL0 = RM_QT * (TC_EP / 2);               // 208: two accumulator buffers of RM_QT x 48 columns
+constexpr int RM_DCOL0 = RM_QT * (TC_EP / 2);               // 208: three accumulator buffers of RM_QT x 48 columns
+constexpr int RM_DBUF = 3;
 constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 
 // smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits.
 // The query tiles live in TMEM (A operand of the MMAs, TS form: 27.7 instead of ~51 cycles per N = 48 MMA) and a CTA
 // serves two query tiles per K fetch (the pre-pass would otherwise be bound by the L2 -> SM traffic of the K tiles).
-//   TMEM: Qh(q0) [0,104) | Qh(q1) [104,208) | D0 [208,304) | D1 [304,400)
+//   TMEM: Qh(q0) [0,104) | Qh(q1) [104,208) | D0 [208,304) | D1 [304,400) | D2 [400,496)
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
                  int qt_base, int qt_end, unsigned* __restrict__ smax) {
@@ -615,9 +616,9 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   uint64_t* q_ready = bars + 0;   // 128 arrivals: the query tiles are in TMEM
   uint64_t* k_full = bars + 1;    // [4]
   uint64_t* k_empty = bars + 5;   // [4]
-  uint64_t* d_full = bars + 9;    // [2]
-  uint64_t* d_empty = bars + 11;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* d_full = bars + 9;    // [3]
+  uint64_t* d_empty = bars + 12;  // [3]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const int qt0 = qt_base + blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
@@ -629,7 +630,7 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   if (tid == 0) {
     mbar_init(q_ready, 128);
     for (int i = 0; i < RM_KSTAGES; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+    for (int i = 0; i < RM_DBUF; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -655,9 +656,9 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
       mbar_wait(q_ready, 0);
       tc_fence_after();
       for (int st = 0; st < nsteps; ++st) {
-        const int s = st % RM_KSTAGES, db = st & 1;
+        const int s = st % RM_KSTAGES, db = st % RM_DBUF;
         mbar_wait(k_full + s, (uint32_t)(st / RM_KSTAGES) & 1u);
-        mbar_wait(d_empty + db, ((uint32_t)(st >> 1) & 1u) ^ 1u);
+        mbar_wait(d_empty + db, ((uint32_t)(st / RM_DBUF) & 1u) ^ 1u);
         tc_fence_after();
         const uint64_t dk = smem_desc(smem_u32(smem + RM_SM_K + s * K_HALF_BYTES), (TC_BN / 8) * 128, 128);
         const uint32_t d0 = tbase + RM_DCOL0 + db * RM_DCOLS;
@@ -690,10 +691,10 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     tmem_wait_st();
     tc_fence_before();
     mbar_arrive(q_ready);
-    float m[RM_QT] = {0.f, 0.f};
+    float m[RM_QT][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // four chains per row: a single one is latency-bound
     for (int st = 0; st < nsteps; ++st) {
-      const int db = st & 1;
-      mbar_wait(d_full + db, (uint32_t)(st >> 1) & 1u);
+      const int db = st % RM_DBUF;
+      mbar_wait(d_full + db, (uint32_t)(st / RM_DBUF) & 1u);
       tc_fence_after();
 #pragma unroll
       for (int qi = 0; qi < RM_QT; ++qi) {
@@ -708,7 +709,7 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
         }
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < TC_BN; ++i) m[qi] = fmaxf(m[qi], __uint_as_float(v[i]));
+        for (int i = 0; i < TC_BN; ++i) m[qi][i & 3] = fmaxf(m[qi][i & 3], __uint_as_float(v[i]));
       }
       tc_fence_before();
       __syncwarp();
@@ -717,7 +718,8 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
 #pragma unroll
     for (int qi = 0; qi < RM_QT; ++qi)
       if (qi < nq_here)
-        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row, __float_as_uint(m[qi]));
+        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row,
+                  __float_as_uint(fmaxf(fmaxf(m[qi][0], m[qi][1]), fmaxf(m[qi][2], m[qi][3]))));
   }
   tc_fence_before();
   __syncthreads();
