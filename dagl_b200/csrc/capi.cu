@@ -120,7 +120,8 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
 
 static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B, int H, int W, void* ws,
                         size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz,
-                        float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0, long long y_img_stride = 0) {
+                        float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0, long long y_img_stride = 0,
+                        bool reuse_b = false) {
   call_state().launches = 0;
   call_state().impl = "none";
   int rc = check_weights(w);
@@ -162,7 +163,7 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     if ((rc = launch_feature_maps_tc(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, base + L.feat,
                                      L.embed - L.feat,
                                      w->packed_fc ? static_cast<const char*>(w->packed_fc) + embed_tc_packed_weights_bytes() : nullptr,
-                                     &gb, st))) return rc;
+                                     &gb, reuse_b, st))) return rc;
   } else {
     if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
     if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
@@ -231,8 +232,10 @@ int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_
   const long long stride = (long long)n_heads * CI * H * W;
   for (int h = 0; h < n_heads; ++h) {
     float* yh = ycat ? ycat + (size_t)h * CI * H * W : nullptr;
+    // the heads share the input: its fp16 repack (and maximum) from head 0 stays valid in the workspace for the others
+    const bool reuse_b = h > 0 && heads[h]->in_channels == heads[0]->in_channels;
     const int rc = forward_impl(heads[h], b, yh, B, H, W, workspace, workspace_bytes, impl,
-                                static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, 0, 0, stride);
+                                static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, 0, 0, stride, reuse_b);
     if (rc) return rc;
     total_launches += call_state().launches;
   }

@@ -128,7 +128,7 @@ int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* p
 struct GammaBetaArgs { const float* thr_w; const float* thr_b; const float* bias_w; const float* bias_b; float* gamma; float* beta; };
 int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
                            const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
-                           const void* prepacked, const GammaBetaArgs* gb, cudaStream_t st);
+                           const void* prepacked, const GammaBetaArgs* gb, bool reuse_b, cudaStream_t st);
 size_t embed_tc_packed_weights_bytes();
 int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, void* packed,
                            size_t packed_bytes, cudaStream_t st);

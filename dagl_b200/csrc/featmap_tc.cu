@@ -352,10 +352,11 @@ int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* p
 }
 
 // `prepacked` (nullable): weights packed by launch_pack_feat_weights.  `gb` (nullable): also compute gamma / beta, inside
-// the launch that repacks b.
+// the launch that repacks b.  `reuse_b`: the repacked input (and its maximum) left in `ws` by the previous call is still
+// valid (same b: the heads of one CES stage), so only the gamma / beta part of that launch runs.
 int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
                            const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
-                           const void* prepacked, const GammaBetaArgs* gb, cudaStream_t st) {
+                           const void* prepacked, const GammaBetaArgs* gb, bool reuse_b, cudaStream_t st) {
   const FtGeom eg = ft_geom(g);
   if (!feature_maps_tc_supported(g) || ws_bytes < feature_maps_tc_workspace_bytes(g)) {
     call_state().err = "feature maps (tc): unsupported channel count or workspace too small";
@@ -371,16 +372,19 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
   }
   const unsigned* wmax = reinterpret_cast<const unsigned*>(wpack + align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES));
 
-  DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)g.B * sizeof(unsigned), st));
-  const size_t n_img = (size_t)g.C * g.Nk;
-  DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, g.B), 256, 0, st, b, n_img, bmax));
-  DAGL_LAUNCH_CHECK();
+  if (!reuse_b) {
+    DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)g.B * sizeof(unsigned), st));
+    const size_t n_img = (size_t)g.C * g.Nk;
+    DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, g.B), 256, 0, st, b, n_img, bmax));
+    DAGL_LAUNCH_CHECK();
+  }
   {
     const int n_gb = gb ? ((g.Nq + 31) / 32) * g.B : 0;
-    const int n_pack = ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * g.B;
+    const int n_pack = reuse_b ? 0 : ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * g.B;
     const size_t smem = gamma_beta_smem_bytes(g.C);
     if (smem > 48 * 1024)
       DAGL_CUDA_OK(cudaFuncSetAttribute(pack_b_gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_gb + n_pack > 0)
     DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, smem, st, g, eg, b, bmax, bimg, n_gb, gb ? gb->thr_w : nullptr,
                                                                       gb ? gb->thr_b : nullptr, gb ? gb->bias_w : nullptr,
                                                                       gb ? gb->bias_b : nullptr, gb ? gb->gamma : nullptr,
