@@ -1,0 +1,96 @@
+"""Backward for ``dagl_b200.CE`` (the reference trains through plain autograd,
+DN_Gray/trainer.py:51-57; a forward-only head would silently break ``train.py``).
+
+The forward value comes from the CUDA path.  The backward re-evaluates the block with differentiable torch ops ON THE
+DEVICE and lets autograd differentiate that recompute (flash-attention style: nothing of the N_q x N_k score matrix is
+kept between forward and backward).  The recompute is written in the convolution form of SURVEY.md App. A (embeddings as
+7x7 convolutions, row mean taken per query chunk) and processes the queries in checkpointed chunks, so the memory of a
+backward is O(chunk x N_k) instead of the reference's ~20 N_q x N_k temporaries.
+
+Gradient semantics are the reference's (dagl.py:250-264): the gradient flows through ``S``, through the row mean, through
+``mask = relu(S - mu*gamma + beta)`` where it multiplies the logits, and through the softmax; the 0/1 factor ``mask_b``
+carries none.  ``W`` (unused in forward) gets no gradient, as in the reference.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+
+def _same_pad(n: int, k: int, s: int):
+    total = max(0, ((n + s - 1) // s - 1) * s + k - n)
+    return total // 2, total - total // 2
+
+
+def _rows(Qc, Kt, Vt, gamma_c, beta_c, scale: float):
+    """Aggregation rows of one query chunk: [n, 784]."""
+    S = Qc @ Kt                                                     # [n, Nk]
+    mu = S.mean(dim=1, keepdim=True)
+    m = F.relu(S - mu * gamma_c.unsqueeze(1) + beta_c.unsqueeze(1))
+    P = torch.softmax(S * m * scale, dim=1) * (m != 0).to(S.dtype)
+    return P @ Vt
+
+
+def ce_recompute(b: torch.Tensor, p: Sequence[torch.Tensor], ksize: int = 7, stride_q: int = 4, scale: float = 10.0,
+                 q_chunk: int = 1024) -> torch.Tensor:
+    """Differentiable torch evaluation of the graph block (device tensors).  ``p`` = (g_w, g_b, theta_w, theta_b,
+    fc1_w, fc1_b, fc2_w, fc2_b, thr_w, thr_b, bias_w, bias_b)."""
+    g_w, g_b, th_w, th_b, fc1_w, fc1_b, fc2_w, fc2_b, thr_w, thr_b, bias_w, bias_b = p
+    B, _, H, W = b.shape
+    ci = g_w.shape[0]
+    pad_k = ksize // 2
+    (pt, pb), (pl, pr) = _same_pad(H, ksize, stride_q), _same_pad(W, ksize, stride_q)
+    G = F.conv2d(b, g_w, g_b, padding=1)
+    Th = F.conv2d(b, th_w, th_b)
+    b4 = F.pad(b, (pl, pr, pt, pb))
+    gamma = F.conv2d(b4, thr_w, thr_b, stride=stride_q).flatten(1)                       # [B, Nq]
+    beta = F.conv2d(b4, bias_w, bias_b, stride=stride_q).flatten(1)
+    e = fc1_w.shape[0]
+    Q = F.relu(F.conv2d(F.pad(G, (pl, pr, pt, pb)), fc1_w.view(e, ci, ksize, ksize), fc1_b, stride=stride_q))
+    K = F.relu(F.conv2d(G, fc2_w.view(e, ci, ksize, ksize), fc2_b, padding=pad_k))
+    Q = Q.flatten(2).transpose(1, 2)                                                    # [B, Nq, 196]
+    Kt = K.flatten(2)                                                                   # [B, 196, Nk]
+    Vt = F.unfold(Th, ksize, padding=pad_k).transpose(1, 2)                             # [B, Nk, 784]
+    nq = Q.shape[1]
+    outs: List[torch.Tensor] = []
+    for i in range(B):
+        rows = []
+        for s in range(0, nq, q_chunk):
+            t = min(nq, s + q_chunk)
+            args = (Q[i, s:t], Kt[i], Vt[i], gamma[i, s:t], beta[i, s:t], scale)
+            rows.append(checkpoint(_rows, *args, use_reentrant=False) if nq > q_chunk else _rows(*args))
+        O = torch.cat(rows, dim=0)                                                      # [Nq, 784]
+        outs.append(O.t().unsqueeze(0))
+    O = torch.cat(outs, dim=0)                                                          # [B, 784, Nq]
+    y = F.fold(O, (H, W), ksize, padding=pad_k, stride=stride_q)
+    cnt = F.fold(F.unfold(torch.ones(1, 1, H, W, dtype=b.dtype, device=b.device), ksize, padding=pad_k, stride=stride_q),
+                 (H, W), ksize, padding=pad_k, stride=stride_q)
+    return y / cnt
+
+
+class CEFunction(torch.autograd.Function):
+    """forward: the CUDA path (``module._forward_cuda``); backward: autograd through ``ce_recompute``."""
+
+    @staticmethod
+    def forward(ctx, module, b, *params):
+        with torch.no_grad():
+            y = module._forward_cuda(b)
+        ctx.module = module
+        ctx.save_for_backward(b, *params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        b, *params = ctx.saved_tensors
+        need = ctx.needs_input_grad[1:]
+        m = ctx.module
+        with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+            leaves = [t.detach().requires_grad_(bool(n)) for t, n in zip([b] + params, need)]
+            y = ce_recompute(leaves[0], leaves[1:], ksize=m.ksize, stride_q=m.stride_1, scale=float(m.softmax_scale))
+            wanted = [t for t in leaves if t.requires_grad]
+            grads = list(torch.autograd.grad(y, wanted, dy.contiguous(), allow_unused=True))
+        out = [grads.pop(0) if t.requires_grad else None for t in leaves]
+        return (None, *out)

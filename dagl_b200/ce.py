@@ -4,7 +4,8 @@
 constructor signature and defaults, same parameter names and shapes (so a
 reference ``state_dict`` / checkpoint loads unchanged, including the unused
 ``W`` conv), same ``forward(b) -> [B, inter_channels, H, W]``.  The body of
-``forward`` is one call through ``dagl_ce_forward_f32`` (include/dagl_b200.h);
+``forward`` is one call through ``dagl_ce_forward_f32`` (include/dagl_b200.h)
+(under autograd the backward differentiates a device-side recompute, autograd.py);
 there is no PyTorch/CPU fallback — CPU tensors, non-fp32 input, unsupported
 configurations or a missing library raise.
 
@@ -123,16 +124,28 @@ class CE(nn.Module):
             raise RuntimeError("CE.forward: fp32 only (the reference default precision)")
         if b.shape[1] != self.in_channels:
             raise RuntimeError(f"CE.forward: expected {self.in_channels} channels, got {b.shape[1]}")
-        if torch.is_grad_enabled() and (b.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "dagl_b200.CE is forward-only; call it under torch.no_grad() (training/backward is a "
-                "'next' row, SURVEY.md §8f)")
+
+    def _needs_grad(self, b: torch.Tensor) -> bool:
+        return torch.is_grad_enabled() and (b.requires_grad or any(p.requires_grad for p in self._grad_params()))
+
+    def _grad_params(self):
+        return [self.g.weight, self.g.bias, self.theta.weight, self.theta.bias, self.fc1[0].weight, self.fc1[0].bias,
+                self.fc2[0].weight, self.fc2[0].bias, self.thr_conv.weight, self.thr_conv.bias, self.bias_conv.weight,
+                self.bias_conv.bias]
 
     def forward(self, b: torch.Tensor) -> torch.Tensor:
+        """``CE.forward`` (dagl.py:207-275).  Under autograd (training, trainer.py:51-57) the value still comes from the
+        CUDA path and the backward differentiates a chunked device-side recompute (dagl_b200/autograd.py)."""
         self._check_input(b)
         if not b.is_cuda:
             raise RuntimeError("dagl_b200.CE has no CPU path: input must be a CUDA tensor "
                                "(use forward_host for pinned host buffers)")
+        if self._needs_grad(b):
+            from .autograd import CEFunction
+            return CEFunction.apply(self, b, *self._grad_params())
+        return self._forward_cuda(b)
+
+    def _forward_cuda(self, b: torch.Tensor) -> torch.Tensor:
         L = _lib.lib()
         b = b.contiguous()
         B, Cc, H, W = b.shape
@@ -275,6 +288,8 @@ def stage_heads_forward(heads, x: torch.Tensor) -> torch.Tensor:
     h0 = heads[0]
     for h in heads:
         h._check_input(x)
+    if any(h._needs_grad(x) for h in heads):          # training: per-head calls carry the autograd graph
+        return torch.cat([h(x) for h in heads], dim=1)
     if not x.is_cuda:
         raise RuntimeError("dagl_b200.CE has no CPU path: input must be a CUDA tensor")
     L = _lib.lib()
