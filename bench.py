@@ -54,10 +54,22 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+CE_SHAPES = {"g.weight": (16, C_IN, 3, 3), "g.bias": (16,), "W.weight": (C_IN, 16, 1, 1), "W.bias": (C_IN,),
+             "theta.weight": (16, C_IN, 1, 1), "theta.bias": (16,), "fc1.0.weight": (196, 784), "fc1.0.bias": (196,),
+             "fc2.0.weight": (196, 784), "fc2.0.bias": (196,), "thr_conv.weight": (1, C_IN, 7, 7), "thr_conv.bias": (1,),
+             "bias_conv.weight": (1, C_IN, 7, 7), "bias_conv.bias": (1,)}
+
+
 def workload_tensors(seed: int):
-    """Synthetic, seeded: random-init head (torch default init statistics) and a randn feature map."""
-    from oracle import ce_oracle as O     # only for the shared seeded parameter generator
-    params = O.init_ce_params(1000 + seed, in_channels=C_IN)
+    """Synthetic, seeded: random-init head (torch's default Conv2d / Linear init statistics: weight and bias
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in))) and a randn feature map.  Self-contained: the product arm does not touch oracle/."""
+    import math
+    gen = torch.Generator().manual_seed(1000 + seed)
+    params = {}
+    for name, shape in CE_SHAPES.items():
+        wshape = CE_SHAPES[name.rsplit(".", 1)[0] + ".weight"]
+        bound = 1.0 / math.sqrt(math.prod(wshape[1:]))
+        params[name] = ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * bound).float()
     gen = torch.Generator().manual_seed(2000 + seed)
     x = torch.randn(B_PER_GPU, C_IN, H, W, generator=gen)
     return params, x
