@@ -95,9 +95,9 @@ static int check_shape(int B, int H, int W) {
 }
 
 static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsigned* absmax, cudaStream_t st) {
-  // measured (profiles/r1): the 4-CTA-cluster kernel wins up to ~256^2 keys; beyond that the K tiles stop fitting in
-  // L2 next to four CTAs' worth of traffic and the 2-CTA kernel is slightly ahead
-  if (impl == DAGL_IMPL_AUTO) impl = ((long long)g.Nk <= 160000) ? DAGL_IMPL_TC4 : DAGL_IMPL_TC;
+  // measured (tools/big_shapes.py, round 1): the 4-CTA-cluster kernel is 10-18 % ahead of the 2-CTA one at every size tried,
+  // 64^2 .. 512^2 keys; larger inputs are unmeasured and stay on the 2-CTA kernel
+  if (impl == DAGL_IMPL_AUTO) impl = ((long long)g.Nk <= 300000) ? DAGL_IMPL_TC4 : DAGL_IMPL_TC;
   if (impl == DAGL_IMPL_TC) {
     call_state().impl = "tc";
     return launch_attend_tc(g, a, absmax, 2, st);
