@@ -156,3 +156,19 @@ def test_patch_reference_swaps_all_heads_and_shares_parameters():
     after = dict(net.named_parameters())
     assert all(after[k] is before[k] for k in before)
     assert all(isinstance(getattr(net.body[8], f"c{s}_{h}"), dagl_b200.CE) for s in (1, 2, 3) for h in (1, 2, 3, 4))
+
+
+def test_bench_workload_generator_matches_oracle_init():
+    """bench.py carries its own seeded head generator (the product arm must not import oracle/); it has to produce the
+    weights the oracle-side generator produces, so that both bench arms and the tests talk about the same head."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    params, x = bench.workload_tensors(3)
+    ref = O.init_ce_params(1003, in_channels=64)
+    assert set(params) == set(ref)
+    assert all(torch.equal(params[k], ref[k]) for k in ref)
+    assert x.shape == (1, 64, 256, 256)
