@@ -14,6 +14,8 @@ feature map per GPU — the shape BASELINE.json's metric is quoted on
                time against the measured bf16 tensor peak (the path is a dense
                contraction pair) + algorithmic HBM GB/s for context
   cpu_baseline the CPU oracle port of the reference timed on this box's cores
+  configs      (N = 1) the other shapes of the path: cfg1 64^2, the reference's chop batches, 512^2, the CES caller
+  strong       (N > 1) ONE image query-sharded over the N GPUs with an NCCL all-gather: ms, speed-up, in-run error
 
 ``--impl reference`` times the oracle port (reference op order, torch CPU,
 all host threads) on the same workload; rank 0 only.
@@ -215,13 +217,93 @@ def cpu_baseline_sample():
             "ms_per_step": best * 1e3}
 
 
+def time_call(fn, iters, flush, warm=2):
+    """Mean ms of fn() over `iters` calls, CUDA events per call, L2 flushed (untimed) before each."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
+def other_configs(ce, dev, flush, peaks):
+    """The other shapes the path really runs at (BASELINE cfg1; the reference's chop leaves, model/__init__.py:179-214;
+    512^2 direct; the CES caller row), timed the same way: reported next to the headline, not as bench lines."""
+    import dagl_b200
+    out = []
+    gen = torch.Generator().manual_seed(77)
+
+    def shape_line(name, B, Hh, Ww, iters, fn=None, heads=1):
+        x = torch.randn(B, C_IN, Hh, Ww, generator=gen).to(dev)
+        f = (lambda: fn(x)) if fn else (lambda: ce(x))
+        with torch.no_grad():
+            ms = time_call(f, iters, flush)
+        nq, nk = ((Hh + 3) // 4) * ((Ww + 3) // 4), Hh * Ww
+        flops = heads * B * 2.0 * nq * nk * 980
+        out.append({"workload": name, "ms": ms, "patches_per_s": heads * B * nq / (ms * 1e-3),
+                    "tflops_alg": flops / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]})
+
+    shape_line("cfg1: CE.forward 1x64x64x64", 1, 64, 64, 50)
+    shape_line("chop leaves of 256^2: CE.forward 64x64x72x72", 64, 72, 72, 10)
+    shape_line("chop leaves of 512^2: CE.forward 256x64x76x76", 256, 76, 76, 5)
+    shape_line("cfg3/cfg5 head: CE.forward 1x64x512x512", 1, 512, 512, 5)
+    torch.manual_seed(5)
+    ces = dagl_b200.CES(in_channels=C_IN).to(dev).eval()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        shape_line("CES.forward 1x64x64x64 (12 heads, 3 stage calls + 8 ResBlocks)", 1, 64, 64, 20, fn=ces, heads=12)
+        shape_line("CES.forward 64x64x72x72 (chop batch)", 64, 72, 72, 3, fn=ces, heads=12)
+        shape_line("CES.forward 1x64x256x256 (direct)", 1, 256, 256, 5, fn=ces, heads=12)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    return out
+
+
+def strong_scaling(ce, dev, flush, world, rank, params):
+    """ONE image sharded over all ranks by query tiles (CE.forward_query_sharded: redundant prologue, fused graph stage
+    on this rank's tiles, one NCCL all-gather of the aggregation rows, fold): ms (max over ranks), speed-up against the
+    same image on one GPU, and the in-run difference between the sharded and the single-GPU result."""
+    import torch.distributed as dist
+    from dagl_b200 import parallel
+    rec = []
+    for size, iters in ((256, 20), (512, 5)):
+        gen = torch.Generator().manual_seed(4242 + size)                 # the same image on every rank
+        x = torch.randn(1, C_IN, size, size, generator=gen).to(dev)
+        with torch.no_grad():
+            y1 = ce(x)
+            ys = ce.forward_query_sharded(x)
+            torch.cuda.synchronize()
+            err = float((ys - y1).abs().max() / y1.abs().max())
+            dist.barrier()
+            ms_single = time_call(lambda: ce(x), iters, flush)
+            dist.barrier()
+            ms_shard = time_call(lambda: ce.forward_query_sharded(x), iters, flush)
+        ms_shard = parallel.max_over_ranks(ms_shard, dev)
+        ms_single = parallel.max_over_ranks(ms_single, dev)
+        err = parallel.max_over_ranks(err, dev)
+        nq = (size // 4) ** 2
+        rec.append({"workload": f"CE.forward 1x{C_IN}x{size}x{size}, ONE image over {world} GPUs (query-tile sharding + all-gather of rows)",
+                    "ms_sharded": ms_shard, "ms_single_gpu": ms_single, "speedup": ms_single / ms_shard,
+                    "patches_per_s": nq / (ms_shard * 1e-3), "rel_err_vs_single_gpu": err,
+                    "allgather_bytes": nq * 784 * 4})
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="auto", choices=["auto", "simt", "tc", "tc1", "tc4", "reference"])
+    ap.add_argument("--impl", default="auto", choices=["auto", "simt", "tc", "tc4", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other-shapes table (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -305,6 +387,11 @@ def main():
         e2e_total_ms = sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))
         checksum = float(y_pin.double().abs().sum())
 
+    # ---- beside the headline: other shapes (N = 1), single-image strong scaling (N > 1) ----
+    peaks0 = measured_peaks()
+    extra = other_configs(ce, dev, flush, peaks0) if (world == 1 and not args.no_extra) else None
+    strong = strong_scaling(ce, dev, flush, world, rank, params) if world > 1 else None
+
     total_ms = parallel.max_over_ranks(total_ms, dev)
     e2e_total_ms = parallel.max_over_ranks(e2e_total_ms, dev)
     launches_all = int(parallel.sum_over_ranks(launches, dev))
@@ -330,7 +417,7 @@ def main():
             "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 dense burst (MEASURED_PEAKS.json)",
-            "kernel": {"tc": "attend_tc2_kernel", "tc4": "attend_tc4_kernel", "tc1": "attend_tc_kernel", "simt": "attend_simt_kernel"}.get(impl_used, impl_used), "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
+            "kernel": {"tc": "attend_tc2_kernel", "tc4": "attend_tc4_kernel", "simt": "attend_simt_kernel"}.get(impl_used, impl_used), "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
             "flops_per_launch": B_PER_GPU * FLOPS_ALG, "bytes_per_launch": B_PER_GPU * BYTES_ALG,
             "hbm_gbs_algorithmic": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9,
             "hbm_frac_of_measured": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -338,7 +425,10 @@ def main():
         out = {
             "metric": "graph-block query patches/s (64ch 256x256)", "value": value, "unit": "patches/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 io; split-fp16 x3 MMAs (fp32-accurate) for feature maps / embeddings / scores, fp16 P.V, fp32 accumulate"
+                     if impl_used != "simt" else "f32",
+            "data": "synthetic",
             "config": {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} per GPU (one graph block, direct/no-chop), random-init head",
                        "Nq": NQ, "Nk": NK, "impl": impl_used, "l2": "flushed between timed iterations (256 MiB memset)",
                        "timing": "CUDA events per step, summed; max over ranks"},
@@ -351,6 +441,10 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
+        if world == 1 and not args.no_extra:
+            out["configs"] = extra
+        if strong is not None:
+            out["strong"] = strong
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

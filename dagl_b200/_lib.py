@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DAGL_B200_LIB") or os.path.join(_HERE, "libdagl_b200.so")   # env override: A/B builds in development
 
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC1, IMPL_TC4 = 0, 1, 2, 3, 4
-IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC, "tc1": IMPL_TC1, "tc4": IMPL_TC4}
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC4 = 0, 1, 2, 4
+IMPL_BY_NAME = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tc": IMPL_TC, "tc4": IMPL_TC4}
 
 EXPORTS = [
     "dagl_abi_version", "dagl_last_error", "dagl_ce_workspace_bytes", "dagl_ce_forward_f32",
@@ -18,6 +18,7 @@ EXPORTS = [
     "dagl_last_impl", "dagl_last_launch_count", "dagl_profile_enable", "dagl_profile_read",
     "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
     "dagl_ces_heads_forward_f32", "dagl_ce_packed_weights_bytes", "dagl_ce_pack_weights_f32",
+    "dagl_ces_workspace_bytes", "dagl_ce_rows_workspace_bytes",
 ]
 
 
@@ -73,14 +74,18 @@ def lib() -> C.CDLL:
     L.dagl_ce_num_query_tiles.restype = i32
     L.dagl_ce_num_query_tiles.argtypes = [i32, i32]
     L.dagl_ce_forward_rows_f32.restype = i32
-    L.dagl_ce_forward_rows_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.dagl_ce_forward_rows_f32.argtypes = [C.POINTER(DaglCEWeights), vp, vp, i32, i32, i32, i32, i32, vp, sz, i32, vp]
+    L.dagl_ce_rows_workspace_bytes.restype = sz
+    L.dagl_ce_rows_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+    L.dagl_ces_workspace_bytes.restype = sz
+    L.dagl_ces_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.dagl_ce_fold_rows_f32.restype = i32
     L.dagl_ce_fold_rows_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.dagl_profile_enable.restype = i32
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32
     L.dagl_profile_read.argtypes = [C.POINTER(C.c_float), i32]
-    if L.dagl_abi_version() != 2:
+    if L.dagl_abi_version() != 3:
         raise RuntimeError("libdagl_b200.so ABI version mismatch")
     _lib = L
     return L

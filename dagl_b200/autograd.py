@@ -87,10 +87,18 @@ class CEFunction(torch.autograd.Function):
         b, *params = ctx.saved_tensors
         need = ctx.needs_input_grad[1:]
         m = ctx.module
-        with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
-            leaves = [t.detach().requires_grad_(bool(n)) for t, n in zip([b] + params, need)]
-            y = ce_recompute(leaves[0], leaves[1:], ksize=m.ksize, stride_q=m.stride_1, scale=float(m.softmax_scale))
-            wanted = [t for t in leaves if t.requires_grad]
-            grads = list(torch.autograd.grad(y, wanted, dy.contiguous(), allow_unused=True))
+        # The forward's scores are fp32-accurate (3-term split-fp16 MMAs).  The recompute must be too, whatever the training
+        # script set globally: TF32 convolutions OR TF32 matmuls (`allow_tf32` / set_float32_matmul_precision) would flip
+        # neighbours relative to the forward and put ~1e-3 of error into the gradients.
+        prev_mm = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+                leaves = [t.detach().requires_grad_(bool(n)) for t, n in zip([b] + params, need)]
+                y = ce_recompute(leaves[0], leaves[1:], ksize=m.ksize, stride_q=m.stride_1, scale=float(m.softmax_scale))
+                wanted = [t for t in leaves if t.requires_grad]
+                grads = list(torch.autograd.grad(y, wanted, dy.contiguous(), allow_unused=True))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_mm
         out = [grads.pop(0) if t.requires_grad else None for t in leaves]
         return (None, *out)

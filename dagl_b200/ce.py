@@ -16,6 +16,7 @@ reference being importable; its convolutions are plain ``torch.nn`` layers.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -24,17 +25,29 @@ import torch.nn as nn
 from . import _lib
 
 _WS_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
+_WS_LOCK = threading.Lock()
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Caller-owned workspace, allocated through torch's caching allocator so the
-    usual stream semantics hold.  One buffer per device, grown on demand."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), 0)
-    buf = _WS_CACHE.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
-        _WS_CACHE[key] = buf
-    return buf
+    """Caller-owned workspace, allocated through torch's caching allocator.  One buffer per (device, CUDA stream), grown
+    on demand: the kernels of a forward are ordered on the caller's current stream, so two forwards may share scratch
+    memory only if they are on the same stream.  Different streams (and the per-device threads of ``nn.DataParallel``, which
+    run on different devices) get different buffers; a buffer that is replaced by a larger one is only ever freed to
+    torch's allocator on the stream that used it, so the usual stream-ordered reuse rules hold."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, torch.cuda.current_stream(device).cuda_stream)
+    with _WS_LOCK:
+        buf = _WS_CACHE.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
+            _WS_CACHE[key] = buf
+        return buf
+
+
+def release_workspaces() -> None:
+    """Drop every cached workspace (they are plain torch tensors; memory returns to the caching allocator)."""
+    with _WS_LOCK:
+        _WS_CACHE.clear()
 
 
 class CE(nn.Module):
@@ -214,40 +227,60 @@ class CE(nn.Module):
         prologue redundantly and the fused graph stage for its share of the 128-query tiles only; the merged
         aggregation rows are exchanged with ONE all-gather and every rank folds the full result
         (SURVEY §8e scheme 3: rows of the score matrix are independent given all keys).  Without an
-        initialised process group this is ``forward``."""
+        initialised process group this is ``forward``.  Inference only (no autograd graph is recorded)."""
         import torch.distributed as dist
-        from . import parallel
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return self.forward(b)
         self._check_input(b)
         if not b.is_cuda:
             raise RuntimeError("dagl_b200.CE has no CPU path")
+        if self._needs_grad(b):
+            raise RuntimeError("forward_query_sharded is an inference path: call it under torch.no_grad() "
+                               "(training uses forward(), which records the backward)")
+        if self.impl == "simt":
+            raise RuntimeError("forward_query_sharded needs a tensor-core impl (auto, tc, tc4)")
         L = _lib.lib()
         b = b.contiguous()
         B, Cc, H, W = b.shape
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         nqt = L.dagl_ce_num_query_tiles(H, W)
-        nq = ((H + 3) // 4) * ((W + 3) // 4)
         tpr = (nqt + world - 1) // world                      # tiles per rank (last ranks may own fewer / none)
         t0, t1 = min(nqt, rank * tpr), min(nqt, (rank + 1) * tpr)
+        rpr = tpr * 128                                       # rows per rank in the exchange buffer
         with torch.cuda.device(b.device):
-            rows = torch.zeros(B, nqt * 128, 784, dtype=torch.float32, device=b.device)
+            # exchange buffer [world][B][rpr][784]: this rank's kernel writes straight into its slot through a row-offset
+            # view (the library indexes rows by global query id), so there is no staging copy on either side
+            full = torch.empty(world, B, rpr, 784, dtype=torch.float32, device=b.device)
             stream = torch.cuda.current_stream(b.device).cuda_stream
             if t1 > t0:
-                ws = _workspace(b.device, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+                if B != 1:
+                    mine = torch.empty(B, nqt * 128, 784, dtype=torch.float32, device=b.device)
+                    rows_ptr = mine.data_ptr()
+                else:
+                    mine = None
+                    rows_ptr = full[rank].data_ptr() - t0 * 128 * 784 * 4      # row q of the image lives at slot row q - t0*128
+                ws = _workspace(b.device, L.dagl_ce_rows_workspace_bytes(B, Cc, H, W, t0, t1))
                 w, keep = self._weights(b.device)
-                # the library writes rows [B][Nq][784]; use a view with the true row count, then pad to tiles
-                rows_nq = torch.empty(B, nq, 784, dtype=torch.float32, device=b.device)
-                rc = L.dagl_ce_forward_rows_f32(C.byref(w), b.data_ptr(), rows_nq.data_ptr(), B, H, W, t0, t1,
-                                                ws.data_ptr(), ws.numel(), stream)
+                rc = L.dagl_ce_forward_rows_f32(C.byref(w), b.data_ptr(), rows_ptr, B, H, W, t0, t1,
+                                                ws.data_ptr(), ws.numel(), _lib.IMPL_BY_NAME[self.impl], stream)
                 _lib.check(rc, "dagl_ce_forward_rows_f32")
                 self.last_impl = L.dagl_last_impl().decode()
                 self.last_launches = L.dagl_last_launch_count()
-                q0, q1 = t0 * 128, min(nq, t1 * 128)
-                rows[:, q0:q1] = rows_nq[:, q0:q1]
-            full = parallel.gather_query_rows(rows, tpr * 128, nq, group=group)     # [B, Nq, 784] on every rank
+                if mine is not None:
+                    nq = ((H + 3) // 4) * ((W + 3) // 4)
+                    q0, q1 = t0 * 128, min(nq, t1 * 128)
+                    full[rank, :, : q1 - q0] = mine[:, q0:q1]
+            # in place: rank r's contribution already sits in slot r of the gathered buffer (NCCL's in-place all-gather layout)
+            dist.all_gather_into_tensor(full.view(world * B, rpr, 784), full[rank], group=group)
+            if B == 1:
+                rows = full.view(1, world * rpr, 784)                                    # already in query order
+            else:
+                rows = full.permute(1, 0, 2, 3).reshape(B, world * rpr, 784)
+            nq = ((H + 3) // 4) * ((W + 3) // 4)
+            if rows.shape[1] != nq or not rows.is_contiguous():
+                rows = rows[:, :nq].contiguous()
             y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
-            rc = L.dagl_ce_fold_rows_f32(full.data_ptr(), y.data_ptr(), B, H, W, stream)
+            rc = L.dagl_ce_fold_rows_f32(rows.data_ptr(), y.data_ptr(), B, H, W, stream)
             _lib.check(rc, "dagl_ce_fold_rows_f32")
         return y
 
@@ -265,6 +298,10 @@ class CE(nn.Module):
         B, Cc, H, W = b_host.shape
         if y_host is None:
             y_host = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32).pin_memory()
+        elif (not isinstance(y_host, torch.Tensor) or y_host.is_cuda or y_host.dtype != torch.float32 or
+              tuple(y_host.shape) != (B, self.inter_channels, H, W) or not y_host.is_contiguous()):
+            raise RuntimeError(f"forward_host: y_host must be a contiguous fp32 host tensor of shape "
+                               f"{(B, self.inter_channels, H, W)}")
         with torch.cuda.device(device):
             nbytes = L.dagl_ce_workspace_bytes(B, Cc, H, W) + L.dagl_ce_host_staging_bytes(B, Cc, H, W)
             ws = _workspace(device, nbytes)
@@ -297,7 +334,7 @@ def stage_heads_forward(heads, x: torch.Tensor) -> torch.Tensor:
     B, Cc, H, W = x.shape
     with torch.cuda.device(x.device):
         ycat = torch.empty(B, h0.inter_channels * len(heads), H, W, dtype=torch.float32, device=x.device)
-        ws = _workspace(x.device, L.dagl_ce_workspace_bytes(B, Cc, H, W))
+        ws = _workspace(x.device, L.dagl_ces_workspace_bytes(len(heads), B, Cc, H, W))
         structs, keep = [], []
         for h in heads:
             w, k = h._weights(x.device)
@@ -352,10 +389,27 @@ class CES(nn.Module):
         return self._stage(3, out)
 
 
-def patch_reference(module: nn.Module, impl: str = "auto") -> int:
+def _ces_stage_forward(self, x):
+    """Body of the reference ``CES.forward`` (dagl.py:112-119) with each ``torch.cat`` of four head calls replaced by one
+    stage call (``dagl_ces_heads_forward_f32``: heads as a grid dimension, results written into the concatenated buffer).
+    Bound onto the reference's own CES instances by ``patch_reference(..., fuse_stages=True)``; same sub-modules, same
+    parameters, bit-identical values."""
+    out = self.c1_c(stage_heads_forward((self.c1_1, self.c1_2, self.c1_3, self.c1_4), x)) + x
+    out = self.RBS1(out)
+    out = self.c2_c(stage_heads_forward((self.c2_1, self.c2_2, self.c2_3, self.c2_4), out)) + out
+    out = self.RBS2(out)
+    out = self.c3_c(stage_heads_forward((self.c3_1, self.c3_2, self.c3_3, self.c3_4), out)) + out
+    return out
+
+
+def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = True) -> int:
     """Replace every reference ``CE`` instance inside ``module`` (e.g. an ``RR``
     or ``CES`` built by the unmodified reference code) with a ``dagl_b200.CE``
-    that *shares* the same Parameters.  Returns the number of heads swapped."""
+    that *shares* the same Parameters.  Returns the number of heads swapped.
+
+    ``fuse_stages``: also rebind ``forward`` of every reference ``CES`` instance whose twelve heads were swapped, so that
+    the four heads of a stage go through ONE stage call instead of four head calls + ``torch.cat`` (same values)."""
+    import types
     n = 0
     for parent in module.modules():
         for name, child in list(parent.named_children()):
@@ -369,6 +423,12 @@ def patch_reference(module: nn.Module, impl: str = "auto") -> int:
                     setattr(new, sub, getattr(child, sub))
                 setattr(parent, name, new)
                 n += 1
+    if fuse_stages:
+        heads = [f"c{s}_{h}" for s in (1, 2, 3) for h in (1, 2, 3, 4)]
+        for m in module.modules():
+            if type(m).__name__ == "CES" and not isinstance(m, CES) and \
+                    all(isinstance(getattr(m, h, None), CE) for h in heads) and hasattr(m, "RBS1") and hasattr(m, "c3_c"):
+                m.forward = types.MethodType(_ces_stage_forward, m)
     return n
 
 

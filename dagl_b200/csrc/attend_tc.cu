@@ -42,14 +42,10 @@ constexpr int TH_STAGE_BYTES = TH_SLOTS * TH_SEG_BYTES;
 constexpr int TC_THREADS = 448;                 // 1 TMA + 1 MMA + 12 softmax warps
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_S_COL0 = 400;                    // S/P buffers at columns 400 and 448
-constexpr float TC_RESCALE_LOG2 = 10.f;           // lazy rescale threshold of the softmax reference
 
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + Q_TILE_BYTES;                 // 2 stages
 constexpr int SM_T = SM_K + 2 * K_TILE_BYTES;             // 2 stages
-constexpr int SM_BAR = SM_T + 2 * TH_STAGE_BYTES;
-constexpr int SM_XCH = SM_BAR + 256;                      // softmax exchange: [2][4][3][32] floats
-constexpr int SM_TOTAL = SM_XCH + 2 * 4 * 3 * 32 * 4;
 static_assert(SM_K % 1024 == 0 && SM_T % 1024 == 0 && K_TILE_BYTES % 1024 == 0, "smem carve-up alignment");
 
 struct TcGeom {
@@ -265,320 +261,108 @@ __constant__ PvGroup c_groups[2][4] = {
     {{0, 0, 112, 0}, {1, 0, 112, 112}, {2, 0, 112, 224}, {3, 0, 64, 336}},
     {{3, 4, 48, 0}, {4, 0, 112, 48}, {5, 0, 112, 160}, {6, 0, 112, 272}}};
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-attend_tc_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
-                 const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
-                 const float* __restrict__ thrA, const float* __restrict__ thrB,
-                 const unsigned* __restrict__ absmax, float sm_scale_log2, int nsplit,
-                 float* __restrict__ Opart, float* __restrict__ mpart, float* __restrict__ lpart,
-                 uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* t_full = bars + 5;    // [2]
-  uint64_t* t_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* pv_done = bars + 13;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+// ---------------------------------------------------------------------------------------------
+// Softmax reference of a query row (shared by the clustered kernels and the refinement pass below).
+//
+// The pre-pass gives smax_hi = max_k Qh.Kh.  With |x - hi(x)| <= 2^-11 |x| for both operands, S <= Qh.Kh * (1 + 2^-10 +
+// 2^-22); RM_INFL = 1 + 1.25 * 2^-10 also covers the fp32 accumulation of the 13 k-steps.  The logit c*s*relu(s - T) is
+// monotone in s >= 0, so ref = logit(RM_INFL * smax_hi) - 12 bounds every term: P <= 2^12, inside fp16.
+// The logit is quadratic in s, so the bound overshoots the true row maximum by up to ~2^-8 of the maximum logit.  That
+// is < 1 log2 unit for the trained heads (logits <= 140), but for logits of several thousand units every fp16 P would
+// drift into the subnormal range and finally flush to zero.  Rows whose possible overshoot exceeds RM_REFINE_LOG2 units
+// are therefore re-done exactly (fp32, 3 terms) by rowmax_refine_kernel, which stores the exact maximum in smax2.
+// ---------------------------------------------------------------------------------------------
+constexpr float RM_INFL = 1.f + 1.25f / 1024.f;
+constexpr float RM_INFL_EXACT = 1.f + 1.f / 262144.f;     // exact maximum: covers the rounding of 208 fp32 FMAs vs the 3-term MMA sum
+constexpr float RM_REFINE_LOG2 = 12.f;
 
-  const int warp = warp_id_uniform();
-  const int tid = threadIdx.x;
-  const int img = blockIdx.z, split = blockIdx.y;
-  const int qt = blockIdx.x >> 1, half = blockIdx.x & 1;
-  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
-  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
-  const int ntiles = t_end - t_begin;
-#ifdef DAGL_TC_TRACE
-  long long tr_a = 0, tr_b = 0, tr_c = 0;
-  const long long tr_start = clock64();
-  const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-#endif
+__device__ __forceinline__ float row_logit_log2(float s, float tA, float tB, float sm_scale_log2) {
+  const float rl = fmaxf((s - tA) + tB, 0.f);
+  return (s * rl) * sm_scale_log2;
+}
+__device__ __forceinline__ bool row_needs_refine(float s_hi /*unscaled Qh.Kh maximum*/, float tA, float tB, float sm_scale_log2) {
+  return row_logit_log2(s_hi * RM_INFL, tA, tB, sm_scale_log2) - row_logit_log2(s_hi * (2.f - RM_INFL), tA, tB, sm_scale_log2) >
+         RM_REFINE_LOG2;
+}
+__device__ __forceinline__ float row_softmax_ref(unsigned smax_bits, unsigned smax2_bits, float inv_s, float tA, float tB,
+                                                 float sm_scale_log2) {
+  const float s_hi = smax2_bits != 0u ? __uint_as_float(smax2_bits) * inv_s * RM_INFL_EXACT
+                                      : __uint_as_float(smax_bits) * inv_s * RM_INFL;
+  return row_logit_log2(s_hi, tA, tB, sm_scale_log2) - 12.f;
+}
 
-  if (tid == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-      mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1);
-      mbar_init(s_full + i, 1); mbar_init(p_full + i, 384);
-      mbar_init(pv_done + i, 1);
-    }
-    mbar_init_fence();
-  }
-  if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tmem_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
-      mbar_arrive_expect_tx(q_full, Q_TILE_BYTES);
-      bulk_g2s(smem + SM_Q, qsrc, Q_HALF_BYTES, q_full);
-      bulk_g2s(smem + SM_Q + Q_HALF_BYTES, qsrc + Q_HALF_BYTES, Q_HALF_BYTES, q_full);
-      const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
-      for (int j = 0; j < ntiles; ++j) {
-        const int t = t_begin + j, s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        { TRACE_T0(); mbar_wait(k_empty + s, ph ^ 1u); TRACE_ADD(tr_a); }
-        mbar_arrive_expect_tx(k_full + s, K_TILE_BYTES);
-        bulk_g2s(smem + SM_K + s * K_TILE_BYTES, Kp + ((size_t)img * tg.NT + t) * K_TILE_BYTES, K_TILE_BYTES, k_full + s);
-        { TRACE_T0(); mbar_wait(t_empty + s, ph ^ 1u); TRACE_ADD(tr_b); }
-        mbar_arrive_expect_tx(t_full + s, TH_STAGE_BYTES);
+// Exact row maxima for the rows flagged by row_needs_refine (huge logits: rgb_range = 255 models, diverging training).
+// Always launched, but a CTA whose 128 rows are all unflagged exits after reading them (the normal case: ~2 us).
+// Flagged tiles: S = (Qh+Ql).(Kh+Kl) in fp32 FMAs from the packed tiles, key range split over blockIdx.y.
+constexpr int RF_THREADS = 256;
+constexpr int RF_QPITCH = TC_EP + 1;
+constexpr int RF_SM_TOTAL = (TC_BM + TC_BN) * RF_QPITCH * 4;
+__global__ void __launch_bounds__(RF_THREADS)
+rowmax_refine_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
+                     const float* __restrict__ thrA, const float* __restrict__ thrB, const unsigned* __restrict__ absmax,
+                     const unsigned* __restrict__ smax, float sm_scale_log2, int qt_base, unsigned* __restrict__ smax2) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float rf_s[];
+  float* Qs = rf_s;                                  // [128][209]
+  float* Ks = rf_s + TC_BM * RF_QPITCH;              // [48][209]
+  const int qt = qt_base + blockIdx.x, img = blockIdx.z, tid = threadIdx.x;
+  const size_t qidx0 = ((size_t)img * tg.nqt + qt) * TC_BM;
+  const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
+  bool flag = false;
+  if (tid < TC_BM)
+    flag = row_needs_refine(__uint_as_float(__ldg(smax + qidx0 + tid)) * inv_s, __ldg(thrA + qidx0 + tid), __ldg(thrB + qidx0 + tid),
+                            sm_scale_log2);
+  if (!__syncthreads_or(flag ? 1 : 0)) return;
+  const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
+  for (int i = tid; i < TC_BM * TC_ECH; i += RF_THREADS) {            // chunk (kc, row) at kc*2048 + row*16
+    const int kc = i / TC_BM, row = i % TC_BM;
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(qsrc + kc * (TC_BM / 8) * 128 + row * 16));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(qsrc + Q_HALF_BYTES + kc * (TC_BM / 8) * 128 + row * 16));
+    const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-        for (int sl = 0; sl < TH_SLOTS; ++sl) {
-          const int dy = c_groups[half][sl].dy;
-          const int first = (t * TC_BN + dy * tg.Wp) & ~7;
-          bulk_g2s(smem + SM_T + s * TH_STAGE_BYTES + sl * TH_SEG_BYTES, thp + (size_t)first * 32, TH_SEG_BYTES, t_full + s);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idS = instr_desc(128, TC_BN, FMT_F16, FMT_F16, 0, 0);
-      const uint32_t q_hi = smem_u32(smem + SM_Q), q_lo = q_hi + Q_HALF_BYTES;
-      const uint64_t dq_hi = smem_desc(q_hi, (TC_BM / 8) * 128, 128);
-      const uint64_t dq_lo = smem_desc(q_lo, (TC_BM / 8) * 128, 128);
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-
-      auto issue_S = [&](int j) {
-        const int s = j & 1;
-        { TRACE_T0(); mbar_wait(k_full + s, (uint32_t)(j >> 1) & 1u); TRACE_ADD(tr_a); }
-        tc_fence_after();
-        const uint32_t k_hi = smem_u32(smem + SM_K + s * K_TILE_BYTES), k_lo = k_hi + K_HALF_BYTES;
-        const uint64_t dk_hi = smem_desc(k_hi, (TC_BN / 8) * 128, 128);
-        const uint64_t dk_lo = smem_desc(k_lo, (TC_BN / 8) * 128, 128);
-        const uint32_t d = tbase + TC_S_COL0 + s * TC_BN;
-        // Tensor-core fp32 accumulation truncates; its error is relative to the running sum.  The two
-        // cross terms are ~2^-11 of the result, so the 13 Ql.Kh steps go first (while the
-        // accumulator is small); Qh.Kl is paired with Qh.Kh to share the A operand through the collector.
-#ifdef DAGL_TC_TRACE
-        if (!(g_tc_dbg_mode & 1))
-#endif
-        {
-#pragma unroll
-          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-            const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);   // advance start address (16-byte units)
-            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-            mma_f16_ss(d, dq_lo + qo, dk_hi + ko, idS, ks > 0);             // Ql.Kh
-          }
-#pragma unroll
-          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-            const uint64_t qo = (uint64_t)(ks * 2 * (TC_BM / 8) * 128 >> 4);
-            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-            mma_f16_ss_a_fill(d, dq_hi + qo, dk_lo + ko, idS, 1);           // Qh.Kl, keep Qh in the A collector
-            mma_f16_ss_a_lastuse(d, dq_hi + qo, dk_hi + ko, idS, 1);        // Qh.Kh, A re-used (no smem read)
-          }
-        }
-        mma_commit(s_full + s);
-        mma_commit(k_empty + s);
-      };
-
-      if (ntiles > 0) issue_S(0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        if (j + 1 < ntiles) issue_S(j + 1);
-        { TRACE_T0(); mbar_wait(p_full + s, ph); TRACE_ADD(tr_b); }
-        { TRACE_T0(); mbar_wait(t_full + s, ph); TRACE_ADD(tr_c); }
-        tc_fence_after();
-        const int t = t_begin + j;
-        const uint32_t tstage = smem_u32(smem + SM_T + s * TH_STAGE_BYTES);
-        const uint32_t p_tmem = tbase + TC_S_COL0 + s * TC_BN;
-#ifdef DAGL_TC_TRACE
-        if (!(g_tc_dbg_mode & 2))
-#endif
-#pragma unroll
-        for (int ks = 0; ks < TC_BN / 16; ++ks) {
-#pragma unroll
-          for (int sl = 0; sl < TH_SLOTS; ++sl) {
-            const PvGroup gp = c_groups[half][sl];
-            const int off = ((t * TC_BN + gp.dy * tg.Wp) & 7) + gp.dx0 + ks * 16;
-            const uint32_t start = tstage + sl * TH_SEG_BYTES + off * 32;
-            // MN-major, SWIZZLE_32B: LBO = 32 B (next 16-channel N group = next pixel), SBO = 256 B (next 8 keys)
-            uint64_t bd = (uint64_t)((start >> 4) & 0x3FFF) | ((uint64_t)(32 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
-                          ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-            const uint32_t idP = instr_desc(128, (uint32_t)gp.n, FMT_F16, FMT_F16, 0, 1);
-            mma_f16_ts(tbase + gp.col0, p_tmem + ks * 8, bd, idP, (j > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        mma_commit(t_empty + s);
-        mma_commit(pv_done + s);
-      }
-    }
-  } else {
-    // ===================== softmax / epilogue warps =====================
-    // 12 warps: TMEM lane quadrant = warp % 4 (hardware rule), `sub` = which 16 of the 48 key columns.
-    // The three warps of a quadrant own the same 32 query rows; they exchange the per-row tile maximum
-    // through smem + a 96-thread named barrier, which also orders "everyone has read S" before anyone
-    // overwrites the S columns with P.
-    const int quad = warp & 3;
-    const int sub = (warp - 2) >> 2;
-    const int lane = tid & 31;
-    const int row = quad * 32 + lane;
-    const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
-    float* xch = reinterpret_cast<float*>(smem + SM_XCH);       // [2 parity][4 quad][3 sub][32]
-    const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
-    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
-    const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
-    const int q = qt * TC_BM + row;
-    const bool qvalid = q < g.Nq;
-    float m_ref = -INFINITY, l_run = 0.f;
-    int cnt = 0;
-    const int nwords = (g.Nk + 31) / 32;
-    const int ncol = half == 0 ? 400 : 384;
-
-    for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      const int t = t_begin + j;
-      const unsigned vbits = (unsigned)(__ldg(tilemask + (size_t)img * tg.NT + t) >> (16 * sub)) & 0xffffu;
-      { TRACE_T0(); mbar_wait(s_full + s, ph); TRACE_ADD(tr_a); }
-      tc_fence_after();
-      float sv[16];
-      {
-        uint32_t r0[16];
-        tmem_ld16(trow + TC_S_COL0 + s * TC_BN + 16 * sub, r0);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sv[i] = __uint_as_float(r0[i]);
-      }
-      // neighbour mask + exponent (dagl.py:256-260), log2 domain
-      float tmax = -INFINITY;
-      unsigned mk = 0u;
-      if (vbits == 0xffffu) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float sc = sv[i] * inv_s;                     // exact: inv_s is a power of two
-          const float rl = fmaxf((sc - tA) + tB, 0.f);
-          if (rl != 0.f) mk |= 1u << i;
-          sv[i] = (sc * rl) * sm_scale_log2;
-          tmax = fmaxf(tmax, sv[i]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const bool valid = (vbits >> i) & 1u;
-          const float sc = sv[i] * inv_s;
-          const float rl = fmaxf((sc - tA) + tB, 0.f);
-          if (valid && rl != 0.f) mk |= 1u << i;
-          sv[i] = valid ? (sc * rl) * sm_scale_log2 : -INFINITY;   // dummy key slots contribute nothing
-          tmax = fmaxf(tmax, sv[i]);
-        }
-      }
-      // row maximum over the three column groups
-      float* xq = xch + ((s * 4 + quad) * 3) * 32;
-      xq[sub * 32 + lane] = tmax;
-      { TRACE_T0(); asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory"); TRACE_ADD(tr_b); }
-      tmax = fmaxf(fmaxf(xq[lane], xq[32 + lane]), xq[64 + lane]);
-      // lazy reference update (identical in the three warps: same inputs)
-      float factor = 1.f;
-      if (tmax > m_ref + TC_RESCALE_LOG2) {
-        factor = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - tmax);
-        m_ref = tmax;
-        l_run *= factor;
-      }
-      const bool need = (j > 0) && (factor != 1.f);
-      if (__any_sync(0xffffffffu, need)) {
-        // the accumulator must be idle: P.V of the previous tile has to be complete
-        mbar_wait(pv_done + ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
-        tc_fence_after();
-        for (int c0 = 16 * sub; c0 < ncol; c0 += 48) {
-          uint32_t v[16];
-          tmem_ld16(trow + c0, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-          tmem_st16(trow + c0, v);
-        }
-        tmem_wait_st();
-      }
-      // probabilities: denominator over every valid key, numerator only neighbours
-      uint32_t pk[8];
-      float psum = 0.f;
-      const float mr = (m_ref == -INFINITY) ? 0.f : m_ref;
-#pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const float p0 = ex2_approx(sv[i] - mr), p1 = ex2_approx(sv[i + 1] - mr);   // ex2(-inf) = 0
-        psum += p0 + p1;
-        pk[i / 2] = pack_half2(((mk >> i) & 1u) ? p0 : 0.f, ((mk >> (i + 1)) & 1u) ? p1 : 0.f);
-      }
-      l_run += psum;
-      cnt += __popc(mk);
-      tmem_st8(trow + TC_S_COL0 + s * TC_BN + 8 * sub, pk);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_full + s);
-
-      if (mask_bits != nullptr && qvalid && mk != 0u) {      // debug path only
-        uint32_t* mrow = mask_bits + ((size_t)img * g.Nq + q) * nwords;
-        unsigned rem = mk;
-        while (rem) {
-          const int i = __ffs((int)rem) - 1;
-          rem &= rem - 1;
-          const int kp = t * TC_BN + 16 * sub + i;
-          const int kk = (kp / tg.Wp) * g.W + (kp % tg.Wp);
-          atomicOr(mrow + (kk >> 5), 1u << (kk & 31));
-        }
-      }
-    }
-
-    // ---- epilogue: partial accumulator -> global ----
-    if (ntiles > 0) {
-      mbar_wait(pv_done + ((ntiles - 1) & 1), (uint32_t)((ntiles - 1) >> 1) & 1u);
-      tc_fence_after();
-    }
-    const float inv_t = 1.f / pow2_scale(absmax[img * AMAX_STRIDE + AMAX_THETA], 12);
-    const size_t prow = ((size_t)img * nsplit + split) * g.Nq;
-    float* orow = Opart + (prow + (qvalid ? q : 0)) * VD;
-    int chunk = 0;
-#pragma unroll 1
-    for (int sl = 0; sl < TH_SLOTS; ++sl) {
-      const PvGroup gp = c_groups[half][sl];
-      for (int gdx = 0; gdx < gp.n / 16; ++gdx, ++chunk) {
-        if (chunk % 3 != sub) continue;                      // warp-uniform: the three warps share the columns
-        uint32_t v[16];
-        tmem_ld16(trow + gp.col0 + gdx * 16, v);
-        tmem_wait_ld();
-        if (qvalid) {
-          float4* dst = reinterpret_cast<float4*>(orow + (gp.dy * KS + gp.dx0 + gdx) * CI);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]) * inv_t, __uint_as_float(v[4 * i + 1]) * inv_t,
-                                 __uint_as_float(v[4 * i + 2]) * inv_t, __uint_as_float(v[4 * i + 3]) * inv_t);
-        }
-      }
-    }
-    // row sums / neighbour counts of the three column groups
-    float* xl = xch + (quad * 3) * 32;                         // parity-0 slots are free again
-    int* xc = reinterpret_cast<int*>(xch + (4 + quad) * 3 * 32);
-    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
-    xl[sub * 32 + lane] = l_run;
-    xc[sub * 32 + lane] = cnt;
-    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
-    if (sub == 0 && qvalid && half == 0) {
-      mpart[prow + q] = m_ref;
-      lpart[prow + q] = (xl[lane] + xl[32 + lane]) + xl[64 + lane];
-      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hv[j]));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lv[j]));
+      Qs[row * RF_QPITCH + kc * 8 + 2 * j] = a.x + b.x;
+      Qs[row * RF_QPITCH + kc * 8 + 2 * j + 1] = a.y + b.y;
     }
   }
-
-#ifdef DAGL_TC_TRACE
-  if (tr_cta < 1024 && (tid & 31) == 0 && warp <= 2) {
-    long long* o = g_tc_trace[tr_cta] + warp * 4;        // warp 0 producer, 1 mma, 2 softmax
-    o[0] = tr_a; o[1] = tr_b; o[2] = tr_c; o[3] = clock64() - tr_start;
-    if (warp == 0) { g_tc_trace[tr_cta][12] = ntiles; unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); g_tc_trace[tr_cta][13] = sm; g_tc_trace[tr_cta][14] = tr_start; }
+  const int t_begin = (int)(((long long)blockIdx.y * tg.NT) / gridDim.y);
+  const int t_end = (int)(((long long)(blockIdx.y + 1) * tg.NT) / gridDim.y);
+  const int r = tid & (TC_BM - 1), kh = tid / TC_BM;                   // row, key half (24 keys)
+  float best = 0.f;
+  for (int t = t_begin; t < t_end; ++t) {
+    __syncthreads();
+    const uint8_t* ksrc = Kp + ((size_t)img * tg.NT + t) * K_TILE_BYTES;
+    for (int i = tid; i < TC_BN * TC_ECH; i += RF_THREADS) {
+      const int kc = i / TC_BN, row = i % TC_BN;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(ksrc + kc * (TC_BN / 8) * 128 + row * 16));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(ksrc + K_HALF_BYTES + kc * (TC_BN / 8) * 128 + row * 16));
+      const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hv[j]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lv[j]));
+        Ks[row * RF_QPITCH + kc * 8 + 2 * j] = a.x + b.x;
+        Ks[row * RF_QPITCH + kc * 8 + 2 * j + 1] = a.y + b.y;
+      }
+    }
+    __syncthreads();
+    float acc[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) acc[k] = 0.f;
+    for (int e = 0; e < TC_EP; ++e) {
+      const float q = Qs[r * RF_QPITCH + e];
+#pragma unroll
+      for (int k = 0; k < 24; ++k) acc[k] = fmaf(q, Ks[(kh * 24 + k) * RF_QPITCH + e], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 24; ++k) best = fmaxf(best, acc[k]);           // dummy key slots are zero rows: S = 0 <= max
   }
-#endif
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
+  // only flagged rows take the exact value (both key halves of a row: two threads -> atomicMax); Q, K >= 0 so best >= 0
+  const bool mine = row_needs_refine(__uint_as_float(__ldg(smax + qidx0 + r)) * inv_s, __ldg(thrA + qidx0 + r), __ldg(thrB + qidx0 + r),
+                                     sm_scale_log2);
+  if (mine) atomicMax(smax2 + qidx0 + r, __float_as_uint(fmaxf(best, 1e-30f)));
 }
 
 // =============================================================================================
@@ -742,7 +526,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ thrA, const float* __restrict__ thrB,
-                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
+                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
+                  float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   pdl_prologue();
@@ -942,15 +727,10 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                                pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
     const bool qvalid = q < g.Nq;
-    // fixed softmax reference: exponent of an upper bound of the row maximum (the pre-pass is Qh.Kh only, 2^-10 rel.)
-    float ref;
-    {
-      const float s_hi = __uint_as_float(__ldg(smax + qidx)) * inv_s * 1.00390625f;
-      const float rl = fmaxf((s_hi - tA) + tB, 0.f);
-      // ... minus 12: P is stored as fp16, so the row maximum is placed near 2^12 (fp16 max is 2^16) to keep the
-      // long tail of small weights (which carries real mass in dense rows) out of the fp16 subnormal range
-      ref = (s_hi * rl) * sm_scale_log2 - 12.f;
-    }
+    // fixed softmax reference: logit of an upper bound of the row maximum, minus 12: P is stored as fp16, so the row
+    // maximum is placed near 2^12 (fp16 max is 2^16) to keep the long tail of small weights (which carries real mass in
+    // dense rows) out of the fp16 subnormal range
+    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2);
     float l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
@@ -1138,7 +918,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(V4_THREADS, 1)
 attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ thrA, const float* __restrict__ thrB,
-                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, float sm_scale_log2,
+                  const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
+                  float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][4][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   pdl_prologue();
@@ -1441,12 +1222,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                                pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
     const bool qvalid = q < g.Nq;
-    float ref;
-    {
-      const float s_hi = __uint_as_float(__ldg(smax + qidx)) * inv_s * 1.00390625f;
-      const float rl = fmaxf((s_hi - tA) + tB, 0.f);
-      ref = (s_hi * rl) * sm_scale_log2 - 12.f;             // see v2
-    }
+    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2);
     float l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
@@ -1616,7 +1392,9 @@ __global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int nparts, i
   float L = 0.f;
   for (int s = 0; s < nsplit; ++s)
     for (int h = 0; h < nparts; ++h) L += lpart[(((size_t)img * nsplit + s) * nparts + h) * Nq + q];
-  const float inv = 1.f / L;
+  // L > 0 whenever the row has a valid key (the row maximum itself contributes ~2^12); guard the degenerate case so that
+  // it can never turn into inf * 0 = NaN in the fold
+  const float inv = L > 0.f ? 1.f / L : 0.f;
   for (int s = 0; s < nsplit; ++s) coef[((size_t)img * nsplit + s) * Nq + q] = inv;
 }
 
@@ -1641,18 +1419,19 @@ static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range, int csize =
 }
 
 struct TcWs {
-  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, Opart, mpart, lpart, coef, Om, smax, colsum, kbar, total;
+  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, smax, colsum, kbar, Opart, lpart, coef, total;
   int nsplit;
 };
 
-static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
+// `nqt_range`: number of 128-query tiles the launch will cover (0: all).  The key-split factor (and with it the size of
+// the partial-result buffers, which come last so that every other offset is independent of it) is the larger of what the
+// 2-CTA and the 4-CTA kernel would choose for that range.
+static TcWs tc_ws(const Geom& g, const TcGeom& tg, int nqt_range = 0) {
   TcWs w;
-  // key-split factor the workspace is sized for: the larger of the full launch and an 8-way query-sharded launch
+  const int range = (nqt_range > 0 && nqt_range < tg.nqt) ? nqt_range : tg.nqt;
   {
-    const int full = tc_splits(g, tg, tg.nqt), shard = tc_splits(g, tg, tg.nqt >= 8 ? tg.nqt / 8 : 1);
-    const int full4 = tc_splits(g, tg, tg.nqt, 4);
-    w.nsplit = full > shard ? full : shard;
-    if (full4 > w.nsplit) w.nsplit = full4;
+    const int s2 = tc_splits(g, tg, range, 2), s4 = tc_splits(g, tg, range, 4);
+    w.nsplit = s2 > s4 ? s2 : s4;
   }
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
@@ -1663,20 +1442,18 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg) {
   w.tilemask = take((size_t)g.B * tg.NT * 8);
   w.thrA = take((size_t)g.B * tg.nqt * TC_BM * 4);
   w.thrB = take((size_t)g.B * tg.nqt * TC_BM * 4);
-  const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
-  w.Opart = take(rows * VD * 4);
-  w.mpart = take(rows * 4);
-  w.lpart = take(4 * rows * 4);                 // v2 / v4 keep one row-sum partial per cluster rank
-  w.coef = take(rows * 4);
-  w.Om = take(merge_fold_scratch_bytes(g));
-  w.smax = take((size_t)g.B * tg.nqt * TC_BM * 4);
+  w.smax = take(2 * (size_t)g.B * tg.nqt * TC_BM * 4);      // pre-pass maxima | exact maxima of refined rows
   w.colsum = take((size_t)g.B * tg.NT * ED * 4);
   w.kbar = take((size_t)g.B * ED * 4);
+  const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
+  w.Opart = take(rows * VD * 4);
+  w.lpart = take(4 * rows * 4);                 // one row-sum partial per cluster rank
+  w.coef = take(rows * 4);
   w.total = off;
   return w;
 }
 
-size_t attend_tc_workspace_bytes(const Geom& g) { return tc_ws(g, tc_geom(g)).total; }
+size_t attend_tc_workspace_bytes(const Geom& g, int nqt_range) { return tc_ws(g, tc_geom(g), nqt_range).total; }
 
 void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, float** colsum) {
   const TcWs w = tc_ws(g, tc_geom(g));
@@ -1688,17 +1465,18 @@ void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, flo
 
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_in, int variant, cudaStream_t st) {
   const TcGeom tg = tc_geom(g);
-  TcWs w = tc_ws(g, tg);
   const int qt_begin = a.qt_begin > 0 ? a.qt_begin : 0;
   const int qt_end = (a.qt_end > 0 && a.qt_end < tg.nqt) ? a.qt_end : tg.nqt;
   if (qt_begin >= qt_end) {
     call_state().err = "empty query-tile range";
     return -1;
   }
-  if ((qt_begin != 0 || qt_end != tg.nqt || a.rows_out != nullptr) && variant != 2 && variant != 4) {
-    call_state().err = "query-tile ranges / row output need the clustered tensor-core kernel (impl tc)";
-    return -2;
+  if (variant != 2 && variant != 4) {
+    call_state().err = "unknown tensor-core variant";
+    return -1;
   }
+  const bool ranged = (qt_begin != 0 || qt_end != tg.nqt);
+  TcWs w = tc_ws(g, tg, ranged ? qt_end - qt_begin : 0);
   {
     const int want = tc_splits(g, tg, qt_end - qt_begin, variant == 4 ? 4 : 2);
     if (want < w.nsplit) w.nsplit = want;           // never more splits than the workspace was sized for
@@ -1716,10 +1494,8 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   float* thrA = reinterpret_cast<float*>(base + w.thrA);
   float* thrB = reinterpret_cast<float*>(base + w.thrB);
   float* Opart = reinterpret_cast<float*>(base + w.Opart);
-  float* mpart = reinterpret_cast<float*>(base + w.mpart);
   float* lpart = reinterpret_cast<float*>(base + w.lpart);
   float* coef = reinterpret_cast<float*>(base + w.coef);
-  float* Om = reinterpret_cast<float*>(base + w.Om);
 
   if (absmax_in != nullptr) {
     absmax = const_cast<unsigned*>(absmax_in);      // filled by the prologue kernels of the same forward
@@ -1735,6 +1511,9 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   const int nwords = (g.Nk + 31) / 32;
   if (a.mask_bits) DAGL_CUDA_OK(cudaMemsetAsync(a.mask_bits, 0, (size_t)g.B * g.Nq * nwords * sizeof(uint32_t), st));
   if (a.nnz) DAGL_CUDA_OK(cudaMemsetAsync(a.nnz, 0, (size_t)g.B * g.Nq * sizeof(int32_t), st));
+  unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
+  unsigned* smax2 = smax + (size_t)g.B * tg.nqt * TC_BM;
+  DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, 2 * (size_t)g.B * tg.nqt * TC_BM * 4, st));
 
   {
     // keys first: the pack kernel also produces the per-tile column sums from which Kbar is formed when the
@@ -1766,47 +1545,42 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
 
   const float sm_scale_log2 = a.scale * 1.4426950408889634f;
   dim3 grid((qt_end - qt_begin) * (variant == 4 ? 4 : 2), w.nsplit, g.B);
-  if (variant == 2 || variant == 4) {
-    unsigned* smax = reinterpret_cast<unsigned*>(base + w.smax);
-    DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, (size_t)g.B * tg.nqt * TC_BM * 4, st));
-    // pre-pass: row maxima of the scores (Qh.Kh only)
-    const int nqg = (qt_end - qt_begin + RM_QT - 1) / RM_QT;
-    int pre_split = 148 / (nqg * g.B);
-    if (pre_split < 1) pre_split = 1;
-    const int max_split = tg.NT;
-    if (pre_split > max_split) pre_split = max_split;
-    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin, qt_end, smax));
+  // pre-pass: row maxima of the scores (Qh.Kh only) ...
+  const int nqg = (qt_end - qt_begin + RM_QT - 1) / RM_QT;
+  int pre_split = 148 / (nqg * g.B);
+  if (pre_split < 1) pre_split = 1;
+  const int max_split = tg.NT;
+  if (pre_split > max_split) pre_split = max_split;
+  DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
+  DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin, qt_end, smax));
+  DAGL_LAUNCH_CHECK();
+  // ... made exact for rows with huge logits (normally every CTA exits at once)
+  {
+    int rsplit = tg.NT < 8 ? tg.NT : 8;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(rowmax_refine_kernel, dim3(qt_end - qt_begin, rsplit, g.B), RF_THREADS, RF_SM_TOTAL, st, tg, Qp, Kp, thrA, thrB,
+                            absmax, smax, sm_scale_log2, qt_begin, smax2));
     DAGL_LAUNCH_CHECK();
-    if (int rc = prof_begin(st)) return rc;
-    if (variant == 4) {
-      DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
-      DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
-                                                           sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
-                                                           a.nnz));
-    } else {
-      DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
-      DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax,
-                                                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits,
-                                                            a.nnz));
-    }
-    DAGL_LAUNCH_CHECK();
-    if (int rc = prof_end(st)) return rc;
-    const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
-    const int nq_total = g.B * g.Nq;
-    DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef));
-    DAGL_LAUNCH_CHECK();
-    if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
-      return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
-    return launch_fold_partials(g, w.nsplit, Opart, coef, a.y, st);
   }
-  DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
   if (int rc = prof_begin(st)) return rc;
-  attend_tc_kernel<<<grid, TC_THREADS, SM_TOTAL, st>>>(g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, sm_scale_log2,
-                                                       w.nsplit, Opart, mpart, lpart, a.mask_bits, a.nnz);
+  if (variant == 4) {
+    DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax, smax2,
+                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+  } else {
+    DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax, smax2,
+                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+  }
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
-  return launch_merge_fold(g, w.nsplit, Opart, mpart, lpart, coef, Om, a.y, /*log2_units=*/1, /*shift_major=*/1, 1.f, st);
+  const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
+  const int nq_total = g.B * g.Nq;
+  DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef));
+  DAGL_LAUNCH_CHECK();
+  if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
+    return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
+  return launch_fold_partials(g, w.nsplit, Opart, coef, a.y, st);
 }
 
 }  // namespace dagl

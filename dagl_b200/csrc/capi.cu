@@ -39,7 +39,7 @@ struct WsLayout {
   int kblocks_simt, kblocks_tc;
 };
 
-static WsLayout ws_layout(const Geom& g) {
+static WsLayout ws_layout(const Geom& g, int nqt_range = 0) {
   WsLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
@@ -59,7 +59,7 @@ static WsLayout ws_layout(const Geom& g) {
   L.feat = take(feature_maps_tc_workspace_bytes(g));
   L.embed = take(embed_tc_workspace_bytes(g));
   L.attend = off;
-  const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g);
+  const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g, nqt_range);
   off += align_up(a_simt > a_tc ? a_simt : a_tc);
   L.total = off;
   return L;
@@ -95,9 +95,9 @@ static int check_shape(int B, int H, int W) {
 }
 
 static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsigned* absmax, cudaStream_t st) {
-  // measured (tools/big_shapes.py, round 1): the 4-CTA-cluster kernel is 10-18 % ahead of the 2-CTA one at every size tried,
-  // 64^2 .. 512^2 keys; larger inputs are unmeasured and stay on the 2-CTA kernel
-  if (impl == DAGL_IMPL_AUTO) impl = ((long long)g.Nk <= 300000) ? DAGL_IMPL_TC4 : DAGL_IMPL_TC;
+  // measured (tools/big_shapes.py, round 1): the 4-CTA-cluster kernel is 10-18 % ahead of the 2-CTA one at every size tried
+  // (64^2 .. 512^2 keys), so it is the default at every size; the 2-CTA kernel stays selectable for A/B checks
+  if (impl == DAGL_IMPL_AUTO) impl = DAGL_IMPL_TC4;
   if (impl == DAGL_IMPL_TC) {
     call_state().impl = "tc";
     return launch_attend_tc(g, a, absmax, 2, st);
@@ -105,10 +105,6 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
   if (impl == DAGL_IMPL_TC4) {
     call_state().impl = "tc4";
     return launch_attend_tc(g, a, absmax, 4, st);
-  }
-  if (impl == DAGL_IMPL_TC1) {
-    call_state().impl = "tc1";
-    return launch_attend_tc(g, a, absmax, 1, st);
   }
   if (impl != DAGL_IMPL_SIMT) {
     call_state().err = "unknown impl";
@@ -118,29 +114,47 @@ static int run_attend(const Geom& g, const AttendArgs& a, int impl, const unsign
   return launch_attend_simt(g, a, st);
 }
 
-static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B, int H, int W, void* ws,
+// One forward of `nh` heads (1 <= nh <= MAX_HEADS) that share the input b.  nh == 1 is CE.forward; nh > 1 is the head
+// batch of a CES stage (heads as a grid dimension; tensor-core path only): every kernel runs once over B x nh virtual
+// images and head h's result lands at channel offset 16 h of y (y_img_stride between real images).
+static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* b, float* y, int B, int H, int W, void* ws,
                         size_t ws_bytes, int impl, cudaStream_t st, uint32_t* mask_bits, int32_t* nnz,
                         float* rows_out = nullptr, int qt_begin = 0, int qt_end = 0, long long y_img_stride = 0,
                         bool reuse_b = false) {
   call_state().launches = 0;
   call_state().impl = "none";
-  int rc = check_weights(w);
-  if (rc) return rc;
-  rc = check_shape(B, H, W);
+  if (!heads || nh < 1 || nh > MAX_HEADS) {
+    call_state().err = "bad head list";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  int rc;
+  for (int h = 0; h < nh; ++h) {
+    if ((rc = check_weights(heads[h]))) return rc;
+    if (heads[h]->in_channels != heads[0]->in_channels || heads[h]->softmax_scale != heads[0]->softmax_scale) {
+      call_state().err = "heads of one batched stage call must share in_channels and softmax_scale";
+      return DAGL_ERR_INVALID_ARG;
+    }
+  }
+  const DaglCEWeights* w = heads[0];
+  rc = check_shape(B * nh, H, W);
   if (rc) return rc;
   if (!b || (!y && !rows_out) || !ws) {
     call_state().err = "null buffer";
     return DAGL_ERR_INVALID_ARG;
   }
-  Geom g = make_geom(B, w->in_channels, H, W);
+  Geom g = make_geom(B, w->in_channels, H, W, nh);
+  if (nh > 1 && (impl == DAGL_IMPL_SIMT || !feature_maps_tc_supported(g) || rows_out || mask_bits || nnz)) {
+    call_state().err = "batched heads need the tensor-core path (in_channels 64), without debug / row outputs";
+    return DAGL_ERR_UNSUPPORTED;
+  }
   if (y_img_stride != 0) {
     if (y_img_stride < g.y_img_stride) {
-      call_state().err = "output image stride smaller than one [16,H,W] result";
+      call_state().err = "output image stride smaller than one [16*heads,H,W] result";
       return DAGL_ERR_INVALID_ARG;
     }
     g.y_img_stride = y_img_stride;
   }
-  const WsLayout L = ws_layout(g);
+  const WsLayout L = ws_layout(g, rows_out ? qt_end - qt_begin : 0);
   if (ws_bytes < L.total) {
     call_state().err = "workspace too small";
     return DAGL_ERR_WORKSPACE;
@@ -156,14 +170,20 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
   float* Kbar = reinterpret_cast<float*>(base + L.Kbar);
   unsigned* absmax = reinterpret_cast<unsigned*>(base + L.absmax);
 
+  HeadWeights hw{};
+  for (int h = 0; h < nh; ++h) {
+    const DaglCEWeights* x = heads[h];
+    hw.g_w[h] = x->g_w; hw.g_b[h] = x->g_b; hw.th_w[h] = x->theta_w; hw.th_b[h] = x->theta_b;
+    hw.fc1_w[h] = x->fc1_w; hw.fc1_b[h] = x->fc1_b; hw.fc2_w[h] = x->fc2_w; hw.fc2_b[h] = x->fc2_b;
+    hw.thr_w[h] = x->thr_w; hw.thr_b[h] = x->thr_b; hw.bias_w[h] = x->bias_w; hw.bias_b[h] = x->bias_b;
+    hw.packed[h] = x->packed_fc;
+  }
+
   bool k_packed = false;
+  const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
   if (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g)) {
-    const GammaBetaArgs gb{w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta};       // computed inside the b-repack launch
-    if ((rc = launch_feature_maps_tc(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, base + L.feat,
-                                     L.embed - L.feat,
-                                     w->packed_fc ? static_cast<const char*>(w->packed_fc) + embed_tc_packed_weights_bytes() : nullptr,
-                                     &gb, reuse_b, st))) return rc;
+    if ((rc = launch_feature_maps_tc(g, b, hw, G, Th, gamma, beta, absmax, base + L.feat, L.embed - L.feat, reuse_b, st))) return rc;
   } else {
     if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
     if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
@@ -177,9 +197,7 @@ static int forward_impl(const DaglCEWeights* w, const float* b, float* y, int B,
     // only materialised for the debug entry (parity tests read it through dagl_ce_workspace_view)
     uint8_t* ktiles; float* colsum;
     attend_tc_key_buffers(g, base + L.attend, &ktiles, &colsum);
-    const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
-    if ((rc = launch_embed_tc(g, G, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, Q, debug ? K : nullptr, absmax, base + L.embed,
-                              L.attend - L.embed, w->packed_fc, ktiles, colsum, st))) return rc;
+    if ((rc = launch_embed_tc(g, G, hw, Q, debug ? K : nullptr, absmax, base + L.embed, L.attend - L.embed, ktiles, colsum, st))) return rc;
     Kbar = nullptr;      // formed inside the tensor-core launcher from the key column sums
     k_packed = true;
   }
@@ -210,15 +228,27 @@ size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
   return ws_layout(make_geom(B, C, H, W)).total;
 }
 
+size_t dagl_ce_rows_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t q_tile_begin, int32_t q_tile_end) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || q_tile_end <= q_tile_begin) return 0;
+  return ws_layout(make_geom(B, C, H, W), q_tile_end - q_tile_begin).total;
+}
+
+size_t dagl_ces_workspace_bytes(int32_t n_heads, int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (n_heads <= 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  const int nh = n_heads < MAX_HEADS ? n_heads : MAX_HEADS;
+  const size_t batched = ws_layout(make_geom(B, C, H, W, nh)).total, single = ws_layout(make_geom(B, C, H, W)).total;
+  return batched > single ? batched : single;
+}
+
 int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y, int32_t B, int32_t H, int32_t W,
                             void* workspace, size_t workspace_bytes, int32_t impl, void* stream) {
-  return forward_impl(w, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+  return forward_impl(&w, 1, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), nullptr, nullptr);
 }
 
 int32_t dagl_ce_forward_debug_f32(const DaglCEWeights* w, const float* b, float* y, int32_t B, int32_t H, int32_t W,
                                   void* workspace, size_t workspace_bytes, int32_t impl, void* stream,
                                   uint32_t* mask_bits, int32_t* nnz) {
-  return forward_impl(w, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), mask_bits, nnz);
+  return forward_impl(&w, 1, b, y, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream), mask_bits, nnz);
 }
 
 int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_heads, const float* b, float* ycat,
@@ -228,14 +258,35 @@ int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_
     call_state().err = "bad head list";
     return DAGL_ERR_INVALID_ARG;
   }
-  int total_launches = 0;
+  for (int h = 0; h < n_heads; ++h)
+    if (!heads[h]) { call_state().err = "null head"; return DAGL_ERR_INVALID_ARG; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long stride = (long long)n_heads * CI * H * W;
+  int total_launches = 0;
+  // Heads as a grid dimension: groups of up to MAX_HEADS heads run as ONE set of launches over B x heads virtual images
+  // (tensor-core path, 64 input channels, equal softmax scale).  Anything else takes the serial per-head route.
+  bool batch_ok = impl != DAGL_IMPL_SIMT && n_heads > 1 && heads[0]->in_channels == 64 &&
+                  workspace_bytes >= dagl_ces_workspace_bytes(n_heads, B, heads[0]->in_channels, H, W);
+  for (int h = 1; h < n_heads && batch_ok; ++h)
+    batch_ok = heads[h]->in_channels == heads[0]->in_channels && heads[h]->softmax_scale == heads[0]->softmax_scale;
+  if (batch_ok) {
+    for (int h0 = 0; h0 < n_heads; h0 += MAX_HEADS) {
+      const int nh = n_heads - h0 < MAX_HEADS ? n_heads - h0 : MAX_HEADS;
+      float* yh = ycat ? ycat + (size_t)h0 * CI * H * W : nullptr;
+      const int rc = forward_impl(heads + h0, nh, b, yh, B, H, W, workspace, workspace_bytes, impl, st, nullptr, nullptr, nullptr,
+                                  0, 0, stride, /*reuse_b=*/h0 > 0 && nh == MAX_HEADS);   // same workspace layout as the first group
+      if (rc) return rc;
+      total_launches += call_state().launches;
+    }
+    call_state().launches = total_launches;
+    return 0;
+  }
   for (int h = 0; h < n_heads; ++h) {
     float* yh = ycat ? ycat + (size_t)h * CI * H * W : nullptr;
     // the heads share the input: its fp16 repack (and maximum) from head 0 stays valid in the workspace for the others
     const bool reuse_b = h > 0 && heads[h]->in_channels == heads[0]->in_channels;
-    const int rc = forward_impl(heads[h], b, yh, B, H, W, workspace, workspace_bytes, impl,
-                                static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, 0, 0, stride, reuse_b);
+    const int rc = forward_impl(heads + h, 1, b, yh, B, H, W, workspace, workspace_bytes, impl, st, nullptr, nullptr, nullptr, 0, 0,
+                                stride, reuse_b);
     if (rc) return rc;
     total_launches += call_state().launches;
   }
@@ -296,7 +347,7 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
   const size_t y_bytes = (size_t)B * CI * H * W * sizeof(float);
   float* y_dev = reinterpret_cast<float*>(base + need + align_up(b_bytes));
   DAGL_CUDA_OK(cudaMemcpyAsync(b_dev, b_host, b_bytes, cudaMemcpyHostToDevice, st));
-  rc = forward_impl(w, b_dev, y_dev, B, H, W, workspace, need, impl, st, nullptr, nullptr);
+  rc = forward_impl(&w, 1, b_dev, y_dev, B, H, W, workspace, need, impl, st, nullptr, nullptr);
   if (rc) return rc;
   DAGL_CUDA_OK(cudaMemcpyAsync(y_host, y_dev, y_bytes, cudaMemcpyDeviceToHost, st));
   return 0;
@@ -310,12 +361,16 @@ int32_t dagl_ce_num_query_tiles(int32_t H, int32_t W) {
 
 int32_t dagl_ce_forward_rows_f32(const DaglCEWeights* w, const float* b, float* rows, int32_t B, int32_t H, int32_t W,
                                  int32_t q_tile_begin, int32_t q_tile_end, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+                                 int32_t impl, void* stream) {
   if (q_tile_begin < 0 || q_tile_end <= q_tile_begin || q_tile_end > dagl_ce_num_query_tiles(H, W)) {
     call_state().err = "bad query-tile range";
     return DAGL_ERR_INVALID_ARG;
   }
-  return forward_impl(w, b, nullptr, B, H, W, workspace, workspace_bytes, DAGL_IMPL_AUTO, static_cast<cudaStream_t>(stream),
+  if (impl == DAGL_IMPL_SIMT) {
+    call_state().err = "query-tile ranges / row output need a tensor-core impl (auto, tc, tc4)";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  return forward_impl(&w, 1, b, nullptr, B, H, W, workspace, workspace_bytes, impl, static_cast<cudaStream_t>(stream),
                       nullptr, nullptr, rows, q_tile_begin, q_tile_end);
 }
 

@@ -18,11 +18,23 @@ constexpr int PADK = 3;          // SAME pad of the stride-1 unfold, also the fo
 constexpr int AMAX_STRIDE = 4;
 enum { AMAX_Q = 0, AMAX_K = 1, AMAX_THETA = 2, AMAX_G = 3 };
 
+// Heads of one CES stage as a grid dimension (dagl.py:114-118: four CE heads run on the SAME input): the kernels see
+// B = (real images) x NH "virtual images", virtual image v = img * NH + head.  Only three things know about heads: the
+// kernels that read the shared input b (real image v / NH), the kernels that read weights (head v % NH, through HeadPtrs)
+// and the fold, which writes head h's 16 channels at channel offset 16 h of the concatenated output.
+constexpr int MAX_HEADS = 4;
+struct HeadPtrs { const void* p[MAX_HEADS]; };
+
 struct Geom {
-  int B, C, H, W;
+  int B, C, H, W;                // B counts virtual images (real images x NH)
   int nqy, nqx, Nq, Nk;
   int qpad_top, qpad_left;       // SAME pad of the stride-4 unfold (dagl.py:126-136)
-  long long y_img_stride;        // elements between consecutive images of the OUTPUT (CI*Nk, or the channel-concatenated stage buffer)
+  long long y_img_stride;        // elements between consecutive REAL images of the OUTPUT (NH*CI*Nk, or the caller's stage buffer)
+  int NH;                        // heads per real image (1: plain CE.forward)
+  __host__ __device__ int real_img(int v) const { return NH == 1 ? v : v / NH; }
+  __host__ __device__ int head(int v) const { return NH == 1 ? 0 : v % NH; }
+  // start of the [16][H][W] result of virtual image v inside the output buffer
+  __host__ __device__ size_t y_offset(int v) const { return (size_t)real_img(v) * y_img_stride + (size_t)head(v) * CI * Nk; }
 };
 
 __host__ __device__ inline int same_pad_before(int n, int k, int s) {
@@ -32,14 +44,15 @@ __host__ __device__ inline int same_pad_before(int n, int k, int s) {
   return total / 2;
 }
 
-inline Geom make_geom(int B, int C, int H, int W) {
+inline Geom make_geom(int B, int C, int H, int W, int NH = 1) {
   Geom g;
-  g.B = B; g.C = C; g.H = H; g.W = W;
+  g.NH = NH;
+  g.B = B * NH; g.C = C; g.H = H; g.W = W;
   g.nqy = (H + SQ - 1) / SQ; g.nqx = (W + SQ - 1) / SQ;
   g.Nq = g.nqy * g.nqx; g.Nk = H * W;
   g.qpad_top = same_pad_before(H, KS, SQ);
   g.qpad_left = same_pad_before(W, KS, SQ);
-  g.y_img_stride = (long long)CI * H * W;
+  g.y_img_stride = (long long)NH * CI * H * W;
   return g;
 }
 
@@ -125,16 +138,20 @@ bool feature_maps_tc_supported(const Geom& g);
 size_t feature_maps_tc_workspace_bytes(const Geom& g);
 size_t feature_maps_tc_packed_weights_bytes();
 int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* packed, size_t packed_bytes, cudaStream_t st);
-struct GammaBetaArgs { const float* thr_w; const float* thr_b; const float* bias_w; const float* bias_b; float* gamma; float* beta; };
-int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
-                           const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
-                           const void* prepacked, const GammaBetaArgs* gb, bool reuse_b, cudaStream_t st);
+// per-head parameter pointers of the (up to MAX_HEADS) heads that share the input
+struct HeadWeights {
+  const float* g_w[MAX_HEADS]; const float* g_b[MAX_HEADS]; const float* th_w[MAX_HEADS]; const float* th_b[MAX_HEADS];
+  const float* fc1_w[MAX_HEADS]; const float* fc1_b[MAX_HEADS]; const float* fc2_w[MAX_HEADS]; const float* fc2_b[MAX_HEADS];
+  const float* thr_w[MAX_HEADS]; const float* thr_b[MAX_HEADS]; const float* bias_w[MAX_HEADS]; const float* bias_b[MAX_HEADS];
+  const void* packed[MAX_HEADS];       // nullable: dagl_ce_pack_weights_f32 image (fc1 | fc2 | meta, then g/theta)
+};
+int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw, float* G, float* Th, float* gamma,
+                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, cudaStream_t st);
 size_t embed_tc_packed_weights_bytes();
 int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, void* packed,
                            size_t packed_bytes, cudaStream_t st);
-int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    const void* prepacked, uint8_t* ktiles, float* colsum, cudaStream_t st);
+int launch_embed_tc(const Geom& g, const float* G, const HeadWeights& hw, float* Q, float* K, unsigned* absmax, void* ws,
+                    size_t ws_bytes, uint8_t* ktiles, float* colsum, cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
@@ -168,8 +185,8 @@ int launch_attend_simt(const Geom& g, const AttendArgs& a, cudaStream_t st);
 
 // tensor-core path (attend_tc.cu).  `absmax` [B][AMAX_STRIDE] holds max Q, max K, max|theta| as float bits;
 // when null the launcher computes it with a reduction kernel (split entry).
-size_t attend_tc_workspace_bytes(const Geom& g);
-// variant 1: one CTA per value-column half (scores computed twice); variant 2: 2-CTA clusters sharing P (DSMEM)
+size_t attend_tc_workspace_bytes(const Geom& g, int nqt_range = 0);   // nqt_range: query tiles a ranged (sharded) launch covers; 0 = all
+// variant 2: 2-CTA clusters sharing P (DSMEM); variant 4: 4-CTA clusters, query tile resident in TMEM
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, int variant, cudaStream_t st);
 
 }  // namespace dagl

@@ -48,8 +48,8 @@ constexpr int EB_SM_G = 0;                                           // two halo
 constexpr int EB_SM_W = 2 * EB_G_BYTES;                              // 129024 = 126 * 1024
 constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-sum exchange [4][112] floats
 constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
-constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + EB_N * 4;   // mbarriers + TMEM base (384 B), then the bias vector
-constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + EB_N * 4;   // query launch
+constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + MAX_HEADS * EB_N * 4;   // mbarriers + TMEM base (384 B), then the bias vectors [heads][208]
+constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4;   // query launch
 constexpr int EB_THREADS = 384;                    // warps 0, 7 weight taps (even / odd), 1 MMA issuer, 2-5 + 8-11 epilogue, 6 G halos
 constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
 constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
@@ -122,10 +122,11 @@ pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, u
 // G [16][H][W] fp32 -> zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
 __global__ void __launch_bounds__(256)
 pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restrict__ absmax,
-              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, const float* __restrict__ kmeta /*nullable*/) {
+              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, HeadPtrs kmeta_h, int fused_keys) {
   pdl_prologue();
   const int img = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
+  const float* kmeta = fused_keys ? static_cast<const float*>(kmeta_h.p[g.head(img)]) : nullptr;
   // fused key pack: absmax slot 1 <- a-priori bound on max K = max|G| * l1(fc2) + max|b2| (float bits; K >= 0), the
   // fp16 scale of the key tiles; written here because this kernel precedes both embedding launches
   if (kmeta != nullptr && pix == 0) absmax[img * 4 + 1] = __float_as_uint(__uint_as_float(absmax[img * 4 + 3]) * kmeta[2] + kmeta[3]);
@@ -176,8 +177,8 @@ __device__ __forceinline__ void embed_item(const Geom& g, const EmbGeom& eg, int
 template <bool QG>
 __global__ void __launch_bounds__(EB_THREADS, 1)
 embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the gathered query-patch image*/,
-                const uint8_t* __restrict__ glo, const uint8_t* __restrict__ wp, const float* __restrict__ bias,
-                const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, const unsigned* __restrict__ wmax,
+                const uint8_t* __restrict__ glo, HeadPtrs wp_h /*packed fc weights per head*/, HeadPtrs bias_h,
+                const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, HeadPtrs wmax_h,
                 float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
                 uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
                 float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
@@ -214,8 +215,9 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tmem_ptr;
-  float* bias_s = reinterpret_cast<float*>(smem + SM_BAR + 384);       // [208] (behind the mbarriers)
-  for (int e = tid; e < EB_N; e += EB_THREADS) bias_s[e] = e < ED ? __ldg(bias + e) : 0.f;
+  float* bias_all = reinterpret_cast<float*>(smem + SM_BAR + 384);     // [NH][208] (behind the mbarriers)
+  for (int e = tid; e < EB_N * g.NH; e += EB_THREADS)
+    bias_all[e] = (e % EB_N) < ED ? __ldg(static_cast<const float*>(bias_h.p[e / EB_N]) + (e % EB_N)) : 0.f;
   __syncthreads();
 
   if (warp == 0 || warp == 7) {
@@ -228,7 +230,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         int img, tile, eh;
         embed_item<QG>(g, eg, w, img, tile, eh);
         const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
-        const uint8_t* wsrc = wp + (eh ? EB_WHALF1_OFF : 0);
+        const uint8_t* wsrc = static_cast<const uint8_t*>(wp_h.p[g.head(img)]) + (eh ? EB_WHALF1_OFF : 0);
         const uint8_t* asrc = QG ? ghi + ((size_t)img * eg.nqt + tile) * (size_t)(KK * EB_QA_BYTES) : nullptr;
         for (int t = (warp == 0 ? 0 : 1); t < KK; t += 2) {
           const int s = t % EB_WSTAGES;
@@ -326,12 +328,13 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
     const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
     constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
     float* csum_s = reinterpret_cast<float*>(smem + SM_CSUM);             // [4 warps][112]
-    const float winv = 1.f / pow2_scale_e(*wmax, 14);
     int it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       int img, tile, eh;
       embed_item<QG>(g, eg, w, img, tile, eh);
       const int ab = it & 1;
+      const float winv = 1.f / pow2_scale_e(*static_cast<const unsigned*>(wmax_h.p[g.head(img)]), 14);
+      const float* bias_s = bias_all + g.head(img) * EB_N;
       const int e0 = eh ? EB_N0 : 0, ncols = eh ? EB_N1 : EB_N0;
       const int p = tile * EB_M + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
@@ -483,10 +486,11 @@ pack_qpatch_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsign
 // ---- host side -----------------------------------------------------------------------------
 static inline size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static size_t packed_w_bytes();
 size_t embed_tc_workspace_bytes(const Geom& g) {
   const EmbGeom eg = emb_geom(g);
-  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + 2 * align_up_e((size_t)KK * EB_WTAP_BYTES) + align_up_e(64) +   // maps + packed weights
-         align_up_e((size_t)g.B * eg.nqt * KK * EB_QA_BYTES);                                                         // query patch tiles
+  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + (size_t)g.NH * embed_tc_packed_weights_bytes() +   // maps + packed weights
+         align_up_e((size_t)g.B * eg.nqt * KK * EB_QA_BYTES);                                            // query patch tiles
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
@@ -544,13 +548,12 @@ int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* 
 }
 
 // Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
-// absmax slot 3 (max |G|) must already be filled.  `prepacked` (nullable): weights packed by launch_pack_fc_weights.
+// absmax slot 3 (max |G|) must already be filled.  hw.packed[h] (nullable): weights packed by launch_pack_fc_weights.
 // With `ktiles` (and `colsum`) the key launch writes the graph kernel's fp16 hi|lo key tiles and the per-CTA column sums
 // directly (no fp32 K round trip through HBM, no separate pack pass); absmax slot 1 then holds an a-priori bound on K
 // (the fp16 scale) instead of the measured maximum, and K (fp32) is only written when `K` is non-null.
-int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const float* fc1_b, const float* fc2_w,
-                    const float* fc2_b, float* Q, float* K, unsigned* absmax, void* ws, size_t ws_bytes,
-                    const void* prepacked, uint8_t* ktiles, float* colsum, cudaStream_t st) {
+int launch_embed_tc(const Geom& g, const float* G, const HeadWeights& hw, float* Q, float* K, unsigned* absmax, void* ws,
+                    size_t ws_bytes, uint8_t* ktiles, float* colsum, cudaStream_t st) {
   const EmbGeom eg = emb_geom(g);
   if (ws_bytes < embed_tc_workspace_bytes(g)) {
     call_state().err = "embed (tc) workspace too small";
@@ -559,19 +562,23 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   char* p = static_cast<char*>(ws);
   uint8_t* ghi = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
   uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
-  const uint8_t* packed = static_cast<const uint8_t*>(prepacked);
-  if (packed == nullptr) {
-    if (int rc = launch_pack_fc_weights(fc1_w, fc1_b, fc2_w, fc2_b, p, embed_tc_packed_weights_bytes(), st)) return rc;
-    packed = reinterpret_cast<const uint8_t*>(p);
+  HeadPtrs w1{}, w2{}, b1{}, b2{}, wmax1{}, wmax2{}, kmeta{};
+  for (int h = 0; h < g.NH; ++h) {
+    const uint8_t* packed = static_cast<const uint8_t*>(hw.packed[h]);
+    if (packed == nullptr) {
+      char* slot = p + (size_t)h * embed_tc_packed_weights_bytes();
+      if (int rc = launch_pack_fc_weights(hw.fc1_w[h], hw.fc1_b[h], hw.fc2_w[h], hw.fc2_b[h], slot, embed_tc_packed_weights_bytes(), st)) return rc;
+      packed = reinterpret_cast<const uint8_t*>(slot);
+    }
+    const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
+    w1.p[h] = packed; w2.p[h] = packed + packed_w_bytes();
+    wmax1.p[h] = wmax + 0; wmax2.p[h] = wmax + 1; kmeta.p[h] = wmax + 2;
+    b1.p[h] = hw.fc1_b[h]; b2.p[h] = hw.fc2_b[h];
   }
-  const uint8_t* w1 = packed;
-  const uint8_t* w2 = packed + packed_w_bytes();
-  const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
-  DAGL_CUDA_OK(launch_pdl(pack_g_kernel, dim3((eg.NPG + 255) / 256, g.B), 256, 0, st, g, eg, G, absmax, ghi, glo,
-                                                                 ktiles ? reinterpret_cast<const float*>(wmax + 2) : nullptr));
+  DAGL_CUDA_OK(launch_pdl(pack_g_kernel, dim3((eg.NPG + 255) / 256, g.B), 256, 0, st, g, eg, G, absmax, ghi, glo, kmeta, ktiles ? 1 : 0));
   DAGL_LAUNCH_CHECK();
 
-  uint8_t* qimg = reinterpret_cast<uint8_t*>(p) + embed_tc_packed_weights_bytes();       // after the (possibly unused) weight slot
+  uint8_t* qimg = reinterpret_cast<uint8_t*>(p) + (size_t)g.NH * embed_tc_packed_weights_bytes();   // after the (possibly unused) weight slots
   int dev = 0, sms = 148;
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -580,8 +587,8 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   DAGL_LAUNCH_CHECK();
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMQ_TOTAL));
   const int nwork_q = g.B * 2 * eg.nqt;                                                   // persistent: one CTA per SM
-  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, fc1_b, absmax,
-                                                                                        wmax + 0, Q, absmax, nullptr, nullptr));
+  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, b1, absmax,
+                          wmax1, Q, absmax, nullptr, nullptr));
   DAGL_LAUNCH_CHECK();
   // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given
   // (a two-tiles-per-weight-pass variant measured no faster: with one accumulator set per tile its MMA phase and its
@@ -589,7 +596,7 @@ int launch_embed_tc(const Geom& g, const float* G, const float* fc1_w, const flo
   const int nwork_k = g.B * 2 * eg.ntile;
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<false>, nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st, g, eg, ghi, glo, w2,
-                          fc2_b, absmax, wmax + 1, K, absmax, ktiles, colsum));
+                          b2, absmax, wmax2, K, absmax, ktiles, colsum));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

@@ -121,14 +121,16 @@ pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ th_w,
 // input, the gamma/beta part is latency-bound (19 us on its own) and hides behind the bandwidth-bound repack.
 __global__ void __launch_bounds__(GB_THREADS)
 pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const unsigned* __restrict__ bmax,
-                         uint8_t* __restrict__ bimg, int n_gb, const float* __restrict__ thr_w, const float* __restrict__ thr_b,
-                         const float* __restrict__ bias_w, const float* __restrict__ bias_b, float* __restrict__ gamma,
-                         float* __restrict__ beta) {
+                         uint8_t* __restrict__ bimg, int n_gb, HeadPtrs thr_w, HeadPtrs thr_b, HeadPtrs bias_w, HeadPtrs bias_b,
+                         float* __restrict__ gamma, float* __restrict__ beta) {
   pdl_prologue();
   extern __shared__ float gb_smem[];
-  if ((int)blockIdx.x < n_gb) {                           // block-uniform branch
+  if ((int)blockIdx.x < n_gb) {                           // block-uniform branch: (query block, virtual image)
     const int qblocks = (g.Nq + 31) / 32;
-    gamma_beta_body(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta, gb_smem, blockIdx.x % qblocks, blockIdx.x / qblocks);
+    const int v = blockIdx.x / qblocks, h = g.head(v);
+    gamma_beta_body(g, b, static_cast<const float*>(thr_w.p[h]), static_cast<const float*>(thr_b.p[h]),
+                    static_cast<const float*>(bias_w.p[h]), static_cast<const float*>(bias_b.p[h]), gamma, beta, gb_smem,
+                    blockIdx.x % qblocks, v);
     return;
   }
   const int pblocks = (eg.NPG + GB_THREADS - 1) / GB_THREADS;
@@ -169,10 +171,12 @@ pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const u
 // single-buffered and the two 64-column accumulator sets alternate so that the epilogue of a tile overlaps the halo load
 // and the MMAs of the next.
 __global__ void __launch_bounds__(FT_THREADS, 1)
-featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uint8_t* __restrict__ wpack,
-                  const float* __restrict__ g_b, const float* __restrict__ th_b, const unsigned* __restrict__ bmax,
-                  const unsigned* __restrict__ wmax, float* __restrict__ G, float* __restrict__ Th,
+featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs wpack, HeadPtrs g_b, HeadPtrs th_b,
+                  const unsigned* __restrict__ bmax, float* __restrict__ G, float* __restrict__ Th,
                   unsigned* __restrict__ absmax /*[B][AMAX_STRIDE]*/) {
+  // Work item w (head-major: a persistent CTA re-loads the 72 KB of packed weights at most NH times):
+  //   head = w / (nreal * ntile), real image = (w / ntile) % nreal, tile = w % ntile; virtual image = real * NH + head.
+  // wpack.p[h] = packed g/theta weights of head h, followed (256-aligned) by wmax (float bits of max |w|).
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_SM_BAR);
@@ -186,6 +190,8 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const int nwork = g.B * eg.ntile;
+  const int per_head = (g.B / g.NH) * eg.ntile;
+  constexpr size_t WMAX_OFF = ((size_t)FT_VTAPS * FT_WTAP_BYTES + 255) & ~(size_t)255;
 
   if (tid == 0) {
     mbar_init(w_full, 1);
@@ -203,18 +209,18 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
   if (warp == 0) {
     // ===================== producer: one bulk copy per lane (24 halo segments; lane 24: the weights, once) ==========
     const int lane = tid & 31;
-    if (lane == FT_GROUPS * 2 * 3) {
-      mbar_arrive_expect_tx(w_full, FT_VTAPS * FT_WTAP_BYTES);
-      bulk_g2s(smem + FT_SM_W, wpack, FT_VTAPS * FT_WTAP_BYTES, w_full);
-    }
-    int it = 0;
+    int it = 0, cur_head = -1;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-      const int img = w / eg.ntile, p0 = (w % eg.ntile) * FT_M;
+      const int head = w / per_head, img = (w / eg.ntile) % (g.B / g.NH), p0 = (w % eg.ntile) * FT_M;   // img: REAL image
       if (lane == 0) {
-        mbar_wait(a_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_wait(a_empty, ((uint32_t)it & 1u) ^ 1u);        // the MMAs of the previous item are complete: halo AND weights are free
+        if (head != cur_head) mbar_arrive_expect_tx(w_full, FT_VTAPS * FT_WTAP_BYTES);
         mbar_arrive_expect_tx(a_full, FT_GROUPS * 2 * 3 * FT_SEG_BYTES);
       }
       __syncwarp();
+      if (head != cur_head && lane == FT_GROUPS * 2 * 3)
+        bulk_g2s(smem + FT_SM_W, static_cast<const uint8_t*>(wpack.p[head]), FT_VTAPS * FT_WTAP_BYTES, w_full);
+      cur_head = head;
       if (lane < FT_GROUPS * 2 * 3) {
         const int gq = lane / 6, part = (lane / 3) & 1, ky = lane % 3;
         const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
@@ -229,11 +235,11 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
       const uint32_t abase = smem_u32(smem + FT_SM_A), wbase = smem_u32(smem + FT_SM_W);
       constexpr uint32_t id32 = instr_desc(FT_M, 32, FMT_F16, FMT_F16, 0, 0);
       constexpr uint32_t id16 = instr_desc(FT_M, 16, FMT_F16, FMT_F16, 0, 0);
-      mbar_wait(w_full, 0);
-      int it = 0;
+      int it = 0, cur_head = -1, nloads = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-        const int p0 = (w % eg.ntile) * FT_M, ab = it & 1;
+        const int p0 = (w % eg.ntile) * FT_M, ab = it & 1, head = w / per_head;
         const uint32_t d_main = tbase + ab * 64, d_cross = d_main + 32;
+        if (head != cur_head) { mbar_wait(w_full, (uint32_t)nloads & 1u); ++nloads; cur_head = head; }
         mbar_wait(a_full, (uint32_t)it & 1u);
         mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -273,14 +279,17 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
     // ===================== epilogue: thread = pixel row =====================
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
-    const float winv = 1.f / pow2_scale_f(*wmax, 14);
     int it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
-      const int img = w / eg.ntile, ab = it & 1;
+      const int head = w / per_head, real = (w / eg.ntile) % (g.B / g.NH), ab = it & 1;
+      const int img = real * g.NH + head;                                   // virtual image: outputs
       const int p = (w % eg.ntile) * FT_M + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
       const bool valid = (p < eg.NkP) && (x < g.W);
-      const float inv = winv / pow2_scale_f(bmax[img], 14);
+      const unsigned wmax = *reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(wpack.p[head]) + WMAX_OFF);
+      const float inv = 1.f / (pow2_scale_f(wmax, 14) * pow2_scale_f(bmax[real], 14));
+      const float* gbias = static_cast<const float*>(g_b.p[head]);
+      const float* tbias = static_cast<const float*>(th_b.p[head]);
       const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16) + ab * 64;
       mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
@@ -298,7 +307,7 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, const uin
       for (int half = 0; half < 2; ++half) {                 // 0: g outputs, 1: theta outputs
         if (valid) {
           float* dst = (half ? Th : G) + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
-          const float* bias = half ? th_b : g_b;
+          const float* bias = half ? tbias : gbias;
 #pragma unroll
           for (int c = 0; c < CI; ++c) {
             const float o = (__uint_as_float(v[half][c]) + __uint_as_float(vc[half][c])) * inv + __ldg(bias + c);
@@ -331,8 +340,9 @@ bool feature_maps_tc_supported(const Geom& g) { return g.C == FT_C; }
 size_t feature_maps_tc_workspace_bytes(const Geom& g) {
   if (!feature_maps_tc_supported(g)) return 0;
   const FtGeom eg = ft_geom(g);
-  return align_up_f((size_t)g.B * FT_GROUPS * 2 * eg.NPG * 32) + align_up_f((size_t)g.B * sizeof(unsigned)) +
-         align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES) + align_up_f(64);
+  const size_t nreal = (size_t)(g.B / g.NH);
+  return align_up_f(nreal * FT_GROUPS * 2 * eg.NPG * 32) + align_up_f(nreal * sizeof(unsigned)) +
+         (size_t)g.NH * feature_maps_tc_packed_weights_bytes();
 }
 
 // packed g/theta weights | wmax (one unsigned)
@@ -351,44 +361,47 @@ int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* p
   return 0;
 }
 
-// `prepacked` (nullable): weights packed by launch_pack_feat_weights.  `gb` (nullable): also compute gamma / beta, inside
-// the launch that repacks b.  `reuse_b`: the repacked input (and its maximum) left in `ws` by the previous call is still
-// valid (same b: the heads of one CES stage), so only the gamma / beta part of that launch runs.
-int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, const float* g_b, const float* th_w,
-                           const float* th_b, float* G, float* Th, unsigned* absmax, void* ws, size_t ws_bytes,
-                           const void* prepacked, const GammaBetaArgs* gb, bool reuse_b, cudaStream_t st) {
+// hw.packed[h] (nullable): weights of head h packed by dagl_ce_pack_weights_f32 (the g/theta image follows the fc image).
+// gamma / beta (dagl.py:213-215) are computed inside the launch that repacks b.  `reuse_b`: the repacked input (and its
+// maximum) left in `ws` by the previous call is still valid (same b), so only the gamma / beta part of that launch runs.
+int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw, float* G, float* Th, float* gamma,
+                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, cudaStream_t st) {
   const FtGeom eg = ft_geom(g);
   if (!feature_maps_tc_supported(g) || ws_bytes < feature_maps_tc_workspace_bytes(g)) {
     call_state().err = "feature maps (tc): unsupported channel count or workspace too small";
     return -3;
   }
+  const int nreal = g.B / g.NH;
   char* p = static_cast<char*>(ws);
-  uint8_t* bimg = reinterpret_cast<uint8_t*>(p); p += align_up_f((size_t)g.B * FT_GROUPS * 2 * eg.NPG * 32);
-  unsigned* bmax = reinterpret_cast<unsigned*>(p); p += align_up_f((size_t)g.B * sizeof(unsigned));
-  const uint8_t* wpack = static_cast<const uint8_t*>(prepacked);
-  if (wpack == nullptr) {
-    if (int rc = launch_pack_feat_weights(g.C, g_w, th_w, p, feature_maps_tc_packed_weights_bytes(), st)) return rc;
-    wpack = reinterpret_cast<const uint8_t*>(p);
+  uint8_t* bimg = reinterpret_cast<uint8_t*>(p); p += align_up_f((size_t)nreal * FT_GROUPS * 2 * eg.NPG * 32);
+  unsigned* bmax = reinterpret_cast<unsigned*>(p); p += align_up_f((size_t)nreal * sizeof(unsigned));
+  HeadPtrs wpack{}, gb{}, tb{}, thr_w{}, thr_b{}, bias_w{}, bias_b{};
+  for (int h = 0; h < g.NH; ++h) {
+    if (hw.packed[h] != nullptr) {
+      wpack.p[h] = static_cast<const char*>(hw.packed[h]) + embed_tc_packed_weights_bytes();
+    } else {
+      char* slot = p + (size_t)h * feature_maps_tc_packed_weights_bytes();
+      if (int rc = launch_pack_feat_weights(g.C, hw.g_w[h], hw.th_w[h], slot, feature_maps_tc_packed_weights_bytes(), st)) return rc;
+      wpack.p[h] = slot;
+    }
+    gb.p[h] = hw.g_b[h]; tb.p[h] = hw.th_b[h];
+    thr_w.p[h] = hw.thr_w[h]; thr_b.p[h] = hw.thr_b[h]; bias_w.p[h] = hw.bias_w[h]; bias_b.p[h] = hw.bias_b[h];
   }
-  const unsigned* wmax = reinterpret_cast<const unsigned*>(wpack + align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES));
 
   if (!reuse_b) {
-    DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)g.B * sizeof(unsigned), st));
+    DAGL_CUDA_OK(cudaMemsetAsync(bmax, 0, (size_t)nreal * sizeof(unsigned), st));
     const size_t n_img = (size_t)g.C * g.Nk;
-    DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, g.B), 256, 0, st, b, n_img, bmax));
+    DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, nreal), 256, 0, st, b, n_img, bmax));
     DAGL_LAUNCH_CHECK();
   }
   {
-    const int n_gb = gb ? ((g.Nq + 31) / 32) * g.B : 0;
-    const int n_pack = reuse_b ? 0 : ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * g.B;
+    const int n_gb = ((g.Nq + 31) / 32) * g.B;                                   // per VIRTUAL image (head-specific filters)
+    const int n_pack = reuse_b ? 0 : ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * nreal;
     const size_t smem = gamma_beta_smem_bytes(g.C);
     if (smem > 48 * 1024)
       DAGL_CUDA_OK(cudaFuncSetAttribute(pack_b_gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (n_gb + n_pack > 0)
-    DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, smem, st, g, eg, b, bmax, bimg, n_gb, gb ? gb->thr_w : nullptr,
-                                                                      gb ? gb->thr_b : nullptr, gb ? gb->bias_w : nullptr,
-                                                                      gb ? gb->bias_b : nullptr, gb ? gb->gamma : nullptr,
-                                                                      gb ? gb->beta : nullptr));
+    DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, smem, st, g, eg, b, bmax, bimg, n_gb, thr_w, thr_b,
+                            bias_w, bias_b, gamma, beta));
     DAGL_LAUNCH_CHECK();
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
@@ -396,7 +409,7 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const float* g_w, cons
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int nwork = g.B * eg.ntile;
-  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(nwork < sms ? nwork : sms), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, g_b, th_b, bmax, wmax, G, Th, absmax));
+  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(nwork < sms ? nwork : sms), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, gb, tb, bmax, G, Th, absmax));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

@@ -70,7 +70,7 @@ __global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ O
       sum += __ldg(Om + ((size_t)img * g.Nq + q) * VD + d);
     }
   const float cntf = (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
-  y[(size_t)img * g.y_img_stride + (size_t)c * g.Nk + (size_t)py * g.W + px] = sum / cntf;
+  y[g.y_offset(img) + (size_t)c * g.Nk + (size_t)py * g.W + px] = sum / cntf;
 }
 
 // Fused merge + fold for the fixed-reference kernels (shift-major partial rows): every output pixel gathers its <= 2x2
@@ -101,7 +101,7 @@ fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const 
       sum.x = fmaf(c, acc.x, sum.x); sum.y = fmaf(c, acc.y, sum.y); sum.z = fmaf(c, acc.z, sum.z); sum.w = fmaf(c, acc.w, sum.w);
     }
   const float inv = 1.f / (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
-  float* yo = y + (size_t)img * g.y_img_stride + (size_t)(4 * c4) * g.Nk + (size_t)py * g.W + px;
+  float* yo = y + g.y_offset(img) + (size_t)(4 * c4) * g.Nk + (size_t)py * g.W + px;
   yo[0] = sum.x * inv; yo[(size_t)g.Nk] = sum.y * inv; yo[2 * (size_t)g.Nk] = sum.z * inv; yo[3 * (size_t)g.Nk] = sum.w * inv;
 }
 

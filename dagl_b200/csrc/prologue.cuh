@@ -16,7 +16,7 @@ inline size_t gamma_beta_smem_bytes(int C) { return (size_t)(C * KK + GB_GROUPS 
 __device__ __forceinline__ void gamma_beta_body(const Geom& g, const float* __restrict__ b, const float* __restrict__ thr_w,
                                                 const float* __restrict__ thr_b, const float* __restrict__ bias_w,
                                                 const float* __restrict__ bias_b, float* __restrict__ gamma,
-                                                float* __restrict__ beta, float* smem, int qblock, int img) {
+                                                float* __restrict__ beta, float* smem, int qblock, int img /*virtual image: outputs*/) {
   float2* w_s = reinterpret_cast<float2*>(smem);                      // [C*49] (thr, bias)
   float2* red = reinterpret_cast<float2*>(smem) + g.C * KK;           // [GB_GROUPS][32]
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -26,7 +26,7 @@ __device__ __forceinline__ void gamma_beta_body(const Geom& g, const float* __re
   const bool live = q < g.Nq;
   const int qy = live ? q / g.nqx : 0, qx = live ? q % g.nqx : 0;
   const int y0 = qy * SQ - g.qpad_top, x0 = qx * SQ - g.qpad_left;
-  const float* bi = b + (size_t)img * g.C * g.Nk;
+  const float* bi = b + (size_t)g.real_img(img) * g.C * g.Nk;
   bool rok[KS], cok[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) { rok[k] = live && (y0 + k >= 0) && (y0 + k < g.H); cok[k] = (x0 + k >= 0) && (x0 + k < g.W); }

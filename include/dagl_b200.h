@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DAGL_ABI_VERSION 2
+#define DAGL_ABI_VERSION 3
 
 enum {
   DAGL_OK = 0,
@@ -34,10 +34,9 @@ enum {
 
 /* Which fused graph kernel to run. */
 enum {
-  DAGL_IMPL_AUTO = 0,   /* best available for the shape */
+  DAGL_IMPL_AUTO = 0,   /* the tensor-core kernel (currently always DAGL_IMPL_TC4) */
   DAGL_IMPL_SIMT = 1,   /* fp32 CUDA-core kernel (bit-faithful neighbour mask) */
-  DAGL_IMPL_TC = 2,     /* tcgen05 tensor-core kernel (split-fp16 scores, fp16 P.V), 2-CTA clusters sharing P */
-  DAGL_IMPL_TC1 = 3,    /* earlier tensor-core variant (no clusters, online softmax); kept for A/B checks */
+  DAGL_IMPL_TC = 2,     /* tcgen05 tensor-core kernel (split-fp16 scores, fp16 P.V), 2-CTA clusters sharing P; A/B aid */
   DAGL_IMPL_TC4 = 4     /* 4-CTA clusters, query tile resident in TMEM (A operand of the score MMAs) */
 };
 
@@ -72,7 +71,8 @@ int32_t dagl_abi_version(void);
 /* Thread-local description of the last error returned on this thread. */
 const char* dagl_last_error(void);
 
-/* Bytes of device workspace dagl_ce_forward_* needs for a [B,C,H,W] input. */
+/* Bytes of device workspace dagl_ce_forward_* needs for a [B,C,H,W] input (sized for the launch of the whole image:
+ * a query-sharded rows call has its own query, dagl_ce_rows_workspace_bytes). */
 size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
 
 /* y[B,16,H,W] = CE.forward(b[B,C,H,W])          — replaces dagl.py:207-275. */
@@ -92,7 +92,12 @@ int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t pa
 /* The heads of one CES stage (reference CES.forward, dagl.py:114-118: `torch.cat([c_1(x), .., c_4(x)], dim=1)`):
  * head h of `heads[0..n_heads)` runs on the shared input b[B,C,H,W] and writes its 16 channels straight into
  * channels [16h, 16h+16) of ycat[B, 16*n_heads, H, W] — the concatenation is never a separate copy.  The 1x1 merge
- * conv and the residual of the stage stay with the caller.  Workspace: dagl_ce_workspace_bytes() (reused per head). */
+ * conv and the residual of the stage stay with the caller.
+ * With dagl_ces_workspace_bytes() of workspace (and a tensor-core impl, 64 input channels, one softmax scale) the heads
+ * are a GRID DIMENSION: every kernel of the forward runs once over B x n_heads "virtual images" (the shared input is
+ * repacked once; ~15 launches per stage instead of ~15 per head).  With only dagl_ce_workspace_bytes() the heads run one
+ * after the other.  The two routes agree up to the fp32 summation order of the key-split partial sums.              */
+size_t dagl_ces_workspace_bytes(int32_t n_heads, int32_t B, int32_t C, int32_t H, int32_t W);
 int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_heads, const float* b, float* ycat,
                                    int32_t B, int32_t H, int32_t W,
                                    void* workspace, size_t workspace_bytes,
@@ -126,10 +131,12 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
  * for its queries (other rows untouched).  After the ranks exchange their rows (one all-gather),
  * dagl_ce_fold_rows_f32 performs the fold + coverage normalisation (dagl.py:265-272).                         */
 int32_t dagl_ce_num_query_tiles(int32_t H, int32_t W);
+/* workspace for a rows call over [q_tile_begin, q_tile_end) (the key-split factor depends on the range) */
+size_t dagl_ce_rows_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t q_tile_begin, int32_t q_tile_end);
 int32_t dagl_ce_forward_rows_f32(const DaglCEWeights* w, const float* b, float* rows,
                                  int32_t B, int32_t H, int32_t W,
                                  int32_t q_tile_begin, int32_t q_tile_end,
-                                 void* workspace, size_t workspace_bytes, void* stream);
+                                 void* workspace, size_t workspace_bytes, int32_t impl /* auto, tc or tc4 */, void* stream);
 int32_t dagl_ce_fold_rows_f32(const float* rows, float* y, int32_t B, int32_t H, int32_t W, void* stream);
 
 /* Split entry for the fused graph stage alone (dagl.py:250-272), taking the
@@ -152,7 +159,7 @@ const float* dagl_ce_workspace_view(void* workspace, int32_t which,
                                     int32_t B, int32_t C, int32_t H, int32_t W);
 
 /* Name of the kernel family actually used by the last forward on this thread
- * ("simt" or "tc"); lets callers assert that no fallback happened.           */
+ * ("simt", "tc" or "tc4"); lets callers assert that no fallback happened.    */
 const char* dagl_last_impl(void);
 
 /* Number of kernel launches issued by the last forward on this thread.      */

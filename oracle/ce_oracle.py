@@ -167,13 +167,20 @@ def ce_forward(p: Params, b: torch.Tensor, return_aux: bool = False):
     return y, out
 
 
-def ce_forward_chunked(p: Params, b: torch.Tensor, chunk: int = 512, return_nnz: bool = False):
+def ce_forward_chunked(p: Params, b: torch.Tensor, chunk: int = 512, return_nnz: bool = False,
+                       other_mask_bits: Optional[torch.Tensor] = None):
     """Same math with query rows processed ``chunk`` at a time (rows of S are
     independent: dagl.py:250-264 are all row-wise).  Memory ~ 6 * chunk * Nk
-    floats instead of ~20 * Nq * Nk."""
+    floats instead of ~20 * Nq * Nk.
+
+    ``other_mask_bits`` ([B, Nq, ceil(Nk/32)] int32, the layout of ``dagl_ce_forward_debug_f32``): compare another
+    implementation's neighbour mask with the oracle's, chunk by chunk, and return as a third result the list of flipped
+    entries ``(image, query, key, margin_in_ulps)`` with margin = |S - mu*gamma + beta| / (eps * (|S| + |mu*gamma| + |beta|))
+    — how far the flipped entry sits from the relu threshold of dagl.py:256 in units of the fp32 rounding of its operands."""
     B, C, H, W = b.shape
     G, Th, gamma, beta, qp, kp, vp, fold_pad = _prologue(p, b)
-    ys, nnzs = [], []
+    ys, nnzs, flips = [], [], []
+    eps = torch.finfo(torch.float32).eps
     for i in range(B):
         Q = F.relu(F.linear(qp[i].t(), p["fc1.0.weight"], p["fc1.0.bias"]))
         K = F.relu(F.linear(kp[i].t(), p["fc2.0.weight"], p["fc2.0.bias"]))
@@ -189,9 +196,19 @@ def ce_forward_chunked(p: Params, b: torch.Tensor, chunk: int = 512, return_nnz:
             P, mask_b = _edge_weights(S, mu, gamma[i, s:e], beta[i, s:e])
             nnz[s:e] = mask_b.sum(dim=1).to(torch.int64)
             O[s:e] = torch.mm(P, V)
+            if other_mask_bits is not None:
+                diff = unpack_mask_bits(other_mask_bits[i, s:e], S.shape[1]) != mask_b.bool()
+                if bool(diff.any()):
+                    t = (mu * gamma[i, s:e]).unsqueeze(1)
+                    bt = beta[i, s:e].unsqueeze(1)
+                    margin = ((S - t) + bt).abs() / (eps * (S.abs() + t.abs() + bt.abs()))
+                    for r, k in diff.nonzero().tolist():
+                        flips.append((i, s + r, k, float(margin[r, k])))
         ys.append(_fold_normalise(O, H, W, fold_pad))
         nnzs.append(nnz)
     y = torch.cat(ys, dim=0)
+    if other_mask_bits is not None:
+        return y, torch.stack(nnzs), flips
     return (y, torch.stack(nnzs)) if return_nnz else y
 
 

@@ -18,11 +18,10 @@ pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-3          # north_star: <= 1e-3 relative fp32
 TIE_ULPS = 16           # a flipped mask entry must sit within this many fp32 ulps of the threshold
-IMPLS = ["simt", "tc", "tc4"]
+IMPLS = ["simt", "tc", "tc4"]          # "auto" == tc4
 # simt: fp32 kernel, bit-faithful mask, fp32 sums.  tc: tensor-core kernel, split-fp16 scores (fp32-accurate),
 # fp16 P and V operands (2^-11 relative each) -> a few 1e-4 relative on the output, inside the 1e-3 bar; 2-CTA
-# clusters + fixed softmax reference.  tc4: 4-CTA clusters with the query tile resident in TMEM.  tc1: the
-# earlier non-cluster tensor-core variant (online softmax).
+# clusters + fixed softmax reference.  tc4: 4-CTA clusters with the query tile resident in TMEM (the default).
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +66,7 @@ def assert_mask_parity(bits_gpu, aux, max_flips_frac=2e-6):
     return nflip
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["tc1"])
+@pytest.mark.parametrize("impl", IMPLS)
 def test_cfg1_golden(dev, rand_weights, impl):
     """BASELINE config 1: 1x64x64x64, reference-made weights/input/output."""
     g = load_npz("ce_cfg1_64x64.npz")
@@ -86,7 +85,7 @@ def test_cfg1_golden(dev, rand_weights, impl):
     assert torch.equal(y2, y)
 
 
-@pytest.mark.parametrize("impl", IMPLS + ["tc1"])
+@pytest.mark.parametrize("impl", IMPLS)
 def test_ragged_golden(dev, rand_weights, impl):
     """H, W not multiples of 4, non-square, batch 2, tiny (7x9), chop-leaf 72x72."""
     g = load_npz("ce_ragged.npz")
@@ -126,12 +125,18 @@ def test_trained_heads(dev, head, impl):
     if head == "c3_3":
         assert int(nnz.sum()) == 0 and float(y.abs().max()) == 0.0
     else:
-        # one flipped neighbour in a sparse row moves it by ~1/nnz; only assert the
-        # tolerance on rows without flips
-        if nflip == 0:
-            assert rel_err(y.cpu(), g["y"]) <= REL_TOL
-        else:
-            assert rel_err(y.cpu(), g["y"]) <= 2e-2
+        # one flipped neighbour in a sparse row moves it by ~1/nnz: only the pixels a flipped query row
+        # folds into are exempt from the bar (at 48^2 no flip has been observed)
+        H, W = g["x"].shape[-2:]
+        exempt = torch.zeros(H, W, dtype=torch.bool)
+        if nflip:
+            m_gpu = O.unpack_mask_bits(bits.cpu(), H * W)
+            nqx = (W + 3) // 4
+            for q in (m_gpu != aux["mask"]).any(dim=-1)[0].nonzero().flatten().tolist():
+                qy, qx = divmod(q, nqx)
+                exempt[max(0, 4 * qy - 3):4 * qy + 4, max(0, 4 * qx - 3):4 * qx + 4] = True
+        err = (y.cpu() - g["y"]).abs()[..., ~exempt].max().item() / g["y"].abs().max().item()
+        assert err <= REL_TOL, (err, nflip)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -287,6 +292,33 @@ def test_ces_caller_row(dev, impl):
     assert rel_err(y.cpu(), yref) <= (REL_TOL if impl == "simt" else 4 * REL_TOL)
 
 
+@pytest.mark.parametrize("impl", ["tc", "tc4"])
+def test_large_logits_stay_finite_and_accurate(dev, rand_weights, impl):
+    """Inputs scaled by 3 and by 30: the logit 10*S*relu(S - T) is quadratic in S ~ |x|^2, so the maximum logit grows by
+    81x (~1e4 log2 units) and 810 000x.  The fixed softmax reference comes from a hi-part-only pre-pass whose 2^-10
+    uncertainty, amplified by the logit, would push every fp16 P into underflow (row sum 0 -> NaN): rows like that get
+    their maximum from the exact refinement pass (rowmax_refine_kernel).  At such magnitudes the softmax is nearly one-hot
+    and the reference's own fp32 rounding of S is amplified the same way, so the bar is taken relative to what the fp32
+    CUDA-core kernel achieves on the same input."""
+    gen = torch.Generator().manual_seed(41)
+    x = torch.randn(1, 64, 40, 44, generator=gen)
+    for scale, check in ((3.0, True), (30.0, False)):
+        xs = x * scale
+        ce = make_ce(rand_weights, dev, impl)
+        with torch.no_grad():
+            y = ce(xs.to(dev)).cpu()
+        assert torch.isfinite(y).all(), scale
+        yref = O.ce_forward(rand_weights, xs)
+        assert torch.isfinite(yref).all()
+        if check:
+            with torch.no_grad():
+                y_simt = make_ce(rand_weights, dev, "simt")(xs.to(dev)).cpu()
+            e_tc, e_simt = rel_err(y, yref), rel_err(y_simt, yref)
+            print(f"   x*{scale}: rel err {impl} {e_tc:.2e}, simt {e_simt:.2e}")
+            assert e_tc <= max(REL_TOL, 4 * e_simt), (e_tc, e_simt)
+            assert float(y.abs().max()) > 0.1 * float(yref.abs().max())          # not the L == 0 guard's zeros
+
+
 def test_unsupported_configuration_raises(dev):
     import dagl_b200
     ce = dagl_b200.CE(ksize=5, in_channels=64).to(dev)
@@ -298,7 +330,7 @@ def test_auto_dispatch_uses_tensor_core_kernel(dev, rand_weights):
     ce = make_ce(rand_weights, dev, "auto")
     with torch.no_grad():
         ce(torch.zeros(1, 64, 32, 32, device=dev))
-    assert ce.last_impl in ("tc", "tc4")
+    assert ce.last_impl == "tc4"
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -363,7 +395,14 @@ def test_stage_entry_equals_cat_of_heads(dev, impl):
         want = torch.cat([h(x) for h in heads], dim=1)
         got = stage_heads_forward(heads, x)
     assert got.shape == (2, 64, 22, 27)
-    assert torch.equal(got, want)
+    # simt: the heads run one after the other with the single-head geometry -> bit-identical.  Tensor-core path: the heads
+    # are a grid dimension (B x 4 virtual images), which may pick another key-split factor, i.e. another fp32 summation
+    # order of the partial sums; P and the value operands are identical.
+    if impl == "simt":
+        assert torch.equal(got, want)
+    else:
+        assert rel_err(got, want) <= 1e-6
+        assert heads[0].last_launches <= 20, heads[0].last_launches      # ONE set of launches for the four heads
     assert heads[0].last_impl == impl
 
 
