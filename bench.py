@@ -255,14 +255,11 @@ def other_configs(ce, dev, flush, peaks):
     shape_line("cfg3/cfg5 head: CE.forward 1x64x512x512", 1, 512, 512, 5)
     torch.manual_seed(5)
     ces = dagl_b200.CES(in_channels=C_IN).to(dev).eval()
-    prev = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        shape_line("CES.forward 1x64x64x64 (12 heads, 3 stage calls + 8 ResBlocks)", 1, 64, 64, 20, fn=ces, heads=12)
-        shape_line("CES.forward 64x64x72x72 (chop batch)", 64, 72, 72, 3, fn=ces, heads=12)
-        shape_line("CES.forward 1x64x256x256 (direct)", 1, 256, 256, 5, fn=ces, heads=12)
-    finally:
-        torch.backends.cudnn.allow_tf32 = prev
+    # the ResBlocks / 1x1 merges of CES are plain cuDNN convolutions under torch's defaults (TF32 allowed), as they are when the
+    # reference runs on this GPU; only the twelve heads are this repo's kernels
+    shape_line("CES.forward 1x64x64x64 (12 heads as 3 stage calls + 8 cuDNN ResBlocks)", 1, 64, 64, 20, fn=ces, heads=12)
+    shape_line("CES.forward 64x64x72x72 (chop batch)", 64, 72, 72, 3, fn=ces, heads=12)
+    shape_line("CES.forward 1x64x256x256 (direct)", 1, 256, 256, 5, fn=ces, heads=12)
     return out
 
 

@@ -262,18 +262,20 @@ __constant__ PvGroup c_groups[2][4] = {
     {{3, 4, 48, 0}, {4, 0, 112, 48}, {5, 0, 112, 160}, {6, 0, 112, 272}}};
 
 // ---------------------------------------------------------------------------------------------
-// Softmax reference of a query row (shared by the clustered kernels and the refinement pass below).
+// Softmax reference of a query row (shared by the clustered kernels and the exact pass below).
 //
 // The pre-pass gives smax_hi = max_k Qh.Kh.  With |x - hi(x)| <= 2^-11 |x| for both operands, S <= Qh.Kh * (1 + 2^-10 +
 // 2^-22); RM_INFL = 1 + 1.25 * 2^-10 also covers the fp32 accumulation of the 13 k-steps.  The logit c*s*relu(s - T) is
 // monotone in s >= 0, so ref = logit(RM_INFL * smax_hi) - 12 bounds every term: P <= 2^12, inside fp16.
 // The logit is quadratic in s, so the bound overshoots the true row maximum by up to ~2^-8 of the maximum logit.  That
-// is < 1 log2 unit for the trained heads (logits <= 140), but for logits of several thousand units every fp16 P would
-// drift into the subnormal range and finally flush to zero.  Rows whose possible overshoot exceeds RM_REFINE_LOG2 units
-// are therefore re-done exactly (fp32, 3 terms) by rowmax_refine_kernel, which stores the exact maximum in smax2.
+// is < 1 log2 unit for the trained heads (logits <= 140), but for logits of several thousand units (random-init networks
+// a few stages deep, rgb_range = 255 models, diverging training) every fp16 P would drift into the subnormal range and
+// finally flush to zero.  Query tiles with a row whose possible overshoot exceeds RM_REFINE_LOG2 units get a second,
+// EXACT pass (rowmax_tc_kernel<true>): the same three split-fp16 MMA terms in the same order as the graph kernel, so the
+// scores are the very values the softmax will see, and the row maximum of the LOGIT is stored in smax2.  With it the row
+// maximum lands on 2^12 exactly, whatever the magnitude.
 // ---------------------------------------------------------------------------------------------
 constexpr float RM_INFL = 1.f + 1.25f / 1024.f;
-constexpr float RM_INFL_EXACT = 1.f + 1.f / 262144.f;     // exact maximum: covers the rounding of 208 fp32 FMAs vs the 3-term MMA sum
 constexpr float RM_REFINE_LOG2 = 12.f;
 
 __device__ __forceinline__ float row_logit_log2(float s, float tA, float tB, float sm_scale_log2) {
@@ -284,85 +286,13 @@ __device__ __forceinline__ bool row_needs_refine(float s_hi /*unscaled Qh.Kh max
   return row_logit_log2(s_hi * RM_INFL, tA, tB, sm_scale_log2) - row_logit_log2(s_hi * (2.f - RM_INFL), tA, tB, sm_scale_log2) >
          RM_REFINE_LOG2;
 }
+// smax2_bits != 0: exact maximum of the logit (log2 units) from the exact pass
 __device__ __forceinline__ float row_softmax_ref(unsigned smax_bits, unsigned smax2_bits, float inv_s, float tA, float tB,
                                                  float sm_scale_log2) {
-  const float s_hi = smax2_bits != 0u ? __uint_as_float(smax2_bits) * inv_s * RM_INFL_EXACT
-                                      : __uint_as_float(smax_bits) * inv_s * RM_INFL;
-  return row_logit_log2(s_hi, tA, tB, sm_scale_log2) - 12.f;
-}
-
-// Exact row maxima for the rows flagged by row_needs_refine (huge logits: rgb_range = 255 models, diverging training).
-// Always launched, but a CTA whose 128 rows are all unflagged exits after reading them (the normal case: ~2 us).
-// Flagged tiles: S = (Qh+Ql).(Kh+Kl) in fp32 FMAs from the packed tiles, key range split over blockIdx.y.
-constexpr int RF_THREADS = 256;
-constexpr int RF_QPITCH = TC_EP + 1;
-constexpr int RF_SM_TOTAL = (TC_BM + TC_BN) * RF_QPITCH * 4;
-__global__ void __launch_bounds__(RF_THREADS)
-rowmax_refine_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
-                     const float* __restrict__ thrA, const float* __restrict__ thrB, const unsigned* __restrict__ absmax,
-                     const unsigned* __restrict__ smax, float sm_scale_log2, int qt_base, unsigned* __restrict__ smax2) {
-  pdl_prologue();
-  extern __shared__ __align__(16) float rf_s[];
-  float* Qs = rf_s;                                  // [128][209]
-  float* Ks = rf_s + TC_BM * RF_QPITCH;              // [48][209]
-  const int qt = qt_base + blockIdx.x, img = blockIdx.z, tid = threadIdx.x;
-  const size_t qidx0 = ((size_t)img * tg.nqt + qt) * TC_BM;
-  const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
-  bool flag = false;
-  if (tid < TC_BM)
-    flag = row_needs_refine(__uint_as_float(__ldg(smax + qidx0 + tid)) * inv_s, __ldg(thrA + qidx0 + tid), __ldg(thrB + qidx0 + tid),
-                            sm_scale_log2);
-  if (!__syncthreads_or(flag ? 1 : 0)) return;
-  const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
-  for (int i = tid; i < TC_BM * TC_ECH; i += RF_THREADS) {            // chunk (kc, row) at kc*2048 + row*16
-    const int kc = i / TC_BM, row = i % TC_BM;
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(qsrc + kc * (TC_BM / 8) * 128 + row * 16));
-    const uint4 l = __ldg(reinterpret_cast<const uint4*>(qsrc + Q_HALF_BYTES + kc * (TC_BM / 8) * 128 + row * 16));
-    const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hv[j]));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lv[j]));
-      Qs[row * RF_QPITCH + kc * 8 + 2 * j] = a.x + b.x;
-      Qs[row * RF_QPITCH + kc * 8 + 2 * j + 1] = a.y + b.y;
-    }
-  }
-  const int t_begin = (int)(((long long)blockIdx.y * tg.NT) / gridDim.y);
-  const int t_end = (int)(((long long)(blockIdx.y + 1) * tg.NT) / gridDim.y);
-  const int r = tid & (TC_BM - 1), kh = tid / TC_BM;                   // row, key half (24 keys)
-  float best = 0.f;
-  for (int t = t_begin; t < t_end; ++t) {
-    __syncthreads();
-    const uint8_t* ksrc = Kp + ((size_t)img * tg.NT + t) * K_TILE_BYTES;
-    for (int i = tid; i < TC_BN * TC_ECH; i += RF_THREADS) {
-      const int kc = i / TC_BN, row = i % TC_BN;
-      const uint4 h = __ldg(reinterpret_cast<const uint4*>(ksrc + kc * (TC_BN / 8) * 128 + row * 16));
-      const uint4 l = __ldg(reinterpret_cast<const uint4*>(ksrc + K_HALF_BYTES + kc * (TC_BN / 8) * 128 + row * 16));
-      const uint32_t hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hv[j]));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lv[j]));
-        Ks[row * RF_QPITCH + kc * 8 + 2 * j] = a.x + b.x;
-        Ks[row * RF_QPITCH + kc * 8 + 2 * j + 1] = a.y + b.y;
-      }
-    }
-    __syncthreads();
-    float acc[24];
-#pragma unroll
-    for (int k = 0; k < 24; ++k) acc[k] = 0.f;
-    for (int e = 0; e < TC_EP; ++e) {
-      const float q = Qs[r * RF_QPITCH + e];
-#pragma unroll
-      for (int k = 0; k < 24; ++k) acc[k] = fmaf(q, Ks[(kh * 24 + k) * RF_QPITCH + e], acc[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 24; ++k) best = fmaxf(best, acc[k]);           // dummy key slots are zero rows: S = 0 <= max
-  }
-  // only flagged rows take the exact value (both key halves of a row: two threads -> atomicMax); Q, K >= 0 so best >= 0
-  const bool mine = row_needs_refine(__uint_as_float(__ldg(smax + qidx0 + r)) * inv_s, __ldg(thrA + qidx0 + r), __ldg(thrB + qidx0 + r),
-                                     sm_scale_log2);
-  if (mine) atomicMax(smax2 + qidx0 + r, __float_as_uint(fmaxf(best, 1e-30f)));
+  // (1 + 2^-22): the stored maximum is itself rounded (half an ulp: 4 log2 units at logits of 1e8), and 2^(12 + 4) would
+  // overflow fp16; two to four ulps of head-room keep P <= 2^12 at every magnitude
+  if (smax2_bits != 0u) return __uint_as_float(smax2_bits) * (1.f + 1.f / 4194304.f) - 12.f;
+  return row_logit_log2(__uint_as_float(smax_bits) * inv_s * RM_INFL, tA, tB, sm_scale_log2) - 12.f;
 }
 
 // =============================================================================================
@@ -378,25 +308,38 @@ rowmax_refine_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* _
 // =============================================================================================
 constexpr int RM_QT = 2;                                    // query tiles per CTA (each K tile is fetched once for both)
 constexpr int RM_KSTAGES = 4;
-constexpr int RM_SM_K = 0;                                  // ring of Kh tiles (19968 B each)
+constexpr int RM_SM_K = 0;                                  // ring of Kh tiles (19968 B each); exact pass: 3 stages of hi|lo tiles
 constexpr int RM_SM_BAR = RM_SM_K + RM_KSTAGES * K_HALF_BYTES;
 constexpr int RM_SM_TOTAL = RM_SM_BAR + 128;
+constexpr int RMX_KSTAGES = 3;
+constexpr int RMX_SM_BAR = RM_SM_K + RMX_KSTAGES * K_TILE_BYTES;
+constexpr int RMX_SM_TOTAL = RMX_SM_BAR + 128;
 constexpr int RM_THREADS = 192;
-constexpr int RM_QCOL = 0;                                  // Qh of the two query tiles: 2 x 104 TMEM columns
+constexpr int RM_QCOL = 0;                                  // Qh of the two query tiles: 2 x 104 TMEM columns (exact: Qh | Ql of one)
 constexpr int RM_DCOL0 = RM_QT * (TC_EP / 2);               // 208: three accumulator buffers of RM_QT x 48 columns
 constexpr int RM_DBUF = 3;
 constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 
-// smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on float bits.
-// The query tiles live in TMEM (A operand of the MMAs, TS form: 27.7 instead of ~51 cycles per N = 48 MMA) and a CTA
-// serves two query tiles per K fetch (the pre-pass would otherwise be bound by the L2 -> SM traffic of the K tiles).
+// EXACT = false (always runs): smax[b][qt*128 + row] = max over the keys of (Qh . Kh) in scaled units (>= 0); atomicMax on
+//   float bits.  The query tiles live in TMEM (A operand of the MMAs, TS form: 27.7 instead of ~51 cycles per N = 48 MMA)
+//   and a CTA serves two query tiles per K fetch (the pre-pass would otherwise be bound by the L2 -> SM traffic of the K tiles).
 //   TMEM: Qh(q0) [0,104) | Qh(q1) [104,208) | D0 [208,304) | D1 [304,400) | D2 [400,496)
+// EXACT = true (always launched; a CTA whose query tile has no row flagged by row_needs_refine exits at once): one query
+//   tile per CTA, the full 3-term score Ql.Kh + Qh.Kl + Qh.Kh with the MMA sequence of the graph kernels, and
+//   smax2[row] = max over the keys of the LOGIT c * S * relu(S - T) in log2 units (what the softmax exponent will be).
+//   TMEM: Qh [0,104) | Ql [104,208) | D0 [208,256) | D1 [304,352) | D2 [400,448)
+template <bool EXACT>
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
-                 int qt_base, int qt_end, unsigned* __restrict__ smax) {
+                 int qt_base, int qt_end, unsigned* __restrict__ smax, const float* __restrict__ thrA,
+                 const float* __restrict__ thrB, const unsigned* __restrict__ absmax, float sm_scale_log2,
+                 unsigned* __restrict__ smax2) {
   pdl_prologue();
+  constexpr int QT = EXACT ? 1 : RM_QT;
+  constexpr int KST = EXACT ? RMX_KSTAGES : RM_KSTAGES;
+  constexpr int KBYTES = EXACT ? K_TILE_BYTES : K_HALF_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RM_SM_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (EXACT ? RMX_SM_BAR : RM_SM_BAR));
   uint64_t* q_ready = bars + 0;   // 128 arrivals: the query tiles are in TMEM
   uint64_t* k_full = bars + 1;    // [4]
   uint64_t* k_empty = bars + 5;   // [4]
@@ -405,15 +348,26 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int qt0 = qt_base + blockIdx.x * RM_QT, split = blockIdx.y, img = blockIdx.z;
-  const int nq_here = min(RM_QT, qt_end - qt0);
+  const int qt0 = qt_base + blockIdx.x * QT, split = blockIdx.y, img = blockIdx.z;
+  const int nq_here = min(QT, qt_end - qt0);
   const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
   const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int nsteps = t_end - t_begin;                       // one key tile per step
+  const float inv_s = EXACT ? 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14))
+                            : 1.f;
+  if (EXACT) {
+    // does any row of this query tile need the exact maximum?  (block-uniform decision, before anything is allocated)
+    bool flag = false;
+    if (tid < TC_BM) {
+      const size_t qi = ((size_t)img * tg.nqt + qt0) * TC_BM + tid;
+      flag = row_needs_refine(__uint_as_float(__ldg(smax + qi)) * inv_s, __ldg(thrA + qi), __ldg(thrB + qi), sm_scale_log2);
+    }
+    if (!__syncthreads_or(flag ? 1 : 0)) return;
+  }
 
   if (tid == 0) {
     mbar_init(q_ready, 128);
-    for (int i = 0; i < RM_KSTAGES; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < KST; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
     for (int i = 0; i < RM_DBUF; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
     mbar_init_fence();
   }
@@ -427,10 +381,10 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     if (elect_one()) {
       const uint8_t* ksrc = Kp + ((size_t)img * tg.NT + t_begin) * K_TILE_BYTES;
       for (int st = 0; st < nsteps; ++st, ksrc += K_TILE_BYTES) {
-        const int s = st % RM_KSTAGES;
-        mbar_wait(k_empty + s, ((uint32_t)(st / RM_KSTAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(k_full + s, K_HALF_BYTES);
-        bulk_g2s(smem + RM_SM_K + s * K_HALF_BYTES, ksrc, K_HALF_BYTES, k_full + s);
+        const int s = st % KST;
+        mbar_wait(k_empty + s, ((uint32_t)(st / KST) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(k_full + s, KBYTES);
+        bulk_g2s(smem + RM_SM_K + s * KBYTES, ksrc, KBYTES, k_full + s);
       }
     }
   } else if (warp == 1) {
@@ -440,17 +394,34 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
       mbar_wait(q_ready, 0);
       tc_fence_after();
       for (int st = 0; st < nsteps; ++st) {
-        const int s = st % RM_KSTAGES, db = st % RM_DBUF;
-        mbar_wait(k_full + s, (uint32_t)(st / RM_KSTAGES) & 1u);
+        const int s = st % KST, db = st % RM_DBUF;
+        mbar_wait(k_full + s, (uint32_t)(st / KST) & 1u);
         mbar_wait(d_empty + db, ((uint32_t)(st / RM_DBUF) & 1u) ^ 1u);
         tc_fence_after();
-        const uint64_t dk = smem_desc(smem_u32(smem + RM_SM_K + s * K_HALF_BYTES), (TC_BN / 8) * 128, 128);
+        const uint64_t dk = smem_desc(smem_u32(smem + RM_SM_K + s * KBYTES), (TC_BN / 8) * 128, 128);
         const uint32_t d0 = tbase + RM_DCOL0 + db * RM_DCOLS;
+        if (EXACT) {
+          // the MMA sequence of the graph kernels (attend_tc4_kernel score issuer): Ql.Kh first, then Qh.Kl / Qh.Kh
+          const uint64_t dk_lo = smem_desc(smem_u32(smem + RM_SM_K + s * KBYTES + K_HALF_BYTES), (TC_BN / 8) * 128, 128);
+          const uint32_t qh = tbase + RM_QCOL, ql = qh + TC_EP / 2;
 #pragma unroll
-        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-          const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
-          mma_f16_ts(d0, tbase + RM_QCOL + ks * 8, dk + ko, idS, ks > 0);
-          if (two_q) mma_f16_ts(d0 + TC_BN, tbase + RM_QCOL + TC_EP / 2 + ks * 8, dk + ko, idS, ks > 0);
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ts(d0, ql + ks * 8, dk + ko, idS, ks > 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ts(d0, qh + ks * 8, dk_lo + ko, idS, 1);
+            mma_f16_ts(d0, qh + ks * 8, dk + ko, idS, 1);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+            const uint64_t ko = (uint64_t)(ks * 2 * (TC_BN / 8) * 128 >> 4);
+            mma_f16_ts(d0, tbase + RM_QCOL + ks * 8, dk + ko, idS, ks > 0);
+            if (two_q) mma_f16_ts(d0 + TC_BN, tbase + RM_QCOL + TC_EP / 2 + ks * 8, dk + ko, idS, ks > 0);
+          }
         }
         mma_commit(k_empty + s);
         mma_commit(d_full + db);
@@ -460,28 +431,36 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     const int quad = warp & 3, lane = tid & 31;
     const int row = quad * 32 + lane;
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
-    // ---- query tiles (hi parts) -> TMEM: lane = row, column j = elements (2j, 2j+1) ----
+    // ---- query tiles -> TMEM: lane = row, column j = elements (2j, 2j+1); slab = (hi part of tile qi) or (hi / lo part) ----
+    constexpr int NSLAB = 2;
 #pragma unroll 1
-    for (int qi = 0; qi < nq_here; ++qi) {
-      const uint8_t* src = Qp + ((size_t)img * tg.nqt + qt0 + qi) * Q_TILE_BYTES + row * 16;
-#pragma unroll 1
+    for (int sl = 0; sl < NSLAB; ++sl) {
+      if (!EXACT && sl >= nq_here) break;
+      const uint8_t* src = Qp + ((size_t)img * tg.nqt + qt0 + (EXACT ? 0 : sl)) * Q_TILE_BYTES + (EXACT ? sl * Q_HALF_BYTES : 0) + row * 16;
+      uint4 c0[TC_KSTEPS], c1[TC_KSTEPS];                  // all 26 loads in flight before the first TMEM store
+#pragma unroll
       for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-        const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
-        const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
-        const uint32_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        tmem_st8(trow + RM_QCOL + qi * (TC_EP / 2) + ks * 8, v);
+        c0[ks] = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
+        c1[ks] = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
+      }
+#pragma unroll
+      for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+        const uint32_t v[8] = {c0[ks].x, c0[ks].y, c0[ks].z, c0[ks].w, c1[ks].x, c1[ks].y, c1[ks].z, c1[ks].w};
+        tmem_st8(trow + RM_QCOL + sl * (TC_EP / 2) + ks * 8, v);
       }
     }
     tmem_wait_st();
     tc_fence_before();
     mbar_arrive(q_ready);
+    const size_t qidx = ((size_t)img * tg.nqt + qt0) * TC_BM + row;
+    const float tA = EXACT ? __ldg(thrA + qidx) : 0.f, tB = EXACT ? __ldg(thrB + qidx) : 0.f;
     float m[RM_QT][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // four chains per row: a single one is latency-bound
     for (int st = 0; st < nsteps; ++st) {
       const int db = st % RM_DBUF;
       mbar_wait(d_full + db, (uint32_t)(st / RM_DBUF) & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int qi = 0; qi < RM_QT; ++qi) {
+      for (int qi = 0; qi < QT; ++qi) {
         if (qi >= nq_here) break;
         uint32_t v[48];
 #pragma unroll
@@ -492,17 +471,24 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
           for (int i = 0; i < 16; ++i) v[c0 + i] = t16[i];
         }
         tmem_wait_ld();
+        if (EXACT) {
+          // dummy key slots are zero rows: S = 0, logit 0 <= the maximum (logits are >= 0)
 #pragma unroll
-        for (int i = 0; i < TC_BN; ++i) m[qi][i & 3] = fmaxf(m[qi][i & 3], __uint_as_float(v[i]));
+          for (int i = 0; i < TC_BN; ++i)
+            m[qi][i & 3] = fmaxf(m[qi][i & 3], row_logit_log2(__uint_as_float(v[i]) * inv_s, tA, tB, sm_scale_log2));
+        } else {
+#pragma unroll
+          for (int i = 0; i < TC_BN; ++i) m[qi][i & 3] = fmaxf(m[qi][i & 3], __uint_as_float(v[i]));
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty + db);
     }
 #pragma unroll
-    for (int qi = 0; qi < RM_QT; ++qi)
+    for (int qi = 0; qi < QT; ++qi)
       if (qi < nq_here)
-        atomicMax(smax + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row,
+        atomicMax((EXACT ? smax2 : smax) + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row,
                   __float_as_uint(fmaxf(fmaxf(m[qi][0], m[qi][1]), fmaxf(m[qi][2], m[qi][3]))));
   }
   tc_fence_before();
@@ -898,7 +884,8 @@ constexpr int S4_T = S4_K + V4_KST * K_TILE_BYTES;          // 79872 = 78 * 1024
 constexpr int S4_P = S4_T + V4_TST * V4_TSTAGE_BYTES;       // + 43008
 constexpr int S4_BAR = S4_P + V4_PSLOTS * P_SLOT_BYTES;
 constexpr int S4_RED = S4_BAR + 512;
-constexpr int S4_TOTAL = S4_RED + 2 * 4 * 3 * 32 * 4;
+constexpr int S4_LSUM = S4_RED + 2 * 4 * 3 * 32 * 4;         // rank 0: [4 ranks][128 rows] row-sum partials of the cluster
+constexpr int S4_TOTAL = S4_LSUM + 4 * TC_BM * 4;
 static_assert(S4_T % 1024 == 0 && S4_P % 1024 == 0, "v4 smem alignment");
 static_assert(S4_TOTAL <= 232448, "v4 smem");
 
@@ -920,7 +907,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const float* __restrict__ thrA, const float* __restrict__ thrB,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
                   float sm_scale_log2,
-                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][4][Nq]*/,
+                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][Nq]: summed over the cluster*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -955,7 +942,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 #endif
 
   if (tid == 0) {
-    mbar_init(q_ready, 128);
+    mbar_init(q_ready, 12);
     for (int i = 0; i < 2; ++i) {
       mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
       mbar_init(s_full + i, 1); mbar_init(s_free + i, V4_OPT_WARP_ARRIVE ? 12 : 384);
@@ -1199,23 +1186,37 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
     const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
     // ---- query tile -> TMEM (A operand of the score MMAs): lane = row, column j = elements (2j, 2j+1) ----
-    if (sub == 0) {
-      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES;
-#pragma unroll 1
-      for (int part = 0; part < 2; ++part) {
-        const uint8_t* src = qsrc + part * Q_HALF_BYTES + row * 16;
-        const uint32_t col = part ? V4_QL_COL : V4_QH_COL;
-#pragma unroll 1
-        for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-          const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
-          const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
-          const uint32_t v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          tmem_st8(trow + col + ks * 8, v);
+    // All twelve warps take part (the three warps of a lane quadrant split the 26 (part, k-step) slabs) and every thread
+    // issues its loads back to back: with one warp per quadrant and one dependent load -> store pair at a time this
+    // prologue took ~13 us per cluster, a third of a chop-leaf cluster's whole life.
+    {
+      const uint8_t* qsrc = Qp + ((size_t)img * tg.nqt + qt) * Q_TILE_BYTES + row * 16;
+      constexpr int NSLAB = 2 * TC_KSTEPS;                 // slab = (part, k-step): 8 TMEM columns
+      constexpr int PER = (NSLAB + 2) / 3;                 // 9 slabs per warp of the quadrant (the last warp: 8)
+      uint4 c0[PER], c1[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int slab = sub + 3 * i;
+        if (slab < NSLAB) {
+          const int part = slab / TC_KSTEPS, ks = slab % TC_KSTEPS;
+          const uint8_t* src = qsrc + part * Q_HALF_BYTES;
+          c0[i] = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks) * (TC_BM / 8) * 128));
+          c1[i] = __ldg(reinterpret_cast<const uint4*>(src + (2 * ks + 1) * (TC_BM / 8) * 128));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int slab = sub + 3 * i;
+        if (slab < NSLAB) {
+          const int part = slab / TC_KSTEPS, ks = slab % TC_KSTEPS;
+          const uint32_t v[8] = {c0[i].x, c0[i].y, c0[i].z, c0[i].w, c1[i].x, c1[i].y, c1[i].z, c1[i].w};
+          tmem_st8(trow + (part ? V4_QL_COL : V4_QH_COL) + ks * 8, v);
         }
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(q_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);                 // one arrival per warp (12)
     }
     const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
     const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) *
@@ -1358,9 +1359,12 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     xl[sub * 32 + lane] = l_run;
     xc[sub * 32 + lane] = cnt;
     asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
-    if (sub == 0 && qvalid) {
-      lpart[(((size_t)img * nsplit + split) * 4 + rank) * g.Nq + q] = (xl[lane] + xl[32 + lane]) + xl[64 + lane];
-      if (nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
+    if (sub == 0) {
+      // row-sum partial of this rank -> rank 0's smem (DSMEM store, made visible by the cluster barrier below); rank 0 adds
+      // the four in a fixed order, so the fold sees ONE partial per key split
+      const uint32_t dst = mapa(smem_u32(reinterpret_cast<float*>(smem + S4_LSUM) + rank * TC_BM + row), 0u);
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"((xl[lane] + xl[32 + lane]) + xl[64 + lane]) : "memory");
+      if (qvalid && nnz != nullptr) atomicAdd(nnz + (size_t)img * g.Nq + q, xc[lane] + xc[32 + lane] + xc[64 + lane]);
     }
   }
 
@@ -1378,6 +1382,10 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  if (rank == 0 && tid < TC_BM && qt * TC_BM + tid < g.Nq) {
+    const float* ls = reinterpret_cast<const float*>(smem + S4_LSUM) + tid;
+    lpart[((size_t)img * nsplit + split) * g.Nq + qt * TC_BM + tid] = ((ls[0] + ls[TC_BM]) + ls[2 * TC_BM]) + ls[3 * TC_BM];
+  }
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
 }
 
@@ -1551,15 +1559,18 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   if (pre_split < 1) pre_split = 1;
   const int max_split = tg.NT;
   if (pre_split > max_split) pre_split = max_split;
-  DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-  DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin, qt_end, smax));
+  DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
+  DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<false>, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin,
+                          qt_end, smax, thrA, thrB, absmax, sm_scale_log2, smax2));
   DAGL_LAUNCH_CHECK();
-  // ... made exact for rows with huge logits (normally every CTA exits at once)
+  // ... made exact for query tiles with huge logits (normally every CTA exits at once)
   {
-    int rsplit = tg.NT < 8 ? tg.NT : 8;
-    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SM_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(rowmax_refine_kernel, dim3(qt_end - qt_begin, rsplit, g.B), RF_THREADS, RF_SM_TOTAL, st, tg, Qp, Kp, thrA, thrB,
-                            absmax, smax, sm_scale_log2, qt_begin, smax2));
+    int xsplit = 148 / ((qt_end - qt_begin) * g.B);
+    if (xsplit < 1) xsplit = 1;
+    if (xsplit > max_split) xsplit = max_split;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RMX_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<true>, dim3(qt_end - qt_begin, xsplit, g.B), RM_THREADS, RMX_SM_TOTAL, st, tg, Qp, Kp, xsplit,
+                            qt_begin, qt_end, smax, thrA, thrB, absmax, sm_scale_log2, smax2));
     DAGL_LAUNCH_CHECK();
   }
   if (int rc = prof_begin(st)) return rc;
@@ -1575,12 +1586,14 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
   const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
-  const int nq_total = g.B * g.Nq;
-  DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, variant == 4 ? 4 : 2, q_begin, q_end, lpart, coef));
-  DAGL_LAUNCH_CHECK();
-  if (a.rows_out != nullptr)     // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
+  const int nparts = variant == 4 ? 1 : 2;       // row-sum partials per key split (the 4-CTA kernel reduces over its cluster)
+  if (a.rows_out != nullptr) {   // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
+    const int nq_total = g.B * g.Nq;
+    DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, nparts, q_begin, q_end, lpart, coef));
+    DAGL_LAUNCH_CHECK();
     return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
-  return launch_fold_partials(g, w.nsplit, Opart, coef, a.y, st);
+  }
+  return launch_fold_partials(g, w.nsplit, nparts, Opart, lpart, a.y, st);
 }
 
 }  // namespace dagl

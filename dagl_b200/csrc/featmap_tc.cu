@@ -166,6 +166,16 @@ pack_b_gamma_beta_kernel(Geom g, FtGeom eg, const float* __restrict__ b, const u
   dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
+// gamma / beta of all NH heads of a stage in one pass over the shared input (stage calls; launched next to the repack)
+template <int NH>
+__global__ void __launch_bounds__(GB_THREADS)
+gamma_beta_heads_kernel(Geom g, const float* __restrict__ b, HeadPtrs thr_w, HeadPtrs thr_b, HeadPtrs bias_w, HeadPtrs bias_b,
+                        float* __restrict__ gamma, float* __restrict__ beta) {
+  pdl_prologue();
+  extern __shared__ float gbh_smem[];
+  gamma_beta_heads_body<NH>(g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta, gbh_smem, blockIdx.x, blockIdx.y);
+}
+
 // Persistent: one CTA per SM walks the (image, 128-pixel tile) items; the packed weights (72 KB) are loaded ONCE per CTA
 // (they were 40 % of the smem fill of a one-tile CTA, and the kernel is bound by that L2 -> SM traffic), the halo is
 // single-buffered and the two 64-column accumulator sets alternate so that the epilogue of a tile overlaps the halo load
@@ -394,15 +404,26 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw,
     DAGL_CUDA_OK(launch_pdl(absmax_img_kernel, dim3(128, nreal), 256, 0, st, b, n_img, bmax));
     DAGL_LAUNCH_CHECK();
   }
+  if (g.NH > 1) {
+    // stage call: gamma / beta of all heads in one pass over b (own launch: it needs NH x the filter smem, which would
+    // throttle the bandwidth-bound repack CTAs if the two shared a launch as they do for a single head)
+    const size_t smem_h = gamma_beta_heads_smem_bytes(g.C, g.NH);
+    auto kern = g.NH == 2 ? gamma_beta_heads_kernel<2> : g.NH == 3 ? gamma_beta_heads_kernel<3> : gamma_beta_heads_kernel<4>;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+    DAGL_CUDA_OK(launch_pdl(kern, dim3((g.Nq + 31) / 32, nreal), GB_THREADS, smem_h, st, g, b, thr_w, thr_b, bias_w, bias_b, gamma, beta));
+    DAGL_LAUNCH_CHECK();
+  }
   {
-    const int n_gb = ((g.Nq + 31) / 32) * g.B;                                   // per VIRTUAL image (head-specific filters)
+    const int n_gb = g.NH > 1 ? 0 : ((g.Nq + 31) / 32) * g.B;
     const int n_pack = reuse_b ? 0 : ((eg.NPG + GB_THREADS - 1) / GB_THREADS) * FT_GROUPS * nreal;
     const size_t smem = gamma_beta_smem_bytes(g.C);
     if (smem > 48 * 1024)
       DAGL_CUDA_OK(cudaFuncSetAttribute(pack_b_gamma_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, smem, st, g, eg, b, bmax, bimg, n_gb, thr_w, thr_b,
-                            bias_w, bias_b, gamma, beta));
-    DAGL_LAUNCH_CHECK();
+    if (n_gb + n_pack > 0) {
+      DAGL_CUDA_OK(launch_pdl(pack_b_gamma_beta_kernel, n_gb + n_pack, GB_THREADS, n_gb ? smem : 0, st, g, eg, b, bmax, bimg, n_gb, thr_w,
+                              thr_b, bias_w, bias_b, gamma, beta));
+      DAGL_LAUNCH_CHECK();
+    }
   }
   DAGL_CUDA_OK(cudaFuncSetAttribute(featmap_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SM_TOTAL));
   int dev = 0, sms = 148;

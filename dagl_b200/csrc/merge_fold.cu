@@ -74,16 +74,19 @@ __global__ void fold_kernel(Geom g, int shift_major, const float* __restrict__ O
 }
 
 // Fused merge + fold for the fixed-reference kernels (shift-major partial rows): every output pixel gathers its <= 2x2
-// covering queries straight from the key-split partials, scaled by coef[q] = 1 / sum of the row-sum partials
-// (dagl.py:265-272).  Thread = (pixel, 4 channels); fixed summation order, no atomics.
+// covering queries straight from the key-split partials and scales them by 1 / (sum of the row-sum partials): merge
+// coefficients, merge and fold + coverage normalisation (dagl.py:265-272) in ONE pass.  Thread = (pixel, 4 channels) with
+// the channel quad fastest, so four neighbouring threads read the 64 contiguous bytes of one (query, shift) record.
+// Fixed summation order, no atomics.  lpart: [B][nsplit][nparts][Nq].
 __global__ void __launch_bounds__(256)
-fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const float* __restrict__ coef,
+fold_partials_kernel(Geom g, int nsplit, int nparts, const float* __restrict__ Opart, const float* __restrict__ lpart,
                      float* __restrict__ y) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = g.B * 4 * g.Nk;
   if (i >= total) return;
-  const int px = i % g.W, py = (i / g.W) % g.H, c4 = (i / g.Nk) & 3, img = i / (4 * g.Nk);
+  const int c4 = i & 3, pix = (i >> 2) % g.Nk, img = (i >> 2) / g.Nk;
+  const int px = pix % g.W, py = pix / g.W;
   const int qy_lo = py >> 2, qy_hi = min(g.nqy - 1, (py + PADK) >> 2);
   const int qx_lo = px >> 2, qx_hi = min(g.nqx - 1, (px + PADK) >> 2);
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,22 +95,26 @@ fold_partials_kernel(Geom g, int nsplit, const float* __restrict__ Opart, const 
       const int q = qy * g.nqx + qx;
       const int sh = (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float L = 0.f;
       for (int s = 0; s < nsplit; ++s) {
         const size_t row = ((size_t)img * nsplit + s) * g.Nq + q;
         const float4 v = __ldg(reinterpret_cast<const float4*>(Opart + row * VD + sh * CI) + c4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int h = 0; h < nparts; ++h) L += __ldg(lpart + (((size_t)img * nsplit + s) * nparts + h) * g.Nq + q);
       }
-      const float c = __ldg(coef + (size_t)img * nsplit * g.Nq + q);      // same value for every split
+      // L > 0 whenever the row has a valid key (the row maximum itself contributes ~2^12); the guard keeps a degenerate
+      // row from turning into inf * 0 = NaN
+      const float c = L > 0.f ? 1.f / L : 0.f;
       sum.x = fmaf(c, acc.x, sum.x); sum.y = fmaf(c, acc.y, sum.y); sum.z = fmaf(c, acc.z, sum.z); sum.w = fmaf(c, acc.w, sum.w);
     }
   const float inv = 1.f / (float)((qy_hi - qy_lo + 1) * (qx_hi - qx_lo + 1));
-  float* yo = y + g.y_offset(img) + (size_t)(4 * c4) * g.Nk + (size_t)py * g.W + px;
+  float* yo = y + g.y_offset(img) + (size_t)(4 * c4) * g.Nk + pix;
   yo[0] = sum.x * inv; yo[(size_t)g.Nk] = sum.y * inv; yo[2 * (size_t)g.Nk] = sum.z * inv; yo[3 * (size_t)g.Nk] = sum.w * inv;
 }
 
-int launch_fold_partials(const Geom& g, int nsplit, const float* Opart, const float* coef, float* y, cudaStream_t st) {
+int launch_fold_partials(const Geom& g, int nsplit, int nparts, const float* Opart, const float* lpart, float* y, cudaStream_t st) {
   const int total = g.B * 4 * g.Nk;
-  DAGL_CUDA_OK(launch_pdl(fold_partials_kernel, (total + 255) / 256, 256, 0, st, g, nsplit, Opart, coef, y));
+  DAGL_CUDA_OK(launch_pdl(fold_partials_kernel, (total + 255) / 256, 256, 0, st, g, nsplit, nparts, Opart, lpart, y));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

@@ -15,3 +15,5 @@ HEADS=4 HW=64 timeout 300 python tools/launch_timeline.py > $O/${TAG}_timeline_s
 HEADS=4 B=64 HW=72 timeout 300 python tools/launch_timeline.py > $O/${TAG}_timeline_stage_chop64x72.log 2>&1
 HEADS=4 timeout 300 python tools/launch_timeline.py > $O/${TAG}_timeline_stage_256.log 2>&1
 grep -E "passed|failed|error" $O/${TAG}_pytest.log | tail -5; cat $O/${TAG}_smoke.log; cut -c1-1500 $O/${TAG}_bench.log; cat $O/${TAG}_timeline.log $O/${TAG}_timeline_64.log $O/${TAG}_timeline_stage_64.log
+python tools/ces_breakdown.py > $O/${TAG}_ces256.log 2>&1; B=64 HW=72 python tools/ces_breakdown.py > $O/${TAG}_ces_chop.log 2>&1; HW=64 python tools/ces_breakdown.py > $O/${TAG}_ces64.log 2>&1
+cat $O/${TAG}_ces256.log $O/${TAG}_ces_chop.log $O/${TAG}_ces64.log

@@ -8,7 +8,9 @@ from dagl_b200 import _lib
 from oracle import ce_oracle as O
 
 NAMES_TC = ["absmax_img", "pack_b+gamma_beta", "featmap_tc", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar", "pack_tiles(Q)",
-            "pack_theta", "rowmax_tc", "rowmax_refine", "attend_tc4", "merge_coef", "fold_partials"]
+            "pack_theta", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
+NAMES_STAGE = ["absmax_img", "gamma_beta_heads", "pack_b", "featmap_tc", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar",
+               "pack_tiles(Q)", "pack_theta", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
 HEADS = int(os.environ.get("HEADS", "1"))        # > 1: one CES stage call (heads as a grid dimension)
 dev = torch.device("cuda:0")
 H = W = int(os.environ.get("HW", "256"))
@@ -39,7 +41,8 @@ with torch.no_grad():
         L.dagl_profile_enable(0)
         v = [buf[i] * 1e3 for i in range(n)]
         acc = v if acc is None else [a + b for a, b in zip(acc, v)]
-names = NAMES_TC if len(acc) == len(NAMES_TC) else [f"launch {i}" for i in range(len(acc))]
+names = (NAMES_TC if len(acc) == len(NAMES_TC) and HEADS == 1 else NAMES_STAGE if len(acc) == len(NAMES_STAGE) and HEADS > 1 else
+         [f"launch {i}" for i in range(len(acc))])
 tot = 0.0
 for nm, t in zip(names, acc):
     print(f"{nm:16s} {t / reps:8.1f} us")
