@@ -268,8 +268,14 @@ def strong_scaling(ce, dev, flush, world, rank, params):
     on this rank's tiles, one NCCL all-gather of the aggregation rows, fold): ms (max over ranks), speed-up against the
     same image on one GPU, and the in-run difference between the sharded and the single-GPU result."""
     import torch.distributed as dist
+    import dagl_b200
     from dagl_b200 import parallel
     rec = []
+    # every rank must hold the SAME head here (the weak-scaling arm above gives each rank its own image and head)
+    params0, _ = workload_tensors(0)
+    ce = dagl_b200.CE(in_channels=C_IN, impl=ce.impl)
+    ce.load_state_dict(params0)
+    ce = ce.to(dev).eval()
     for size, iters in ((256, 20), (512, 5)):
         gen = torch.Generator().manual_seed(4242 + size)                 # the same image on every rank
         x = torch.randn(1, C_IN, size, size, generator=gen).to(dev)

@@ -247,6 +247,7 @@ class CE(nn.Module):
         tpr = (nqt + world - 1) // world                      # tiles per rank (last ranks may own fewer / none)
         t0, t1 = min(nqt, rank * tpr), min(nqt, (rank + 1) * tpr)
         rpr = tpr * 128                                       # rows per rank in the exchange buffer
+        nq = ((H + 3) // 4) * ((W + 3) // 4)
         with torch.cuda.device(b.device):
             # exchange buffer [world][B][rpr][784]: this rank's kernel writes straight into its slot through a row-offset
             # view (the library indexes rows by global query id), so there is no staging copy on either side
@@ -254,7 +255,7 @@ class CE(nn.Module):
             stream = torch.cuda.current_stream(b.device).cuda_stream
             if t1 > t0:
                 if B != 1:
-                    mine = torch.empty(B, nqt * 128, 784, dtype=torch.float32, device=b.device)
+                    mine = torch.empty(B, nq, 784, dtype=torch.float32, device=b.device)    # the library's row layout: [B][Nq][784]
                     rows_ptr = mine.data_ptr()
                 else:
                     mine = None
@@ -267,7 +268,6 @@ class CE(nn.Module):
                 self.last_impl = L.dagl_last_impl().decode()
                 self.last_launches = L.dagl_last_launch_count()
                 if mine is not None:
-                    nq = ((H + 3) // 4) * ((W + 3) // 4)
                     q0, q1 = t0 * 128, min(nq, t1 * 128)
                     full[rank, :, : q1 - q0] = mine[:, q0:q1]
             # in place: rank r's contribution already sits in slot r of the gathered buffer (NCCL's in-place all-gather layout)
@@ -276,7 +276,6 @@ class CE(nn.Module):
                 rows = full.view(1, world * rpr, 784)                                    # already in query order
             else:
                 rows = full.permute(1, 0, 2, 3).reshape(B, world * rpr, 784)
-            nq = ((H + 3) // 4) * ((W + 3) // 4)
             if rows.shape[1] != nq or not rows.is_contiguous():
                 rows = rows[:, :nq].contiguous()
             y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
