@@ -874,10 +874,24 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 #define V4_OPT_WARP_ARRIVE 1
 #endif
 constexpr int V4_THREADS = TC_THREADS + 96;                 // + forwarder warp + score-MMA issuer warp + K loader warp
-constexpr int V4_KST = 2, V4_TST = 3, V4_TSLOTS = 4;
-constexpr int V4_PSLOTS = 8;                                // P slots: (producer rank) + 4 * (round parity): double buffered
+#ifndef V4_PDEPTH
+#define V4_PDEPTH 2
+#endif
+#ifndef V4_KSTAGES
+#define V4_KSTAGES 2
+#endif
+#ifndef V4_TSTAGES
+#define V4_TSTAGES 3
+#endif
+constexpr int V4_KST = V4_KSTAGES, V4_TST = V4_TSTAGES, V4_TSLOTS = 4;
+constexpr int V4_PD = V4_PDEPTH;                            // P tiles a producer rank may have in flight
+constexpr int V4_PSLOTS = 4 * V4_PD;                        // P slots: (producer rank) + 4 * (own-tile index mod V4_PD)
 constexpr int V4_TSEG_BYTES = (TC_BN + TH_SEG_PIX) * 32;    // one dy row of theta for a pair of tiles: 112 pixels = 3584 B
-constexpr int V4_TSTAGE_BYTES = V4_TSLOTS * V4_TSEG_BYTES;  // one stage = up to 4 theta rows of a tile pair: 14336
+constexpr int V4_TSTAGE_BYTES = V4_TSLOTS * V4_TSEG_BYTES;  // one stage of rank 3 = 4 theta rows of a tile pair: 14336
+#ifndef V4_TASYM
+#define V4_TASYM 0                                          // ranks 0..2 need only 2 theta rows per pair: twice the ring depth in the same smem
+#endif
+constexpr int V4_TST_MAX = V4_TASYM ? 2 * V4_TST : V4_TST;
 constexpr int V4_O_COLS = 208, V4_QH_COL = 208, V4_QL_COL = 312, V4_S_COL0 = 416;
 constexpr int S4_K = 0;
 constexpr int S4_T = S4_K + V4_KST * K_TILE_BYTES;          // 79872 = 78 * 1024
@@ -913,16 +927,17 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
   uint64_t* q_ready = bars + 0;   // query tile resident in TMEM (128 arrivals)
-  uint64_t* k_full = bars + 1;    // [2] ring over OWN tiles
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* t_full = bars + 7;    // [3] ring over PAIRS of tiles
-  uint64_t* t_empty = bars + 10;  // [3]
-  uint64_t* s_full = bars + 13;   // [2]
-  uint64_t* s_free = bars + 15;   // [2]
-  uint64_t* p_full = bars + 17;   // [8] slot r + 4*parity is written by cluster rank r (into all four CTAs)
-  uint64_t* p_free = bars + 25;   // [8] only the slots of `rank` are waited on here: 4 commit arrivals (every CTA's P.V)
-  uint64_t* pv_last = bars + 33;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
+  uint64_t* k_full = bars + 1;                  // [V4_KST] ring over OWN tiles
+  uint64_t* k_empty = k_full + V4_KST;          // [V4_KST]
+  uint64_t* t_full = k_empty + V4_KST;          // [V4_TST] ring over PAIRS of tiles
+  uint64_t* t_empty = t_full + V4_TST_MAX;      // [V4_TST_MAX]
+  uint64_t* s_full = t_empty + V4_TST_MAX;      // [2]
+  uint64_t* s_free = s_full + 2;                // [2]
+  uint64_t* p_full = s_free + 2;                // [V4_PSLOTS] slot r + 4*d is written by cluster rank r (into all four CTAs)
+  uint64_t* p_free = p_full + V4_PSLOTS;        // [V4_PSLOTS] only the slots of `rank` are waited on here: 4 commit arrivals (every CTA's P.V)
+  uint64_t* pv_last = p_free + V4_PSLOTS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_last + 1);
+  static_assert((7 + 2 * V4_KST + 2 * V4_TST_MAX + 2 * V4_PSLOTS) * 8 <= 512, "v4 barrier area");
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
@@ -934,6 +949,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   const int ntiles = t_end - t_begin;
   const int n_own = (ntiles - rank + 3) / 4;                // local tiles j with (j & 3) == rank
   const int nslots = rank == 3 ? 4 : 2;                     // theta rows this rank needs
+  // theta ring of this rank: the same bytes hold twice as many (half-size) stages for the ranks that need two rows
+  const int tst = (V4_TASYM && rank != 3) ? 2 * V4_TST : V4_TST;
+  const int tstage_bytes = (V4_TASYM && rank != 3) ? V4_TSTAGE_BYTES / 2 : V4_TSTAGE_BYTES;
 #ifdef DAGL_TC_TRACE
   long long tr_a = 0, tr_b = 0, tr_c = 0;
   const bool tl_on = (blockIdx.x >> 2) == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -943,11 +961,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 
   if (tid == 0) {
     mbar_init(q_ready, 12);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-      mbar_init(s_full + i, 1); mbar_init(s_free + i, V4_OPT_WARP_ARRIVE ? 12 : 384);
-    }
-    for (int i = 0; i < V4_TST; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1); }
+    for (int i = 0; i < V4_KST; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_free + i, V4_OPT_WARP_ARRIVE ? 12 : 384); }
+    for (int i = 0; i < V4_TST_MAX; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 1); }
     for (int i = 0; i < V4_PSLOTS; ++i) { mbar_init(p_full + i, (i & 3) == rank ? (V4_OPT_WARP_ARRIVE ? 12 : 384) : 1); mbar_init(p_free + i, 4); }
     mbar_init(pv_last, 1);
     mbar_init_fence();
@@ -969,19 +985,19 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       // theta rows of the tile pair (2h, 2h+1): 96 consecutive key slots + the 64-pixel window, ONE copy per row
       const int nhalf = (ntiles + 1) >> 1;
       for (int h = 0; h < nhalf; ++h) {
-        const int s = h % V4_TST;
-        { TRACE_T0(); mbar_wait(t_empty + s, ((uint32_t)(h / V4_TST) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+        const int s = h % tst;
+        { TRACE_T0(); mbar_wait(t_empty + s, ((uint32_t)(h / tst) & 1u) ^ 1u); TRACE_ADD(tr_b); }
 #ifdef DAGL_TC_TRACE
         if (g_tc_dbg_mode & 8) {                             // timing experiment: one small segment per pair
           mbar_arrive_expect_tx(t_full + s, 1024);
-          bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES, thp, 1024, t_full + s);
+          bulk_g2s(smem + S4_T + s * tstage_bytes, thp, 1024, t_full + s);
           continue;
         }
 #endif
         mbar_arrive_expect_tx(t_full + s, (uint32_t)nslots * V4_TSEG_BYTES);
         const int k0 = (t_begin + 2 * h) * TC_BN;            // multiple of 8, and so is Wp
         for (int sl = 0; sl < nslots; ++sl)
-          bulk_g2s(smem + S4_T + s * V4_TSTAGE_BYTES + sl * V4_TSEG_BYTES, thp + (size_t)(k0 + c_rows4[rank][sl] * tg.Wp) * 32,
+          bulk_g2s(smem + S4_T + s * tstage_bytes + sl * V4_TSEG_BYTES, thp + (size_t)(k0 + c_rows4[rank][sl] * tg.Wp) * 32,
                    V4_TSEG_BYTES, t_full + s);
         TL(h >> 1, 20);
       }
@@ -1033,14 +1049,14 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 #define V4_PREWAIT(JN, UN, PN)                                                                            \
       do {                                                                                                \
         if (((UN) & 1) == 0) {                                                                            \
-          if (++w_ts == V4_TST) w_ts = 0;                                                                 \
+          if (++w_ts == tst) w_ts = 0;                                                                    \
           if (w_ts == 0) w_ph ^= 1u;                                                                      \
           { TRACE_T0(); mbar_wait(t_full + w_ts, w_ph); TRACE_ADD(tr_c); }                                \
           if ((UN) == 0) TL(PN, 16);                                                                      \
         }                                                                                                 \
-        const int ps_ = (UN) + 4 * ((PN) & 1);                                                            \
+        const int ps_ = (UN) + 4 * ((PN) % V4_PD);                                                        \
         if ((UN) != rank) mbar_arrive_expect_tx(p_full + ps_, V4_FWD_BYTES);                              \
-        { TRACE_T0(); mbar_wait(p_full + ps_, (uint32_t)((PN) >> 1) & 1u); TRACE_ADD(tr_b); }            \
+        { TRACE_T0(); mbar_wait(p_full + ps_, (uint32_t)((PN) / V4_PD) & 1u); TRACE_ADD(tr_b); }         \
         TL(PN, 8 + 2 * (UN));                                                                             \
         if (!skip_fence) tc_fence_after();                                                                \
       } while (0)
@@ -1055,13 +1071,13 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 #endif
       if (ntiles > 0) V4_PREWAIT(0, 0, 0);
       for (int p = 0; 4 * p < ntiles; ++p) {
-        const uint32_t pslot0 = p_base + (p & 1) * (4 * P_SLOT_BYTES);
+        const uint32_t pslot0 = p_base + (p % V4_PD) * (4 * P_SLOT_BYTES);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = 4 * p + u;                                           // producer rank u, P slot u + 4 * (p & 1)
           if (j >= ntiles) break;
-          if ((u & 1) == 0 && ++i_ts == V4_TST) i_ts = 0;
-          const uint32_t tile0 = t_base + i_ts * V4_TSTAGE_BYTES + (u & 1) * (TC_BN * 32);   // 2nd tile of the pair: +48 pixels
+          if ((u & 1) == 0 && ++i_ts == tst) i_ts = 0;
+          const uint32_t tile0 = t_base + i_ts * tstage_bytes + (u & 1) * (TC_BN * 32);   // 2nd tile of the pair: +48 pixels
           const uint32_t g_start0 = (tile0 + g_off[0]) >> 4, g_start1 = (tile0 + g_off[1]) >> 4;
           const uint64_t ad0 = smem_desc(pslot0 + u * P_SLOT_BYTES, (TC_BM / 8) * 128, 128);
           const uint32_t acc0 = j > 0 ? 1u : 0u;
@@ -1089,12 +1105,12 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
           }
 #ifdef DAGL_TC_TRACE
           if (g_tc_dbg_mode & 32) {                                              // timing experiment: plain arrives instead of tcgen05.commit
-            if (j + 8 < ntiles)
-              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(p_free_prod[u] + 32 * (p & 1)) : "memory");
+            if (j + 4 * V4_PD < ntiles)
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(p_free_prod[u] + 32 * (p % V4_PD)) : "memory");
             if ((u & 1) == 1 || j == ntiles - 1) mbar_arrive(t_empty + i_ts);
           } else {
 #endif
-          if (j + 8 < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p & 1));   // slot may be refilled by its producer CTA (+4 barriers)
+          if (j + 4 * V4_PD < ntiles) mma_commit_caddr(p_free_prod[u] + 32 * (p % V4_PD));   // slot may be refilled by its producer CTA (+4 barriers)
           if ((u & 1) == 1 || j == ntiles - 1) mma_commit(t_empty + i_ts);
 #ifdef DAGL_TC_TRACE
           }
@@ -1161,8 +1177,8 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         rbar[u] = mapa(smem_u32(p_full + rank), peer);
       }
       for (int i = 0; i < n_own; ++i) {
-        const uint32_t par = (uint32_t)(i & 1);                            // slot rank + 4*par
-        mbar_wait(p_full + rank + 4 * par, (uint32_t)(i >> 1) & 1u);
+        const uint32_t par = (uint32_t)(i % V4_PD);                        // slot rank + 4*par
+        mbar_wait(p_full + rank + 4 * par, (uint32_t)(i / V4_PD) & 1u);
         TL(i, 17);
 #ifdef DAGL_TC_TRACE
         const uint32_t fwd_bytes = (g_tc_dbg_mode & 4) ? 16u : (uint32_t)P_SLOT_BYTES;   // timing experiment: 16-byte forwards
@@ -1298,10 +1314,10 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         cnt += __popc(mk);
       }
       l_run += psum;
-      const int par = i & 1;                                // my slot for this tile: rank + 4*par (last used by own tile i-2)
+      const int par = i % V4_PD;                            // my slot for this tile: rank + 4*par (last used by own tile i - V4_PD)
       const uint32_t p_local = p_local0 + par * 4 * P_SLOT_BYTES;
       if (warp == 2 && lane == 0) TL(i, 2);
-      { TRACE_T0(); mbar_wait(p_free + rank + 4 * par, ((uint32_t)(i >> 1) & 1u) ^ 1u); TRACE_ADD(tr_b); }
+      { TRACE_T0(); mbar_wait(p_free + rank + 4 * par, ((uint32_t)(i / V4_PD) & 1u) ^ 1u); TRACE_ADD(tr_b); }
       if (warp == 2 && lane == 0) TL(i, 3);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_local + 2048), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
