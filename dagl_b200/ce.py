@@ -115,14 +115,15 @@ class CE(nn.Module):
         """fc1/fc2 and g/theta packed once for the tensor-core kernels (``dagl_ce_pack_weights_f32``) and reused while the
         weights are unchanged (eval mode only; keyed on the tensors' storage and in-place version counters, so
         ``load_state_dict`` / optimiser steps invalidate it)."""
-        ws = (self.fc1[0].weight, self.fc2[0].weight, self.g.weight, self.theta.weight, self.fc1[0].bias, self.fc2[0].bias)
+        ws = (self.fc1[0].weight, self.fc2[0].weight, self.g.weight, self.theta.weight, self.fc1[0].bias, self.fc2[0].bias,
+              self.g.bias, self.theta.bias)
         key = (str(device),) + tuple(v for t in ws for v in (t.data_ptr(), t._version))
         if self._packed_key != key:
             L = _lib.lib()
             buf = torch.empty(L.dagl_ce_packed_weights_bytes(), dtype=torch.uint8, device=device)
-            t1, t2, t3, t4, t5, t6 = (t.detach().contiguous() for t in ws)
+            t1, t2, t3, t4, t5, t6, t7, t8 = (t.detach().contiguous() for t in ws)
             tmp = _lib.DaglCEWeights(fc1_w=t1.data_ptr(), fc2_w=t2.data_ptr(), g_w=t3.data_ptr(), theta_w=t4.data_ptr(),
-                                     fc1_b=t5.data_ptr(), fc2_b=t6.data_ptr(),
+                                     fc1_b=t5.data_ptr(), fc2_b=t6.data_ptr(), g_b=t7.data_ptr(), theta_b=t8.data_ptr(),
                                      in_channels=self.in_channels, inter_channels=self.inter_channels, ksize=self.ksize)
             rc = L.dagl_ce_pack_weights_f32(C.byref(tmp), buf.data_ptr(), buf.numel(),
                                             torch.cuda.current_stream(device).cuda_stream)

@@ -20,6 +20,7 @@
 //    through the softmax.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_utils.cuh"
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256)
 pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsigned* __restrict__ absmax,
                   uint8_t* __restrict__ tiles, unsigned long long* __restrict__ tilemask,
                   const float* __restrict__ Kbar, const float* __restrict__ gamma, const float* __restrict__ beta,
-                  float* __restrict__ thrA, float* __restrict__ thrB, float* __restrict__ colsum_partial) {
+                  float4* __restrict__ thr4, float* __restrict__ colsum_partial) {
   pdl_prologue();
   extern __shared__ __align__(16) float rows_s[];            // [RPB][196]
   constexpr int BPT = ROWS / RPB;                            // blocks per tile
@@ -190,8 +191,8 @@ pack_tiles_kernel(Geom g, TcGeom tg, const float* __restrict__ src, const unsign
       if (lane == 0) {
         const size_t idx = ((size_t)img * ntile + t) * ROWS + r;
         const float mu = (float)s;
-        thrA[idx] = (q < g.Nq) ? mu * __ldg(gamma + (size_t)img * g.Nq + q) : 0.f;
-        thrB[idx] = (q < g.Nq) ? __ldg(beta + (size_t)img * g.Nq + q) : -1.f;
+        thr4[idx] = (q < g.Nq) ? make_float4(mu, 0.f, __ldg(gamma + (size_t)img * g.Nq + q), __ldg(beta + (size_t)img * g.Nq + q))
+                               : make_float4(0.f, 0.f, 0.f, -1.f);
       }
     }
   }
@@ -331,8 +332,8 @@ constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 template <bool EXACT>
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
-                 int qt_base, int qt_end, unsigned* __restrict__ smax, const float* __restrict__ thrA,
-                 const float* __restrict__ thrB, const unsigned* __restrict__ absmax, float sm_scale_log2,
+                 int qt_base, int qt_end, unsigned* __restrict__ smax, const float4* __restrict__ thr4,
+                 const unsigned* __restrict__ absmax, float sm_scale_log2,
                  unsigned* __restrict__ smax2) {
   pdl_prologue();
   constexpr int QT = EXACT ? 1 : RM_QT;
@@ -360,7 +361,8 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     bool flag = false;
     if (tid < TC_BM) {
       const size_t qi = ((size_t)img * tg.nqt + qt0) * TC_BM + tid;
-      flag = row_needs_refine(__uint_as_float(__ldg(smax + qi)) * inv_s, __ldg(thrA + qi), __ldg(thrB + qi), sm_scale_log2);
+      const float4 t4 = __ldg(thr4 + qi);
+      flag = row_needs_refine(__uint_as_float(__ldg(smax + qi)) * inv_s, (t4.x + t4.y) * t4.z, t4.w, sm_scale_log2);
     }
     if (!__syncthreads_or(flag ? 1 : 0)) return;
   }
@@ -453,7 +455,8 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     tc_fence_before();
     mbar_arrive(q_ready);
     const size_t qidx = ((size_t)img * tg.nqt + qt0) * TC_BM + row;
-    const float tA = EXACT ? __ldg(thrA + qidx) : 0.f, tB = EXACT ? __ldg(thrB + qidx) : 0.f;
+    const float4 t4 = EXACT ? __ldg(thr4 + qidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float tA = (t4.x + t4.y) * t4.z, tB = t4.w;             // T = mu * gamma - beta (dagl.py:256), mu from two column halves
     float m[RM_QT][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // four chains per row: a single one is latency-bound
     for (int st = 0; st < nsteps; ++st) {
       const int db = st % RM_DBUF;
@@ -511,7 +514,7 @@ static_assert(S2_TOTAL <= 232448, "v2 kernel exceeds the 227 KB dynamic shared m
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
-                  const float* __restrict__ thrA, const float* __restrict__ thrB,
+                  const float4* __restrict__ thr4 /*per query row: mu partials (x, y), gamma, beta*/,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
                   float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
@@ -708,7 +711,8 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     const int row = quad * 32 + lane;
     const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16);
     const size_t qidx = ((size_t)img * tg.nqt + qt) * TC_BM + row;
-    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
+    const float4 t4 = __ldg(thr4 + qidx);
+    const float tA = (t4.x + t4.y) * t4.z, tB = t4.w;             // T = mu * gamma - beta (dagl.py:256), mu from two column halves
     const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) *
                                pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
@@ -918,7 +922,7 @@ __constant__ PvGroup4 c_groups4[4][2] = {
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(V4_THREADS, 1)
 attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp,
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
-                  const float* __restrict__ thrA, const float* __restrict__ thrB,
+                  const float4* __restrict__ thr4 /*per query row: mu partials (x, y), gamma, beta*/,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
                   float sm_scale_log2,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][Nq]: summed over the cluster*/,
@@ -1234,7 +1238,8 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
       __syncwarp();
       if (lane == 0) mbar_arrive(q_ready);                 // one arrival per warp (12)
     }
-    const float tA = __ldg(thrA + qidx), tB = __ldg(thrB + qidx);
+    const float4 t4 = __ldg(thr4 + qidx);
+    const float tA = (t4.x + t4.y) * t4.z, tB = t4.w;             // T = mu * gamma - beta (dagl.py:256), mu from two column halves
     const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) *
                                pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
@@ -1427,6 +1432,10 @@ __global__ void merge_coef_fixed_kernel(int B, int Nq, int nsplit, int nparts, i
 // ---------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static double split_cost() {
+  static const double c = [] { const char* e = getenv("DAGL_SPLIT_COST"); return e ? atof(e) : 4.0; }();
+  return c;
+}
 static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range, int csize = 2) {
   const long long base = (long long)g.B * nqt_range * csize;
   const int sms = csize == 4 ? 132 : 148;          // 4-CTA clusters cannot use every SM (GPC sizes 16/18/20)
@@ -1435,15 +1444,16 @@ static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range, int csize =
   double best_cost = 1e30;
   for (int s = 1; s <= smax; ++s) {
     const double waves = (double)((base * s + sms - 1) / sms);
-    // time ~ waves * (tiles per CTA + fixed per-CTA overhead of ~6 tiles), plus partial traffic
-    const double cost = waves * ((double)tg.NT / s + 6.0) + 0.5 * s;
+    // time ~ waves * (tiles per CTA + fixed per-CTA overhead of ~6 tiles), plus the fold's serial loop over the splits
+    // (measured at 64^2: ~2.5 us per split = ~5 tile times; DAGL_SPLIT_COST overrides for experiments)
+    const double cost = waves * ((double)tg.NT / s + 6.0) + split_cost() * s;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return best;
 }
 
 struct TcWs {
-  size_t absmax, Qp, Kp, Thp, tilemask, thrA, thrB, smax, colsum, kbar, Opart, lpart, coef, total;
+  size_t absmax, Qp, Kp, Thp, tilemask, thr4, smax, colsum, kbar, Opart, lpart, coef, total;
   int nsplit;
 };
 
@@ -1464,8 +1474,7 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg, int nqt_range = 0) {
   w.Kp = take((size_t)g.B * tg.NT * K_TILE_BYTES);
   w.Thp = take((size_t)g.B * tg.NP * 32);
   w.tilemask = take((size_t)g.B * tg.NT * 8);
-  w.thrA = take((size_t)g.B * tg.nqt * TC_BM * 4);
-  w.thrB = take((size_t)g.B * tg.nqt * TC_BM * 4);
+  w.thr4 = take((size_t)g.B * tg.nqt * TC_BM * 16);
   w.smax = take(2 * (size_t)g.B * tg.nqt * TC_BM * 4);      // pre-pass maxima | exact maxima of refined rows
   w.colsum = take((size_t)g.B * tg.NT * ED * 4);
   w.kbar = take((size_t)g.B * ED * 4);
@@ -1479,11 +1488,22 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg, int nqt_range = 0) {
 
 size_t attend_tc_workspace_bytes(const Geom& g, int nqt_range) { return tc_ws(g, tc_geom(g), nqt_range).total; }
 
-void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, float** colsum) {
-  const TcWs w = tc_ws(g, tc_geom(g));
+// operand buffers inside the graph kernel's workspace that the prologue kernels write directly (none of these offsets
+// depends on the key-split factor)
+AttendBuffers attend_tc_buffers(const Geom& g, void* attend_ws) {
+  const TcGeom tg = tc_geom(g);
+  const TcWs w = tc_ws(g, tg);
   char* base = static_cast<char*>(attend_ws);
-  *ktiles = reinterpret_cast<uint8_t*>(base + w.Kp);
-  *colsum = reinterpret_cast<float*>(base + w.colsum);
+  AttendBuffers b;
+  b.ktiles = reinterpret_cast<uint8_t*>(base + w.Kp);
+  b.colsum = reinterpret_cast<float*>(base + w.colsum);
+  b.qtiles = reinterpret_cast<uint8_t*>(base + w.Qp);
+  b.thp = reinterpret_cast<uint8_t*>(base + w.Thp);
+  b.np_t = tg.NP;
+  b.tilemask = reinterpret_cast<unsigned long long*>(base + w.tilemask);
+  b.thr4 = reinterpret_cast<float*>(base + w.thr4);
+  b.kbar = reinterpret_cast<float*>(base + w.kbar);
+  return b;
 }
 
 
@@ -1515,8 +1535,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   uint8_t* Kp = reinterpret_cast<uint8_t*>(base + w.Kp);
   uint8_t* Thp = reinterpret_cast<uint8_t*>(base + w.Thp);
   unsigned long long* tilemask = reinterpret_cast<unsigned long long*>(base + w.tilemask);
-  float* thrA = reinterpret_cast<float*>(base + w.thrA);
-  float* thrB = reinterpret_cast<float*>(base + w.thrB);
+  float4* thr4 = reinterpret_cast<float4*>(base + w.thr4);
   float* Opart = reinterpret_cast<float*>(base + w.Opart);
   float* lpart = reinterpret_cast<float*>(base + w.lpart);
   float* coef = reinterpret_cast<float*>(base + w.coef);
@@ -1539,31 +1558,28 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   unsigned* smax2 = smax + (size_t)g.B * tg.nqt * TC_BM;
   DAGL_CUDA_OK(cudaMemsetAsync(smax, 0, 2 * (size_t)g.B * tg.nqt * TC_BM * 4, st));
 
-  {
-    // keys first: the pack kernel also produces the per-tile column sums from which Kbar is formed when the
-    // caller did not supply it (full forward); the query pack needs Kbar for the per-query thresholds.
+  if (!a.k_packed) {
+    // split entry (embeddings supplied by the caller as fp32): pack them into the operand tiles here.  Keys first: the
+    // pack kernel also produces the per-tile column sums from which Kbar is formed when the caller did not supply it;
+    // the query pack needs Kbar for the per-query thresholds.  (The full forward writes all of this from the epilogues of
+    // the feature-map and embedding kernels: a.k_packed.)
     const float* Kbar = a.Kbar;
     float* colsum = nullptr;
     if (Kbar == nullptr) colsum = reinterpret_cast<float*>(base + w.colsum);
-    int kblocks = tg.NT;
-    if (a.k_packed) {                                   // the embedding kernel wrote Kp and the column sums already;
-      kblocks = a.kblocks;                              // the tile validity masks come from pack_theta_kernel below
-    } else {
-      auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
-      const size_t smem_k = (size_t)TC_BN * ED * 4;
-      kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, nullptr, colsum);
-      DAGL_LAUNCH_CHECK();
-    }
+    auto kk = pack_tiles_kernel<TC_BN, 1, TC_BN>;
+    const size_t smem_k = (size_t)TC_BN * ED * 4;
+    kk<<<dim3(tg.NT, g.B), 256, smem_k, st>>>(g, tg, a.K, absmax, Kp, tilemask, nullptr, nullptr, nullptr, nullptr, colsum);
+    DAGL_LAUNCH_CHECK();
     if (Kbar == nullptr) {
       float* kb = a.kbar_out ? a.kbar_out : reinterpret_cast<float*>(base + w.kbar);
-      if (int rc = launch_kbar(g, colsum, kblocks, kb, st)) return rc;
+      if (int rc = launch_kbar(g, colsum, tg.NT, kb, st)) return rc;
       Kbar = kb;
     }
     auto kq = pack_tiles_kernel<TC_BM, 0, 16>;
     const size_t smem = (size_t)16 * ED * 4;
-    DAGL_CUDA_OK(launch_pdl(kq, dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st, g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thrA, thrB, nullptr));
+    DAGL_CUDA_OK(launch_pdl(kq, dim3(tg.nqt * (TC_BM / 16), g.B), 256, smem, st, g, tg, a.Q, absmax, Qp, nullptr, Kbar, a.gamma, a.beta, thr4, nullptr));
     DAGL_LAUNCH_CHECK();
-    DAGL_CUDA_OK(launch_pdl(pack_theta_kernel, dim3((tg.NP + 255) / 256, g.B), 256, 0, st, g, tg, a.theta, absmax, Thp, a.k_packed ? tilemask : nullptr));
+    DAGL_CUDA_OK(launch_pdl(pack_theta_kernel, dim3((tg.NP + 255) / 256, g.B), 256, 0, st, g, tg, a.theta, absmax, Thp, nullptr));
     DAGL_LAUNCH_CHECK();
   }
 
@@ -1577,7 +1593,7 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   if (pre_split > max_split) pre_split = max_split;
   DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
   DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<false>, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin,
-                          qt_end, smax, thrA, thrB, absmax, sm_scale_log2, smax2));
+                          qt_end, smax, thr4, absmax, sm_scale_log2, smax2));
   DAGL_LAUNCH_CHECK();
   // ... made exact for query tiles with huge logits (normally every CTA exits at once)
   {
@@ -1586,17 +1602,17 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
     if (xsplit > max_split) xsplit = max_split;
     DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RMX_SM_TOTAL));
     DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<true>, dim3(qt_end - qt_begin, xsplit, g.B), RM_THREADS, RMX_SM_TOTAL, st, tg, Qp, Kp, xsplit,
-                            qt_begin, qt_end, smax, thrA, thrB, absmax, sm_scale_log2, smax2));
+                            qt_begin, qt_end, smax, thr4, absmax, sm_scale_log2, smax2));
     DAGL_LAUNCH_CHECK();
   }
   if (int rc = prof_begin(st)) return rc;
   if (variant == 4) {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax, smax2,
+    DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
                             sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
   } else {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thrA, thrB, absmax, smax, smax2,
+    DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
                             sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
   }
   DAGL_LAUNCH_CHECK();

@@ -35,7 +35,7 @@ int prof_end(cudaStream_t st) {
 
 // Workspace carve-up shared by workspace_bytes / forward / workspace_view.
 struct WsLayout {
-  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, feat, embed, attend, total;
+  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, packw, feat, embed, attend, total;
   int kblocks_simt, kblocks_tc;
 };
 
@@ -56,6 +56,7 @@ static WsLayout ws_layout(const Geom& g, int nqt_range = 0) {
   L.kpart = take((size_t)g.B * kblocks * ED * f);
   L.Kbar = take((size_t)g.B * ED * f);
   L.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
+  L.packw = take((size_t)g.NH * (embed_tc_packed_weights_bytes() + feature_maps_tc_packed_weights_bytes()));   // per-call weight packing
   L.feat = take(feature_maps_tc_workspace_bytes(g));
   L.embed = take(embed_tc_workspace_bytes(g));
   L.attend = off;
@@ -181,32 +182,48 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
 
   bool k_packed = false;
   const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
+  const bool tc_prologue = impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g);
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
-  if (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g)) {
-    if ((rc = launch_feature_maps_tc(g, b, hw, G, Th, gamma, beta, absmax, base + L.feat, L.embed - L.feat, reuse_b, st))) return rc;
+  if (tc_prologue) {
+    // Tensor-core prologue: every kernel writes the next one's operands from its epilogue.  feature maps -> fp16 images of G
+    // (embedding input) and theta (graph kernel's value operand) + all fp16 scales; key embedding -> key tiles + column sums;
+    // Kbar; query embedding -> query tiles + threshold terms.  The fp32 intermediates exist only for the debug entry
+    // (parity tests read them through dagl_ce_workspace_view).
+    const size_t pack_bytes = embed_tc_packed_weights_bytes() + feature_maps_tc_packed_weights_bytes();
+    for (int h = 0; h < nh; ++h)
+      if (hw.packed[h] == nullptr) {                    // the caller did not pre-pack (dagl_ce_pack_weights_f32): do it per call
+        char* slot = base + L.packw + (size_t)h * pack_bytes;
+        if ((rc = launch_pack_fc_weights(hw.fc1_w[h], hw.fc1_b[h], hw.fc2_w[h], hw.fc2_b[h], slot, embed_tc_packed_weights_bytes(), st))) return rc;
+        if ((rc = launch_pack_feat_weights(g.C, hw.g_w[h], hw.g_b[h], hw.th_w[h], hw.th_b[h], slot + embed_tc_packed_weights_bytes(),
+                                           feature_maps_tc_packed_weights_bytes(), st))) return rc;
+        hw.packed[h] = slot;
+      }
+    const AttendBuffers ab = attend_tc_buffers(g, base + L.attend);
+    uint8_t *ghi, *glo;
+    int npg;
+    embed_tc_g_buffers(g, base + L.embed, &ghi, &glo, &npg);
+    const FeatTargets ft{ghi, glo, npg, ab.thp, ab.np_t};
+    if ((rc = launch_feature_maps_tc(g, b, hw, debug ? G : nullptr, debug ? Th : nullptr, gamma, beta, absmax, base + L.feat,
+                                     L.embed - L.feat, reuse_b, ft, st))) return rc;
+    const EmbTargets et{ab.ktiles, ab.colsum, Kbar, ab.qtiles, ab.thr4, ab.tilemask};
+    if ((rc = launch_embed_tc(g, hw, debug ? Q : nullptr, debug ? K : nullptr, absmax, base + L.embed, L.attend - L.embed, gamma,
+                              beta, et, st))) return rc;
+    k_packed = true;
   } else {
+    // fp32 CUDA-core prologue (impl simt, or an input channel count the tensor-core feature kernel is not built for): the
+    // graph kernel packs its operands itself from the fp32 embeddings
     if ((rc = launch_feature_maps(g, b, w->g_w, w->g_b, w->theta_w, w->theta_b, G, Th, absmax, st))) return rc;
     if ((rc = launch_gamma_beta(g, b, w->thr_w, w->thr_b, w->bias_w, w->bias_b, gamma, beta, st))) return rc;
-  }
-  if (impl == DAGL_IMPL_SIMT) {
     if ((rc = launch_embed(g, G, w->fc1_w, w->fc1_b, Q, g.nqy, g.nqx, SQ, g.qpad_top, g.qpad_left, nullptr, absmax, AMAX_Q, st))) return rc;
     if ((rc = launch_embed(g, G, w->fc2_w, w->fc2_b, K, g.H, g.W, 1, PADK, PADK, kpart, absmax, AMAX_K, st))) return rc;
     if ((rc = launch_kbar(g, kpart, L.kblocks_simt, Kbar, st))) return rc;
-  } else {
-    // the key embeddings go straight into the graph kernel's fp16 key tiles (+ column sums for Kbar); the fp32 K array is
-    // only materialised for the debug entry (parity tests read it through dagl_ce_workspace_view)
-    uint8_t* ktiles; float* colsum;
-    attend_tc_key_buffers(g, base + L.attend, &ktiles, &colsum);
-    if ((rc = launch_embed_tc(g, G, hw, Q, debug ? K : nullptr, absmax, base + L.embed, L.attend - L.embed, ktiles, colsum, st))) return rc;
-    Kbar = nullptr;      // formed inside the tensor-core launcher from the key column sums
-    k_packed = true;
   }
 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
-  a.k_packed = k_packed; a.kblocks = L.kblocks_tc;
+  a.k_packed = k_packed;
   a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
   a.rows_out = rows_out; a.qt_begin = qt_begin; a.qt_end = qt_end;
   return run_attend(g, a, impl, absmax, st);
@@ -298,7 +315,7 @@ size_t dagl_ce_packed_weights_bytes(void) { return embed_tc_packed_weights_bytes
 
 int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t packed_bytes, void* stream) {
   call_state().launches = 0;
-  if (!w || !w->fc1_w || !w->fc2_w || !w->fc1_b || !w->fc2_b || !w->g_w || !w->theta_w || !packed) {
+  if (!w || !w->fc1_w || !w->fc2_w || !w->fc1_b || !w->fc2_b || !w->g_w || !w->g_b || !w->theta_w || !w->theta_b || !packed) {
     call_state().err = "null pointer";
     return DAGL_ERR_INVALID_ARG;
   }
@@ -313,7 +330,7 @@ int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t pa
   int rc = launch_pack_fc_weights(w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, packed, embed_tc_packed_weights_bytes(),
                                   static_cast<cudaStream_t>(stream));
   if (rc == 0)
-    rc = launch_pack_feat_weights(w->in_channels, w->g_w, w->theta_w, static_cast<char*>(packed) + embed_tc_packed_weights_bytes(),
+    rc = launch_pack_feat_weights(w->in_channels, w->g_w, w->g_b, w->theta_w, w->theta_b, static_cast<char*>(packed) + embed_tc_packed_weights_bytes(),
                                   feature_maps_tc_packed_weights_bytes(), static_cast<cudaStream_t>(stream));
   return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
 }

@@ -137,7 +137,11 @@ int embed_tc_num_tiles(const Geom& g);
 bool feature_maps_tc_supported(const Geom& g);
 size_t feature_maps_tc_workspace_bytes(const Geom& g);
 size_t feature_maps_tc_packed_weights_bytes();
-int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* packed, size_t packed_bytes, cudaStream_t st);
+int launch_pack_feat_weights(int C, const float* g_w, const float* g_b, const float* th_w, const float* th_b, void* packed,
+                             size_t packed_bytes, cudaStream_t st);
+// where the feature-map epilogue writes the fp16 images of G (embed_tc.cu's input) and theta (attend_tc.cu's value operand)
+struct FeatTargets { uint8_t* ghi; uint8_t* glo; int npg; uint8_t* thp; int np_t; };
+const float* embed_tc_fc_meta(const void* packed);    // [l1 fc1, max|b1|, l1 fc2, max|b2|] inside a packed-weights image
 // per-head parameter pointers of the (up to MAX_HEADS) heads that share the input
 struct HeadWeights {
   const float* g_w[MAX_HEADS]; const float* g_b[MAX_HEADS]; const float* th_w[MAX_HEADS]; const float* th_b[MAX_HEADS];
@@ -146,12 +150,20 @@ struct HeadWeights {
   const void* packed[MAX_HEADS];       // nullable: dagl_ce_pack_weights_f32 image (fc1 | fc2 | meta, then g/theta)
 };
 int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw, float* G, float* Th, float* gamma,
-                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, cudaStream_t st);
+                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, const FeatTargets& out,
+                           cudaStream_t st);
 size_t embed_tc_packed_weights_bytes();
 int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, void* packed,
                            size_t packed_bytes, cudaStream_t st);
-int launch_embed_tc(const Geom& g, const float* G, const HeadWeights& hw, float* Q, float* K, unsigned* absmax, void* ws,
-                    size_t ws_bytes, uint8_t* ktiles, float* colsum, cudaStream_t st);
+// query-side outputs of the embedding epilogue: mu partials [B][nqt*128][2 output halves], gamma / beta padded to whole tiles
+struct EmbQOut { float* thr4; const float* kbar; const float* gamma; const float* beta; };
+// where the embedding epilogues write the graph kernel's operands (inside its workspace, attend_tc_buffers)
+struct EmbTargets {
+  uint8_t* ktiles; float* colsum; float* kbar; uint8_t* qtiles; float* thr4; unsigned long long* tilemask;
+};
+void embed_tc_g_buffers(const Geom& g, void* ws, uint8_t** ghi, uint8_t** glo, int* npg);
+int launch_embed_tc(const Geom& g, const HeadWeights& hw, float* Q, float* K, const unsigned* absmax, void* ws, size_t ws_bytes,
+                    const float* gamma, const float* beta, const EmbTargets& out, cudaStream_t st);
 
 struct AttendArgs {
   const float* Q; const float* K; const float* Kbar; const float* gamma; const float* beta;
@@ -163,13 +175,17 @@ struct AttendArgs {
   // rows_out is set the merged rows [B][Nq][49][16] are written there and the fold is left to the caller
   int qt_begin = 0, qt_end = 0;
   float* rows_out = nullptr;
-  // keys already packed into the tensor-core tiles (and their column sums formed) by the embedding kernel: K is unused,
-  // `kblocks` = number of column-sum partials per image
+  // full forward: every operand of the graph kernel (key / query tiles, theta image, tile masks, threshold terms, Kbar) was
+  // already written into its workspace by the epilogues of the prologue kernels; Q, K, Kbar, gamma, beta, theta are unused
   bool k_packed = false;
-  int kblocks = 0;
 };
-// where the tensor-core graph kernel expects its packed key tiles / column-sum partials inside its workspace
-void attend_tc_key_buffers(const Geom& g, void* attend_ws, uint8_t** ktiles, float** colsum);
+// operand buffers inside the tensor-core graph kernel's workspace that the prologue epilogues write directly
+struct AttendBuffers {
+  uint8_t* ktiles; float* colsum; uint8_t* qtiles; uint8_t* thp; int np_t; unsigned long long* tilemask;
+  float* thr4;      // [B][nqt*128][4]: mu partial (fc1 outputs 0..111), mu partial (112..195), gamma, beta
+  float* kbar;
+};
+AttendBuffers attend_tc_buffers(const Geom& g, void* attend_ws);
 size_t merge_fold_scratch_bytes(const Geom& g);      // Omerged [B][Nq][784]
 int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float* coef, float* Omerged, float* y,
                      int shift_major, cudaStream_t st);

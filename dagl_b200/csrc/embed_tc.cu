@@ -48,8 +48,9 @@ constexpr int EB_SM_G = 0;                                           // two halo
 constexpr int EB_SM_W = 2 * EB_G_BYTES;                              // 129024 = 126 * 1024
 constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-sum exchange [4][112] floats
 constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
-constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + MAX_HEADS * EB_N * 4;   // mbarriers + TMEM base (384 B), then the bias vectors [heads][208]
-constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4;   // query launch
+constexpr int EB_MU_BYTES = 2 * EB_M * 8;            // query launch: the two epilogue warps of a row exchange their partial mu (doubles)
+constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // mbarriers + TMEM base (384 B), bias vectors [heads][208], mu exchange
+constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // query launch
 constexpr int EB_THREADS = 384;                    // warps 0, 7 weight taps (even / odd), 1 MMA issuer, 2-5 + 8-11 epilogue, 6 G halos
 constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
 constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
@@ -119,46 +120,11 @@ pack_fc_kernel(const float* __restrict__ w, const unsigned* __restrict__ wmax, u
   }
 }
 
-// G [16][H][W] fp32 -> zero-padded flat [NPG pixels][16 ch] fp16 hi and lo (SWIZZLE_32B pre-applied)
-__global__ void __launch_bounds__(256)
-pack_g_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, unsigned* __restrict__ absmax,
-              uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, HeadPtrs kmeta_h, int fused_keys) {
-  pdl_prologue();
-  const int img = blockIdx.y;
-  const int pix = blockIdx.x * 256 + threadIdx.x;
-  const float* kmeta = fused_keys ? static_cast<const float*>(kmeta_h.p[g.head(img)]) : nullptr;
-  // fused key pack: absmax slot 1 <- a-priori bound on max K = max|G| * l1(fc2) + max|b2| (float bits; K >= 0), the
-  // fp16 scale of the key tiles; written here because this kernel precedes both embedding launches
-  if (kmeta != nullptr && pix == 0) absmax[img * 4 + 1] = __float_as_uint(__uint_as_float(absmax[img * 4 + 3]) * kmeta[2] + kmeta[3]);
-  if (pix >= eg.NPG) return;
-  const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
-  const int r = pix / eg.Wp, cc = pix % eg.Wp;
-  const int y = r - PADK, x = cc - PADK;
-  const bool inb = (y >= 0 && y < g.H && x >= 0 && x < g.W);
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = 0.f, b = 0.f;
-    if (inb) {
-      a = __ldg(G + (((size_t)img * CI + 2 * j) * g.H + y) * g.W + x) * scale;
-      b = __ldg(G + (((size_t)img * CI + 2 * j + 1) * g.H + y) * g.W + x) * scale;
-    }
-    const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
-    const __half l0 = __float2half_rn(a - __half2float(h0)), l1 = __float2half_rn(b - __half2float(h1));
-    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-  }
-  const int sw = (pix >> 2) & 1;
-  uint4* dh = reinterpret_cast<uint4*>(ghi + ((size_t)img * eg.NPG + pix) * 32);
-  uint4* dl = reinterpret_cast<uint4*>(glo + ((size_t)img * eg.NPG + pix) * 32);
-  dh[sw] = make_uint4(h[0], h[1], h[2], h[3]);
-  dh[sw ^ 1] = make_uint4(h[4], h[5], h[6], h[7]);
-  dl[sw] = make_uint4(l[0], l[1], l[2], l[3]);
-  dl[sw ^ 1] = make_uint4(l[4], l[5], l[6], l[7]);
-}
-
-// QG = false: keys (every pixel) -> out[y*W+x][196] and/or the fp16 key tiles + column sums for Kbar, absmax slot 1
-// QG = true : queries -> out[q][196], absmax slot 0; the A operand is the gathered patch image (pack_qpatch_kernel)
+// QG = false: keys (every pixel) -> the graph kernel's fp16 hi|lo key tiles + per-item column sums for Kbar
+// QG = true : queries -> the graph kernel's fp16 hi|lo query tiles + the per-query threshold terms (mu partial, gamma, beta);
+//             the A operand is the gathered patch image (gather_qpatch_kernel)
+// The fp16 scales are the a-priori bounds in absmax slots 0 (Q) and 1 (K), written by the feature-map epilogue; `out`
+// (fp32 [rows][196]) is only written for the debug entry.
 //
 // Persistent kernel: one CTA per SM walks the work items (image, 128-pixel tile, output half) with a stride of the grid.
 // The G halo and the TMEM accumulators are double buffered, the weight taps stream through one ring that runs across
@@ -178,10 +144,10 @@ template <bool QG>
 __global__ void __launch_bounds__(EB_THREADS, 1)
 embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the gathered query-patch image*/,
                 const uint8_t* __restrict__ glo, HeadPtrs wp_h /*packed fc weights per head*/, HeadPtrs bias_h,
-                const unsigned* __restrict__ absmax_in /*[B][4]: slot 3 = max|G|*/, HeadPtrs wmax_h,
-                float* __restrict__ out /*nullable when key tiles are written*/, unsigned* __restrict__ absmax_out,
-                uint8_t* __restrict__ ktiles /*mode 0, nullable: fp16 hi|lo key tiles of the graph kernel*/,
-                float* __restrict__ colsum /*with ktiles: [B][ntile][196] column sums of a tile's rows*/) {
+                const unsigned* __restrict__ absmax_in /*[B][4]: bounds on Q, K, theta, G*/, HeadPtrs wmax_h,
+                float* __restrict__ out /*nullable: fp32 copy for the debug entry*/,
+                uint8_t* __restrict__ ktiles /*keys: fp16 hi|lo key tiles of the graph kernel; queries: its query tiles*/,
+                float* __restrict__ colsum /*keys: [B][ntile][196] column sums of an item's rows*/, EmbQOut qo /*queries only*/) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int STAGE = QG ? EB_QSTAGE_BYTES : EB_WSTAGE_BYTES;      // QG: [A hi 4 KB | A lo 4 KB | weight tap]
@@ -324,10 +290,11 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
     const int quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
     const uint32_t trow0 = tbase + ((uint32_t)(quad * 32) << 16);
-    const bool fused = !QG && (ktiles != nullptr);
     const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
     constexpr int K_HALF = EB_KTILE * EB_N * 2;                              // 19968: hi part, then lo part
+    constexpr int Q_HALF = EB_M * EB_N * 2;                                  // 53248: query tile, hi part
     float* csum_s = reinterpret_cast<float*>(smem + SM_CSUM);             // [4 warps][112]
+    double* mu_s = reinterpret_cast<double*>(smem + SM_BAR + 384 + MAX_HEADS * EB_N * 4);   // [2][128]
     int it = 0;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       int img, tile, eh;
@@ -348,16 +315,17 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         orow = (size_t)img * g.Nq + p;
       }
       const float inv = winv / pow2_scale_e(absmax_in[img * 4 + 3], 14);
-      // fused key pack: the fp16 scale comes from an a-priori bound on K written to absmax slot 1 BEFORE this launch
-      // (pack_g_kernel), so no pass over K is needed to find its maximum
-      const float kscale = fused ? pow2_scale_e(absmax_in[img * 4 + 1], 14) : 1.f;
+      // fp16 scale of the tiles: an a-priori bound on Q / K (absmax slots 0 / 1), so no pass over the embeddings is needed
+      const float oscale = pow2_scale_e(absmax_in[img * 4 + (QG ? 0 : 1)], 14);
       const int kt = p / EB_KTILE, kr = p % EB_KTILE;                        // key tile / row of this pixel slot
-      uint8_t* ktile = fused && kt < ntile_k ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * K_HALF) : nullptr;
+      uint8_t* ktile = (!QG && kt < ntile_k) ? ktiles + ((size_t)img * ntile_k + kt) * (size_t)(2 * K_HALF) : nullptr;
+      uint8_t* qtile = QG ? ktiles + ((size_t)img * eg.nqt + tile) * (size_t)(2 * Q_HALF) : nullptr;
+      const float* kbar = QG ? qo.kbar + (size_t)img * ED : nullptr;
       const uint32_t trow = trow0 + ab * EB_ACC_COLS;
-      float vmax = 0.f;
+      double mu = 0.0;
       mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      // one 16-column chunk: bias + ReLU, fp32 store and / or fp16 key-tile store + column sums
+      // one 16-column chunk: bias + ReLU, fp16 hi|lo tile store, and column sums (keys) / the mu partial (queries)
       auto process = [&](int c16, const uint32_t (&v)[16], const uint32_t (&vc)[16]) {
         const int eb = e0 + c16 * 16;
         float f[16];
@@ -365,32 +333,42 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         for (int i = 0; i < 16; ++i) {
           const int e = eb + i;
           f[i] = (valid && e < ED) ? fmaxf((__uint_as_float(v[i]) + __uint_as_float(vc[i])) * inv + bias_s[e], 0.f) : 0.f;
-          vmax = fmaxf(vmax, f[i]);
         }
         if (valid && out != nullptr) {
           float4* dst = reinterpret_cast<float4*>(out + orow * ED + eb);
           const int n4 = min(4, (ED - eb) / 4);                    // 196 = 12*16 + 4
           for (int i = 0; i < n4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         }
-        if (fused) {
-          if (ktile != nullptr) {                                  // dummy slots (x >= W, p >= NkP) get zero rows
+        if (QG || ktile != nullptr) {                              // dummy key slots (x >= W, p >= NkP) get zero rows
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              uint32_t hi[4], lo[4];
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float x0 = f[h8 * 8 + 2 * j] * kscale, x1 = f[h8 * 8 + 2 * j + 1] * kscale;
-                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-                hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-              }
-              const int kc = eb / 8 + h8;                          // 16-byte chunk column of the K-major no-swizzle tile
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = f[h8 * 8 + 2 * j] * oscale, x1 = f[h8 * 8 + 2 * j + 1] * oscale;
+              const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+              const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+              hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            const int kc = eb / 8 + h8;                            // 16-byte chunk column of the K-major no-swizzle tile
+            if (QG) {
+              const uint32_t off = (uint32_t)(kc * (EB_M / 8) * 128 + r * 16);
+              *reinterpret_cast<uint4*>(qtile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(qtile + Q_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
               const uint32_t off = (uint32_t)(kc * (EB_KTILE / 8) * 128 + (kr / 8) * 128 + (kr % 8) * 16);
               *reinterpret_cast<uint4*>(ktile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(ktile + K_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
+        }
+        if (QG) {
+          // mu = mean_k S[q,k] = Q[q,:] . Kbar (dagl.py:256 through the row-mean identity), fp64 partial over these columns
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (eb + i < ED) mu += (double)f[i] * (double)__ldg(kbar + eb + i);
+        } else {
           // column sums over this warp's 32 rows, then over the 4 warps below (Kbar = mean_k K).  Transposing butterfly:
           // every step halves the columns a lane carries and doubles the rows they cover (8+4+2+1+1 = 16 shuffles instead
           // of 16 x 5); fixed order, so the result is deterministic.  Lane l ends with column (l >> 1) & 15.
@@ -427,16 +405,25 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty + ab);
-      if (fused) {
+      if (QG) {
+        mu_s[egrp * EB_M + r] = mu;
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // the eight epilogue warps: both column groups of every row
+        if (egrp == 0) {
+          const size_t idx = ((size_t)img * eg.nqt + tile) * EB_M + r;
+          qo.thr4[idx * 4 + eh] = (float)(mu_s[r] + mu_s[EB_M + r]);   // the graph kernel adds the two output halves
+          if (eh == 0) {
+            qo.thr4[idx * 4 + 2] = valid ? __ldg(qo.gamma + orow) : 0.f;
+            qo.thr4[idx * 4 + 3] = valid ? __ldg(qo.beta + orow) : -1.f;   // rows past Nq: nothing is ever selected
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else {
         asm volatile("bar.sync 1, 256;" ::: "memory");              // the eight epilogue warps: csum_s complete
         if (egrp == 0 && r < ncols && e0 + r < ED)
           colsum[((size_t)img * eg.ntile + tile) * ED + e0 + r] =
               ((csum_s[r] + csum_s[EB_N0 + r]) + csum_s[2 * EB_N0 + r]) + csum_s[3 * EB_N0 + r];
         asm volatile("bar.sync 1, 256;" ::: "memory");              // ... and read before the next item overwrites it
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      if (lane == 0 && !fused) atomicMax(absmax_out + img * 4 + (QG ? 0 : 1), __float_as_uint(vmax));
       ++it;
     }
   }
@@ -450,36 +437,43 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
 // A operand [tap][hi|lo][2 k-chunks][128 rows][8 ch].  Queries are 1/16 of the pixels, so this (0.4 MB per tile) is cheap,
 // unlike unfolding the keys; it turns the query embedding (fc1 on the stride-4 unfold, dagl.py:216-221,248) into a dense
 // [Nq x 784] x [784 x 196] GEMM instead of a 7x7 convolution evaluated at every pixel of the query rows.
+// Source: the zero-padded fp16 hi / lo images of G written by the feature-map epilogue (the SAME padding of the stride-4
+// unfold, dagl.py:126-136, never reaches outside their 3-pixel border), so this is a pure gather of 16-byte chunks.
+// The first CTA row also writes the 48-bit validity masks of the graph kernel's key tiles (pure geometry).
 __global__ void __launch_bounds__(256)
-pack_qpatch_kernel(Geom g, EmbGeom eg, const float* __restrict__ G, const unsigned* __restrict__ absmax,
-                   uint8_t* __restrict__ qimg) {
+gather_qpatch_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi, const uint8_t* __restrict__ glo,
+                     uint8_t* __restrict__ qimg, unsigned long long* __restrict__ tilemask, int ntile_k) {
   pdl_prologue();
   const int qt = blockIdx.x / KS, ky = blockIdx.x % KS, img = blockIdx.y;      // one CTA per (query tile, tap row)
-  const float scale = pow2_scale_e(absmax[img * 4 + 3], 14);
+  if (blockIdx.x == 0) {
+    for (int t = threadIdx.x; t < ntile_k; t += 256) {
+      unsigned long long m = 0ull;
+      int kp = t * EB_KTILE, x = kp % eg.Wp;
+      for (int r = 0; r < EB_KTILE; ++r, ++kp) {
+        if (kp < eg.NkP && x < g.W) m |= 1ull << r;
+        if (++x == eg.Wp) x = 0;
+      }
+      tilemask[(size_t)img * ntile_k + t] = m;
+    }
+  }
   uint8_t* tile = qimg + ((size_t)img * eg.nqt + qt) * (size_t)(KK * EB_QA_BYTES);
-  const float* Gi = G + (size_t)img * CI * g.Nk;
+  const uint8_t* sh = ghi + (size_t)img * eg.NPG * 32;
+  const uint8_t* sl = glo + (size_t)img * eg.NPG * 32;
   for (int o = threadIdx.x; o < KS * 2 * EB_M; o += 256) {              // one 16-byte chunk: 8 channels of (tap, k-chunk, row)
     const int row = o % EB_M, kc = (o / EB_M) & 1, t = ky * KS + o / (2 * EB_M);
     const int q = qt * EB_M + row;
-    const int qy = q / g.nqx, qx = q % g.nqx;
-    const int y = qy * SQ - g.qpad_top + t / KS, x = qx * SQ - g.qpad_left + t % KS;
-    const bool inb = (q < g.Nq) && y >= 0 && y < g.H && x >= 0 && x < g.W;
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = 0.f, b = 0.f;
-      if (inb) {
-        a = __ldg(Gi + (size_t)(kc * 8 + 2 * j) * g.Nk + (size_t)y * g.W + x) * scale;
-        b = __ldg(Gi + (size_t)(kc * 8 + 2 * j + 1) * g.Nk + (size_t)y * g.W + x) * scale;
-      }
-      const __half h0 = __float2half_rn(a), h1 = __float2half_rn(b);
-      const __half l0 = __float2half_rn(a - __half2float(h0)), l1 = __float2half_rn(b - __half2float(h1));
-      hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
+    if (q < g.Nq) {
+      const int qy = q / g.nqx, qx = q % g.nqx;
+      const int y = qy * SQ - g.qpad_top + t / KS, x = qx * SQ - g.qpad_left + t % KS;     // in [-3, H+2] x [-3, W+2]
+      const size_t rec = (size_t)(y + PADK) * eg.Wp + (x + PADK);
+      const int c = kc ^ ((int)(rec >> 2) & 1);                        // undo the pre-applied SWIZZLE_32B
+      hv = __ldg(reinterpret_cast<const uint4*>(sh + rec * 32) + c);
+      lv = __ldg(reinterpret_cast<const uint4*>(sl + rec * 32) + c);
     }
     uint8_t* dst = tile + (size_t)t * EB_QA_BYTES + (size_t)(kc * EB_M + row) * 16;     // [kc][row] chunk order
-    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(dst + EB_QA_BYTES / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(dst) = hv;
+    *reinterpret_cast<uint4*>(dst + EB_QA_BYTES / 2) = lv;
   }
 }
 
@@ -489,8 +483,15 @@ static inline size_t align_up_e(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t packed_w_bytes();
 size_t embed_tc_workspace_bytes(const Geom& g) {
   const EmbGeom eg = emb_geom(g);
-  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) + (size_t)g.NH * embed_tc_packed_weights_bytes() +   // maps + packed weights
-         align_up_e((size_t)g.B * eg.nqt * KK * EB_QA_BYTES);                                            // query patch tiles
+  return 2 * align_up_e((size_t)g.B * eg.NPG * 32) +                       // fp16 hi / lo images of G (feature-map epilogue)
+         align_up_e((size_t)g.B * eg.nqt * KK * EB_QA_BYTES);              // query patch tiles
+}
+void embed_tc_g_buffers(const Geom& g, void* ws, uint8_t** ghi, uint8_t** glo, int* npg) {
+  const EmbGeom eg = emb_geom(g);
+  char* p = static_cast<char*>(ws);
+  *ghi = reinterpret_cast<uint8_t*>(p);
+  *glo = reinterpret_cast<uint8_t*>(p + align_up_e((size_t)g.B * eg.NPG * 32));
+  *npg = eg.NPG;
 }
 int embed_tc_num_tiles(const Geom& g) { return emb_geom(g).ntile; }
 
@@ -547,56 +548,56 @@ int launch_pack_fc_weights(const float* fc1_w, const float* fc1_b, const float* 
   return 0;
 }
 
-// Computes Q [B][Nq][196], K [B][Nk][196] (fp32) and the maxima of Q and K into absmax[B][4] (slots 0, 1);
-// absmax slot 3 (max |G|) must already be filled.  hw.packed[h] (nullable): weights packed by launch_pack_fc_weights.
-// With `ktiles` (and `colsum`) the key launch writes the graph kernel's fp16 hi|lo key tiles and the per-CTA column sums
-// directly (no fp32 K round trip through HBM, no separate pack pass); absmax slot 1 then holds an a-priori bound on K
-// (the fp16 scale) instead of the measured maximum, and K (fp32) is only written when `K` is non-null.
-int launch_embed_tc(const Geom& g, const float* G, const HeadWeights& hw, float* Q, float* K, unsigned* absmax, void* ws,
-                    size_t ws_bytes, uint8_t* ktiles, float* colsum, cudaStream_t st) {
+const float* embed_tc_fc_meta(const void* packed) {
+  return reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) + 2 * packed_w_bytes()) + 2;   // after wmax[2]
+}
+
+// Both embeddings, written straight into the graph kernel's operand tiles (EmbTargets): key tiles + column sums, then
+// Kbar = mean_k K, then query tiles + per-query threshold terms (mu partials need Kbar, hence the order).  The fp16 images
+// of G in `ws` were written by the feature-map epilogue.  hw.packed[h] is never null here.  Q / K (nullable): fp32 copies
+// for the debug entry.
+int launch_embed_tc(const Geom& g, const HeadWeights& hw, float* Q, float* K, const unsigned* absmax, void* ws, size_t ws_bytes,
+                    const float* gamma, const float* beta, const EmbTargets& out, cudaStream_t st) {
   const EmbGeom eg = emb_geom(g);
   if (ws_bytes < embed_tc_workspace_bytes(g)) {
     call_state().err = "embed (tc) workspace too small";
     return -3;
   }
-  char* p = static_cast<char*>(ws);
-  uint8_t* ghi = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
-  uint8_t* glo = reinterpret_cast<uint8_t*>(p); p += align_up_e((size_t)g.B * eg.NPG * 32);
-  HeadPtrs w1{}, w2{}, b1{}, b2{}, wmax1{}, wmax2{}, kmeta{};
+  uint8_t *ghi, *glo;
+  int npg;
+  embed_tc_g_buffers(g, ws, &ghi, &glo, &npg);
+  uint8_t* qimg = static_cast<uint8_t*>(ws) + 2 * align_up_e((size_t)g.B * eg.NPG * 32);
+  HeadPtrs w1{}, w2{}, b1{}, b2{}, wmax1{}, wmax2{};
   for (int h = 0; h < g.NH; ++h) {
     const uint8_t* packed = static_cast<const uint8_t*>(hw.packed[h]);
-    if (packed == nullptr) {
-      char* slot = p + (size_t)h * embed_tc_packed_weights_bytes();
-      if (int rc = launch_pack_fc_weights(hw.fc1_w[h], hw.fc1_b[h], hw.fc2_w[h], hw.fc2_b[h], slot, embed_tc_packed_weights_bytes(), st)) return rc;
-      packed = reinterpret_cast<const uint8_t*>(slot);
-    }
     const unsigned* wmax = reinterpret_cast<const unsigned*>(packed + 2 * packed_w_bytes());
     w1.p[h] = packed; w2.p[h] = packed + packed_w_bytes();
-    wmax1.p[h] = wmax + 0; wmax2.p[h] = wmax + 1; kmeta.p[h] = wmax + 2;
+    wmax1.p[h] = wmax + 0; wmax2.p[h] = wmax + 1;
     b1.p[h] = hw.fc1_b[h]; b2.p[h] = hw.fc2_b[h];
   }
-  DAGL_CUDA_OK(launch_pdl(pack_g_kernel, dim3((eg.NPG + 255) / 256, g.B), 256, 0, st, g, eg, G, absmax, ghi, glo, kmeta, ktiles ? 1 : 0));
-  DAGL_LAUNCH_CHECK();
-
-  uint8_t* qimg = reinterpret_cast<uint8_t*>(p) + (size_t)g.NH * embed_tc_packed_weights_bytes();   // after the (possibly unused) weight slots
   int dev = 0, sms = 148;
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // queries: gather the patches, then a dense GEMM against fc1
-  DAGL_CUDA_OK(launch_pdl(pack_qpatch_kernel, dim3(eg.nqt * KS, g.B), 256, 0, st, g, eg, G, absmax, qimg));
+  const int ntile_k = (eg.NkP + EB_KTILE - 1) / EB_KTILE;
+  // queries: gather the patches (+ key-tile validity masks)
+  DAGL_CUDA_OK(launch_pdl(gather_qpatch_kernel, dim3(eg.nqt * KS, g.B), 256, 0, st, g, eg, ghi, glo, qimg, out.tilemask, ntile_k));
   DAGL_LAUNCH_CHECK();
-  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMQ_TOTAL));
-  const int nwork_q = g.B * 2 * eg.nqt;                                                   // persistent: one CTA per SM
-  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, b1, absmax,
-                          wmax1, Q, absmax, nullptr, nullptr));
-  DAGL_LAUNCH_CHECK();
-  // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles when `ktiles` is given
+  // keys: implicit GEMM over the halo, written straight into the graph kernel's key tiles
   // (a two-tiles-per-weight-pass variant measured no faster: with one accumulator set per tile its MMA phase and its
   // epilogue run back to back)
+  const EmbQOut none{};
   const int nwork_k = g.B * 2 * eg.ntile;
   DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SM_TOTAL));
   DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<false>, nwork_k < sms ? nwork_k : sms, EB_THREADS, EB_SM_TOTAL, st, g, eg, ghi, glo, w2,
-                          b2, absmax, wmax2, K, absmax, ktiles, colsum));
+                          b2, absmax, wmax2, K, out.ktiles, out.colsum, none));
+  DAGL_LAUNCH_CHECK();
+  if (int rc = launch_kbar(g, out.colsum, eg.ntile, out.kbar, st)) return rc;
+  // queries: a dense GEMM of the gathered patches against fc1; epilogue = query tiles + threshold terms
+  const EmbQOut qo{out.thr4, out.kbar, gamma, beta};
+  DAGL_CUDA_OK(cudaFuncSetAttribute(embed_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMQ_TOTAL));
+  const int nwork_q = g.B * 2 * eg.nqt;                                                   // persistent: one CTA per SM
+  DAGL_CUDA_OK(launch_pdl(embed_tc_kernel<true>, nwork_q < sms ? nwork_q : sms, EB_THREADS, EB_SMQ_TOTAL, st, g, eg, qimg, nullptr, w1, b1, absmax,
+                          wmax1, Q, out.qtiles, nullptr, qo));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

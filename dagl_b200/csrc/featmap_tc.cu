@@ -39,8 +39,8 @@ static_assert(FT_SM_W % 1024 == 0, "weight image alignment");
 struct FtGeom { int Wp, NkP, ntile, NPG; };
 static FtGeom ft_geom(const Geom& g) {
   FtGeom e;
-  e.Wp = g.W + 2 * PADK;
-  e.NkP = (g.H - 1) * e.Wp + g.W;
+  e.Wp = (g.W + 2 * PADK + 7) & ~7;                 // the padded-flat pitch of embed_tc.cu / attend_tc.cu: pixel slot p of an
+  e.NkP = (g.H - 1) * e.Wp + g.W;                   // item maps to record p + 3 Wp + 3 of their zero-padded fp16 images
   e.ntile = (e.NkP + FT_M - 1) / FT_M;
   const int np = (g.H + 2 * PADK) * e.Wp;
   const int need = FT_M * e.ntile + 2 * PADK * e.Wp + FT_SEG_PIX + 8;
@@ -74,9 +74,28 @@ __global__ void absmax_img_kernel(const float* __restrict__ x, size_t n_per_img,
 // g weight [16][64][3][3], theta weight [16][64] -> per virtual tap (group, tap): [hi|lo][2 k-chunks][32 rows][8 ch] fp16,
 // rows 0..15 = g outputs, rows 16..31 = theta outputs (zero except at the centre tap); wmax[0] = max |w| (float bits).
 __global__ void __launch_bounds__(256)
-pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ th_w, uint8_t* __restrict__ out,
-                  unsigned* __restrict__ wmax) {
+pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ g_b, const float* __restrict__ th_w,
+                  const float* __restrict__ th_b, uint8_t* __restrict__ out, unsigned* __restrict__ wmax) {
   __shared__ float red[8];
+  // meta (floats wmax[1..4]): l1g = max_e sum |g_w[e]|, bg = max |g_b|, l1t, bt  ->  |G| <= max|b| * l1g + bg (a-priori
+  // bound: the fp16 scale of the G / theta images written by the feature-map epilogue, no pass over G needed)
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float l1g = 0.f, l1t = 0.f, bg = 0.f, bt = 0.f;
+    for (int e = 0; e < CI; ++e) {
+      float a = 0.f, t = 0.f;
+      for (int i = lane; i < FT_C * 9; i += 32) a += fabsf(__ldg(g_w + (size_t)e * FT_C * 9 + i));
+      for (int i = lane; i < FT_C; i += 32) t += fabsf(__ldg(th_w + (size_t)e * FT_C + i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+      l1g = fmaxf(l1g, a); l1t = fmaxf(l1t, t);
+      bg = fmaxf(bg, fabsf(__ldg(g_b + e))); bt = fmaxf(bt, fabsf(__ldg(th_b + e)));
+    }
+    if (lane == 0) {
+      float* meta = reinterpret_cast<float*>(wmax);
+      meta[1] = l1g * 1.0001f; meta[2] = bg; meta[3] = l1t * 1.0001f; meta[4] = bt;
+    }
+  }
   float m = 0.f;
   for (int i = threadIdx.x; i < CI * FT_C * 9; i += 256) m = fmaxf(m, fabsf(__ldg(g_w + i)));
   for (int i = threadIdx.x; i < CI * FT_C; i += 256) m = fmaxf(m, fabsf(__ldg(th_w + i)));
@@ -182,8 +201,17 @@ gamma_beta_heads_kernel(Geom g, const float* __restrict__ b, HeadPtrs thr_w, Hea
 // and the MMAs of the next.
 __global__ void __launch_bounds__(FT_THREADS, 1)
 featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs wpack, HeadPtrs g_b, HeadPtrs th_b,
-                  const unsigned* __restrict__ bmax, float* __restrict__ G, float* __restrict__ Th,
-                  unsigned* __restrict__ absmax /*[B][AMAX_STRIDE]*/) {
+                  const unsigned* __restrict__ bmax, float* __restrict__ G /*nullable: fp32 copies for the debug entry*/,
+                  float* __restrict__ Th, unsigned* __restrict__ absmax /*[B][AMAX_STRIDE]*/, HeadPtrs fcmeta,
+                  uint8_t* __restrict__ ghi, uint8_t* __restrict__ glo, int npg /*records per image in ghi / glo*/,
+                  uint8_t* __restrict__ thp, int np_t /*records per image in thp*/) {
+  // Epilogue outputs (what the embedding and graph kernels consume; nothing is re-packed by a later pass):
+  //   ghi / glo  zero-padded flat fp16 hi / lo images of G   [v][npg][16 ch], SWIZZLE_32B pre-applied   (embed_tc.cu)
+  //   thp        zero-padded flat fp16 image of theta          [v][np_t][16 ch], likewise                 (attend_tc.cu)
+  //   absmax[v]  the fp16 scales of everything downstream as a-priori bounds: |G|, |theta| from max|b| and the L1 norms of
+  //              the filters, |Q|, |K| from the bound on |G| and the L1 norms of fc1 / fc2 (fcmeta).  A bound that is loose
+  //              by a factor 2^k costs nothing for hi+lo split operands as long as k < ~17 (fp16 keeps 11 bits per part at
+  //              every exponent above 2^-14: the absolute error floor stays below 2^-22 of the largest value).
   // Work item w (head-major: a persistent CTA re-loads the 72 KB of packed weights at most NH times):
   //   head = w / (nreal * ntile), real image = (w / ntile) % nreal, tile = w % ntile; virtual image = real * NH + head.
   // wpack.p[h] = packed g/theta weights of head h, followed (256-aligned) by wmax (float bits of max |w|).
@@ -296,10 +324,22 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
       const int p = (w % eg.ntile) * FT_M + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
       const bool valid = (p < eg.NkP) && (x < g.W);
-      const unsigned wmax = *reinterpret_cast<const unsigned*>(static_cast<const uint8_t*>(wpack.p[head]) + WMAX_OFF);
+      const float* meta = reinterpret_cast<const float*>(static_cast<const uint8_t*>(wpack.p[head]) + WMAX_OFF);
+      const unsigned wmax = __float_as_uint(meta[0]);
+      const float bmaxf = __uint_as_float(bmax[real]);
+      const float bound_g = bmaxf * meta[1] + meta[2], bound_t = bmaxf * meta[3] + meta[4];
+      const float sg = pow2_scale_f(__float_as_uint(bound_g), 14), st = pow2_scale_f(__float_as_uint(bound_t), 12);
       const float inv = 1.f / (pow2_scale_f(wmax, 14) * pow2_scale_f(bmax[real], 14));
       const float* gbias = static_cast<const float*>(g_b.p[head]);
       const float* tbias = static_cast<const float*>(th_b.p[head]);
+      const int tile = w % eg.ntile;
+      if (tile == 0 && r == 0) {                            // one thread per virtual image: the scales of everything downstream
+        const float* fm = static_cast<const float*>(fcmeta.p[head]);       // [l1 fc1, max|b1|, l1 fc2, max|b2|]
+        absmax[img * AMAX_STRIDE + AMAX_G] = __float_as_uint(bound_g);
+        absmax[img * AMAX_STRIDE + AMAX_THETA] = __float_as_uint(bound_t);
+        absmax[img * AMAX_STRIDE + AMAX_Q] = __float_as_uint(bound_g * fm[0] + fm[1]);
+        absmax[img * AMAX_STRIDE + AMAX_K] = __float_as_uint(bound_g * fm[2] + fm[3]);
+      }
       const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16) + ab * 64;
       mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
@@ -312,29 +352,61 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty + ab);          // the accumulator set is in registers now
-      float gmax = 0.f, tmax = 0.f;
+      // slot p of the padded-flat enumeration is record rec of the zero-padded images; dummy slots (x >= W, p >= NkP) are the
+      // right / left zero borders of the rows, so every record between the head and the tail region is written here
+      const size_t rec = (size_t)p + 3 * eg.Wp + 3;
+      uint32_t gh[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, gl[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, th[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      if (valid) {
+        float og[CI], ot[CI];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {                 // 0: g outputs, 1: theta outputs
-        if (valid) {
-          float* dst = (half ? Th : G) + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
-          const float* bias = half ? tbias : gbias;
+        for (int c = 0; c < CI; ++c) {
+          og[c] = (__uint_as_float(v[0][c]) + __uint_as_float(vc[0][c])) * inv + __ldg(gbias + c);
+          ot[c] = (__uint_as_float(v[1][c]) + __uint_as_float(vc[1][c])) * inv + __ldg(tbias + c);
+        }
+        if (G != nullptr) {                                  // debug entry: fp32 copies (dagl_ce_workspace_view)
+          float* dg = G + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
+          float* dt = Th + (size_t)img * CI * g.Nk + (size_t)y * g.W + x;
 #pragma unroll
-          for (int c = 0; c < CI; ++c) {
-            const float o = (__uint_as_float(v[half][c]) + __uint_as_float(vc[half][c])) * inv + __ldg(bias + c);
-            dst[(size_t)c * g.Nk] = o;
-            if (half) tmax = fmaxf(tmax, fabsf(o)); else gmax = fmaxf(gmax, fabsf(o));
-          }
+          for (int c = 0; c < CI; ++c) { dg[(size_t)c * g.Nk] = og[c]; dt[(size_t)c * g.Nk] = ot[c]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a0 = og[2 * j] * sg, a1 = og[2 * j + 1] * sg;
+          const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+          const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+          gh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          gl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          const __half t0 = __float2half_rn(ot[2 * j] * st), t1 = __float2half_rn(ot[2 * j + 1] * st);
+          th[j] = (uint32_t)__half_as_ushort(t0) | ((uint32_t)__half_as_ushort(t1) << 16);
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-        gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+      {
+        const int sw = (int)(rec >> 2) & 1;                  // SWIZZLE_32B pre-applied: the 16-byte halves swap when (record & 4)
+        uint4* dh = reinterpret_cast<uint4*>(ghi + ((size_t)img * npg + rec) * 32);
+        uint4* dl = reinterpret_cast<uint4*>(glo + ((size_t)img * npg + rec) * 32);
+        uint4* dt = reinterpret_cast<uint4*>(thp + ((size_t)img * np_t + rec) * 32);
+        dh[sw] = make_uint4(gh[0], gh[1], gh[2], gh[3]); dh[sw ^ 1] = make_uint4(gh[4], gh[5], gh[6], gh[7]);
+        dl[sw] = make_uint4(gl[0], gl[1], gl[2], gl[3]); dl[sw ^ 1] = make_uint4(gl[4], gl[5], gl[6], gl[7]);
+        dt[sw] = make_uint4(th[0], th[1], th[2], th[3]); dt[sw ^ 1] = make_uint4(th[4], th[5], th[6], th[7]);
       }
-      if (lane == 0 && absmax != nullptr) {
-        atomicMax(absmax + img * AMAX_STRIDE + AMAX_THETA, __float_as_uint(tmax));
-        atomicMax(absmax + img * AMAX_STRIDE + AMAX_G, __float_as_uint(gmax));
-      }
+      // head (records before the first slot) and tail (after the last slot) of the padded images are zero borders too:
+      // written by the first / last item of the virtual image
+      auto zero_range = [&](size_t a0, size_t end_g, size_t end_t) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = a0 + r; i < (end_g > end_t ? end_g : end_t); i += FT_M) {
+          if (i < end_g) {
+            uint4* dh = reinterpret_cast<uint4*>(ghi + ((size_t)img * npg + i) * 32);
+            uint4* dl = reinterpret_cast<uint4*>(glo + ((size_t)img * npg + i) * 32);
+            dh[0] = z; dh[1] = z; dl[0] = z; dl[1] = z;
+          }
+          if (i < end_t) {
+            uint4* dt = reinterpret_cast<uint4*>(thp + ((size_t)img * np_t + i) * 32);
+            dt[0] = z; dt[1] = z;
+          }
+        }
+      };
+      if (tile == 0) zero_range(0, (size_t)3 * eg.Wp + 3, (size_t)3 * eg.Wp + 3);
+      if (tile == eg.ntile - 1) zero_range((size_t)eg.ntile * FT_M + 3 * eg.Wp + 3, (size_t)npg, (size_t)np_t);
     }
   }
   tc_fence_before();
@@ -351,14 +423,14 @@ size_t feature_maps_tc_workspace_bytes(const Geom& g) {
   if (!feature_maps_tc_supported(g)) return 0;
   const FtGeom eg = ft_geom(g);
   const size_t nreal = (size_t)(g.B / g.NH);
-  return align_up_f(nreal * FT_GROUPS * 2 * eg.NPG * 32) + align_up_f(nreal * sizeof(unsigned)) +
-         (size_t)g.NH * feature_maps_tc_packed_weights_bytes();
+  return align_up_f(nreal * FT_GROUPS * 2 * eg.NPG * 32) + align_up_f(nreal * sizeof(unsigned));
 }
 
-// packed g/theta weights | wmax (one unsigned)
+// packed g/theta weights | wmax (float bits), then the bound meta [l1g, bg, l1t, bt] (pack_featw_kernel)
 size_t feature_maps_tc_packed_weights_bytes() { return align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES) + align_up_f(64); }
 
-int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* packed, size_t packed_bytes, cudaStream_t st) {
+int launch_pack_feat_weights(int C, const float* g_w, const float* g_b, const float* th_w, const float* th_b, void* packed,
+                             size_t packed_bytes, cudaStream_t st) {
   if (C != FT_C) return 0;                                   // fp32 CUDA-core feature kernel: nothing to pack
   if (packed_bytes < feature_maps_tc_packed_weights_bytes()) {
     call_state().err = "packed-weights buffer too small";
@@ -366,16 +438,19 @@ int launch_pack_feat_weights(int C, const float* g_w, const float* th_w, void* p
   }
   uint8_t* wpack = static_cast<uint8_t*>(packed);
   unsigned* wmax = reinterpret_cast<unsigned*>(wpack + align_up_f((size_t)FT_VTAPS * FT_WTAP_BYTES));
-  pack_featw_kernel<<<1, 256, 0, st>>>(g_w, th_w, wpack, wmax);
+  pack_featw_kernel<<<1, 256, 0, st>>>(g_w, g_b, th_w, th_b, wpack, wmax);
   DAGL_LAUNCH_CHECK();
   return 0;
 }
 
-// hw.packed[h] (nullable): weights of head h packed by dagl_ce_pack_weights_f32 (the g/theta image follows the fc image).
-// gamma / beta (dagl.py:213-215) are computed inside the launch that repacks b.  `reuse_b`: the repacked input (and its
-// maximum) left in `ws` by the previous call is still valid (same b), so only the gamma / beta part of that launch runs.
+// hw.packed[h]: weights of head h packed by dagl_ce_pack_weights_f32 (the g/theta image follows the fc image; never null
+// here: forward_impl packs into the workspace when the caller did not).  gamma / beta (dagl.py:213-215) are computed inside
+// the launch that repacks b.  `reuse_b`: the repacked input (and its maximum) left in `ws` by the previous call is still
+// valid (same b), so only the gamma / beta part of that launch runs.  `out`: where the epilogue writes the fp16 images of G
+// and theta that the embedding and graph kernels consume.  G / Th (nullable): fp32 copies for the debug entry.
 int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw, float* G, float* Th, float* gamma,
-                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, cudaStream_t st) {
+                           float* beta, unsigned* absmax, void* ws, size_t ws_bytes, bool reuse_b, const FeatTargets& out,
+                           cudaStream_t st) {
   const FtGeom eg = ft_geom(g);
   if (!feature_maps_tc_supported(g) || ws_bytes < feature_maps_tc_workspace_bytes(g)) {
     call_state().err = "feature maps (tc): unsupported channel count or workspace too small";
@@ -385,15 +460,10 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw,
   char* p = static_cast<char*>(ws);
   uint8_t* bimg = reinterpret_cast<uint8_t*>(p); p += align_up_f((size_t)nreal * FT_GROUPS * 2 * eg.NPG * 32);
   unsigned* bmax = reinterpret_cast<unsigned*>(p); p += align_up_f((size_t)nreal * sizeof(unsigned));
-  HeadPtrs wpack{}, gb{}, tb{}, thr_w{}, thr_b{}, bias_w{}, bias_b{};
+  HeadPtrs wpack{}, gb{}, tb{}, thr_w{}, thr_b{}, bias_w{}, bias_b{}, fcmeta{};
   for (int h = 0; h < g.NH; ++h) {
-    if (hw.packed[h] != nullptr) {
-      wpack.p[h] = static_cast<const char*>(hw.packed[h]) + embed_tc_packed_weights_bytes();
-    } else {
-      char* slot = p + (size_t)h * feature_maps_tc_packed_weights_bytes();
-      if (int rc = launch_pack_feat_weights(g.C, hw.g_w[h], hw.th_w[h], slot, feature_maps_tc_packed_weights_bytes(), st)) return rc;
-      wpack.p[h] = slot;
-    }
+    wpack.p[h] = static_cast<const char*>(hw.packed[h]) + embed_tc_packed_weights_bytes();
+    fcmeta.p[h] = embed_tc_fc_meta(hw.packed[h]);
     gb.p[h] = hw.g_b[h]; tb.p[h] = hw.th_b[h];
     thr_w.p[h] = hw.thr_w[h]; thr_b.p[h] = hw.thr_b[h]; bias_w.p[h] = hw.bias_w[h]; bias_b.p[h] = hw.bias_b[h];
   }
@@ -430,7 +500,8 @@ int launch_feature_maps_tc(const Geom& g, const float* b, const HeadWeights& hw,
   DAGL_CUDA_OK(cudaGetDevice(&dev));
   DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int nwork = g.B * eg.ntile;
-  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(nwork < sms ? nwork : sms), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, gb, tb, bmax, G, Th, absmax));
+  DAGL_CUDA_OK(launch_pdl(featmap_tc_kernel, dim3(nwork < sms ? nwork : sms), FT_THREADS, FT_SM_TOTAL, st, g, eg, bimg, wpack, gb, tb, bmax, G, Th,
+                          absmax, fcmeta, out.ghi, out.glo, out.npg, out.thp, out.np_t));
   DAGL_LAUNCH_CHECK();
   return 0;
 }

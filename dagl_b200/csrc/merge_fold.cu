@@ -96,6 +96,7 @@ fold_partials_kernel(Geom g, int nsplit, int nparts, const float* __restrict__ O
       const int sh = (py - (qy * SQ - PADK)) * KS + (px - (qx * SQ - PADK));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       float L = 0.f;
+#pragma unroll 4
       for (int s = 0; s < nsplit; ++s) {
         const size_t row = ((size_t)img * nsplit + s) * g.Nq + q;
         const float4 v = __ldg(reinterpret_cast<const float4*>(Opart + row * VD + sh * CI) + c4);

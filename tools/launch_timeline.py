@@ -7,10 +7,10 @@ import dagl_b200
 from dagl_b200 import _lib
 from oracle import ce_oracle as O
 
-NAMES_TC = ["absmax_img", "pack_b+gamma_beta", "featmap_tc", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar", "pack_tiles(Q)",
-            "pack_theta", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
-NAMES_STAGE = ["absmax_img", "gamma_beta_heads", "pack_b", "featmap_tc", "pack_g", "pack_qpatch", "embed_tc<Q gemm>", "embed_tc<K>", "kbar",
-               "pack_tiles(Q)", "pack_theta", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
+NAMES_TC = ["absmax_img", "pack_b+gamma_beta", "featmap_tc(+G/theta img)", "gather_qpatch", "embed_tc<K>(+tiles)", "kbar",
+            "embed_tc<Q>(+tiles,thr)", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
+NAMES_STAGE = ["absmax_img", "gamma_beta_heads", "pack_b", "featmap_tc(+G/theta img)", "gather_qpatch", "embed_tc<K>(+tiles)", "kbar",
+               "embed_tc<Q>(+tiles,thr)", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
 HEADS = int(os.environ.get("HEADS", "1"))        # > 1: one CES stage call (heads as a grid dimension)
 dev = torch.device("cuda:0")
 H = W = int(os.environ.get("HW", "256"))
@@ -45,6 +45,6 @@ names = (NAMES_TC if len(acc) == len(NAMES_TC) and HEADS == 1 else NAMES_STAGE i
          [f"launch {i}" for i in range(len(acc))])
 tot = 0.0
 for nm, t in zip(names, acc):
-    print(f"{nm:16s} {t / reps:8.1f} us")
+    print(f"{nm:26s} {t / reps:8.1f} us")
     tot += t / reps
 print(f"{'TOTAL':16s} {tot:8.1f} us   ({B}x64x{H}x{W}, heads {HEADS}, impl {ce.last_impl}, L2 flushed before each forward, mean of {reps})")
