@@ -28,7 +28,7 @@ class DaglCEWeights(C.Structure):
         "thr_w", "thr_b", "bias_w", "bias_b")] + [
         ("in_channels", C.c_int32), ("inter_channels", C.c_int32), ("ksize", C.c_int32),
         ("stride_q", C.c_int32), ("stride_k", C.c_int32), ("softmax_scale", C.c_float),
-        ("packed_fc", C.c_void_p)]
+        ("packed_fc", C.c_void_p), ("legacy_topk", C.c_int32)]
 
 
 _lib = None
@@ -85,7 +85,7 @@ def lib() -> C.CDLL:
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32
     L.dagl_profile_read.argtypes = [C.POINTER(C.c_float), i32]
-    if L.dagl_abi_version() != 3:
+    if L.dagl_abi_version() != 4:
         raise RuntimeError("libdagl_b200.so ABI version mismatch")
     _lib = L
     return L

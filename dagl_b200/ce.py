@@ -55,7 +55,7 @@ class CE(nn.Module):
 
     def __init__(self, ksize=7, stride_1=4, stride_2=1, softmax_scale=10, shape=64, p_len=64, in_channels=64,
                  inter_channels=16, use_multiple_size=False, use_topk=False, add_SE=False, num_edge=50,
-                 impl: str = "auto"):
+                 impl: str = "auto", legacy_topk: int = 0):
         super().__init__()
         self.ksize = ksize
         self.shape = shape
@@ -70,6 +70,10 @@ class CE(nn.Module):
         self.add_SE = add_SE
         self.num_edge = num_edge
         self.impl = impl
+        # Opt-in extension, NOT reference-compatible behaviour: the shipping reference stores use_topk / num_edge and never
+        # reads them, and so does this module.  legacy_topk = k > 0 selects the neighbour rule of the reference's legacy
+        # fixed-top-k variant (GReccR2b_3mh_1-checkpoint.py:243-250) instead of the adaptive threshold.
+        self.legacy_topk = int(legacy_topk)
         # Parameter containers only: the convolutions/linears below are never
         # *called*; the CUDA kernels read their weights directly.
         self.g = nn.Conv2d(in_channels, inter_channels, kernel_size=3, stride=1, padding=1)
@@ -108,7 +112,8 @@ class CE(nn.Module):
             thr_w=ptr(self.thr_conv.weight), thr_b=ptr(self.thr_conv.bias),
             bias_w=ptr(self.bias_conv.weight), bias_b=ptr(self.bias_conv.bias),
             in_channels=self.in_channels, inter_channels=self.inter_channels, ksize=self.ksize,
-            stride_q=self.stride_1, stride_k=self.stride_2, softmax_scale=float(self.softmax_scale))
+            stride_q=self.stride_1, stride_k=self.stride_2, softmax_scale=float(self.softmax_scale),
+            legacy_topk=self.legacy_topk)
         return w, keep
 
     def _packed_fc(self, device: torch.device) -> Optional[int]:
@@ -155,6 +160,8 @@ class CE(nn.Module):
             raise RuntimeError("dagl_b200.CE has no CPU path: input must be a CUDA tensor "
                                "(use forward_host for pinned host buffers)")
         if self._needs_grad(b):
+            if self.legacy_topk:
+                raise RuntimeError("legacy_topk is an inference-only mode (the backward implements the shipping CE)")
             from .autograd import CEFunction
             return CEFunction.apply(self, b, *self._grad_params())
         return self._forward_cuda(b)

@@ -272,28 +272,66 @@ __constant__ PvGroup c_groups[2][4] = {
 // is < 1 log2 unit for the trained heads (logits <= 140), but for logits of several thousand units (random-init networks
 // a few stages deep, rgb_range = 255 models, diverging training) every fp16 P would drift into the subnormal range and
 // finally flush to zero.  Query tiles with a row whose possible overshoot exceeds RM_REFINE_LOG2 units get a second,
-// EXACT pass (rowmax_tc_kernel<true>): the same three split-fp16 MMA terms in the same order as the graph kernel, so the
+// EXACT pass (rowmax_tc_kernel<1>): the same three split-fp16 MMA terms in the same order as the graph kernel, so the
 // scores are the very values the softmax will see, and the row maximum of the LOGIT is stored in smax2.  With it the row
 // maximum lands on 2^12 exactly, whatever the magnitude.
 // ---------------------------------------------------------------------------------------------
+constexpr int TOPK_MAX = 64;                                 // legacy fixed-top-k variant: at most this many edges per query
 constexpr float RM_INFL = 1.f + 1.25f / 1024.f;
 constexpr float RM_REFINE_LOG2 = 12.f;
 
-__device__ __forceinline__ float row_logit_log2(float s, float tA, float tB, float sm_scale_log2) {
+// The softmax logit of dagl.py:256-260, z = c * S * relu(S - T) (`topk` == 0), or of the legacy fixed-top-k variant
+// (GReccR2b_3mh_1-checkpoint.py:243-250), z = c * S * [S among the row's k largest] with the k-th largest score folded into
+// T (`topk` != 0); both are monotone in S >= 0.
+__device__ __forceinline__ float logit_factor(float s, float rl, int topk) { return topk ? (rl != 0.f ? s : 0.f) : s * rl; }
+__device__ __forceinline__ float row_logit_log2(float s, float tA, float tB, float sm_scale_log2, int topk) {
   const float rl = fmaxf((s - tA) + tB, 0.f);
-  return (s * rl) * sm_scale_log2;
+  return logit_factor(s, rl, topk) * sm_scale_log2;
 }
-__device__ __forceinline__ bool row_needs_refine(float s_hi /*unscaled Qh.Kh maximum*/, float tA, float tB, float sm_scale_log2) {
-  return row_logit_log2(s_hi * RM_INFL, tA, tB, sm_scale_log2) - row_logit_log2(s_hi * (2.f - RM_INFL), tA, tB, sm_scale_log2) >
+__device__ __forceinline__ bool row_needs_refine(float s_hi /*unscaled Qh.Kh maximum*/, float tA, float tB, float sm_scale_log2, int topk) {
+  return row_logit_log2(s_hi * RM_INFL, tA, tB, sm_scale_log2, topk) - row_logit_log2(s_hi * (2.f - RM_INFL), tA, tB, sm_scale_log2, topk) >
          RM_REFINE_LOG2;
 }
 // smax2_bits != 0: exact maximum of the logit (log2 units) from the exact pass
 __device__ __forceinline__ float row_softmax_ref(unsigned smax_bits, unsigned smax2_bits, float inv_s, float tA, float tB,
-                                                 float sm_scale_log2) {
+                                                 float sm_scale_log2, int topk) {
   // (1 + 2^-22): the stored maximum is itself rounded (half an ulp: 4 log2 units at logits of 1e8), and 2^(12 + 4) would
   // overflow fp16; two to four ulps of head-room keep P <= 2^12 at every magnitude
   if (smax2_bits != 0u) return __uint_as_float(smax2_bits) * (1.f + 1.f / 4194304.f) - 12.f;
-  return row_logit_log2(__uint_as_float(smax_bits) * inv_s * RM_INFL, tA, tB, sm_scale_log2) - 12.f;
+  return row_logit_log2(__uint_as_float(smax_bits) * inv_s * RM_INFL, tA, tB, sm_scale_log2, topk) - 12.f;
+}
+
+// Legacy fixed-top-k variant: per query row, the k-th largest score over all key splits becomes the selection threshold.
+// thr4 = (T, 0, 1, 0) makes the graph kernels' relu(S - T) positive exactly for S >= tau (T = the float below tau); rows
+// with fewer than k valid keys select everything.  Ties AT the k-th value are all kept (torch.topk keeps an arbitrary
+// subset of them).
+__global__ void topk_merge_kernel(Geom g, TcGeom tg, int nlists, int k, const float* __restrict__ lists,
+                                  const unsigned* __restrict__ absmax, float4* __restrict__ thr4) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.B * tg.nqt * TC_BM) return;
+  const int img = i / (tg.nqt * TC_BM), q = i % (tg.nqt * TC_BM);
+  if (q >= g.Nq) { thr4[i] = make_float4(0.f, 0.f, 0.f, -1.f); return; }
+  const float inv_s = 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
+  const float* src = lists + (size_t)i * nlists * TOPK_MAX;
+  float sel[TOPK_MAX];
+  int nsel = 0, imin = 0;
+  float vmin = 0.f;
+  for (int j = 0; j < nlists * TOPK_MAX; ++j) {
+    const float x = src[j];
+    if (x < 0.f) continue;                                   // unused entry (scores are >= 0)
+    if (nsel < k) {
+      sel[nsel++] = x;
+      if (nsel == k) { vmin = sel[0]; imin = 0; for (int u = 1; u < k; ++u) if (sel[u] < vmin) { vmin = sel[u]; imin = u; } }
+    } else if (x > vmin) {
+      sel[imin] = x;
+      vmin = sel[0]; imin = 0;
+      for (int u = 1; u < k; ++u) if (sel[u] < vmin) { vmin = sel[u]; imin = u; }
+    }
+  }
+  float T = -1.f;                                            // fewer than k valid keys: every key is selected (S >= 0 > T)
+  if (nsel == k) T = nextafterf(vmin * inv_s, -INFINITY);
+  thr4[i] = make_float4(T, 0.f, 1.f, 0.f);
 }
 
 // =============================================================================================
@@ -329,13 +367,17 @@ constexpr int RM_DCOLS = RM_QT * TC_BN;                     // 96
 //   tile per CTA, the full 3-term score Ql.Kh + Qh.Kl + Qh.Kh with the MMA sequence of the graph kernels, and
 //   smax2[row] = max over the keys of the LOGIT c * S * relu(S - T) in log2 units (what the softmax exponent will be).
 //   TMEM: Qh [0,104) | Ql [104,208) | D0 [208,256) | D1 [304,352) | D2 [400,448)
-template <bool EXACT>
+// MODE 2 (legacy fixed-top-k variant only): the exact scores again, but instead of the row maximum every row keeps its
+//   `topk` largest VALID scores (scaled units) of this CTA's key range in a small per-thread selection buffer and writes
+//   them to lists[row][split][TOPK_MAX] (unused entries -1); topk_merge_kernel turns them into the per-row threshold.
+template <int MODE>
 __global__ void __launch_bounds__(RM_THREADS, 1)
 rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __restrict__ Kp, int nsplit,
                  int qt_base, int qt_end, unsigned* __restrict__ smax, const float4* __restrict__ thr4,
-                 const unsigned* __restrict__ absmax, float sm_scale_log2,
-                 unsigned* __restrict__ smax2) {
+                 const unsigned* __restrict__ absmax, float sm_scale_log2, int topk,
+                 unsigned* __restrict__ smax2, const unsigned long long* __restrict__ tilemask, float* __restrict__ lists) {
   pdl_prologue();
+  constexpr bool EXACT = MODE != 0;
   constexpr int QT = EXACT ? 1 : RM_QT;
   constexpr int KST = EXACT ? RMX_KSTAGES : RM_KSTAGES;
   constexpr int KBYTES = EXACT ? K_TILE_BYTES : K_HALF_BYTES;
@@ -356,13 +398,13 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
   const int nsteps = t_end - t_begin;                       // one key tile per step
   const float inv_s = EXACT ? 1.f / (pow2_scale(absmax[img * AMAX_STRIDE + AMAX_Q], 14) * pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14))
                             : 1.f;
-  if (EXACT) {
+  if (MODE == 1) {
     // does any row of this query tile need the exact maximum?  (block-uniform decision, before anything is allocated)
     bool flag = false;
     if (tid < TC_BM) {
       const size_t qi = ((size_t)img * tg.nqt + qt0) * TC_BM + tid;
       const float4 t4 = __ldg(thr4 + qi);
-      flag = row_needs_refine(__uint_as_float(__ldg(smax + qi)) * inv_s, (t4.x + t4.y) * t4.z, t4.w, sm_scale_log2);
+      flag = row_needs_refine(__uint_as_float(__ldg(smax + qi)) * inv_s, (t4.x + t4.y) * t4.z, t4.w, sm_scale_log2, topk);
     }
     if (!__syncthreads_or(flag ? 1 : 0)) return;
   }
@@ -455,9 +497,12 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
     tc_fence_before();
     mbar_arrive(q_ready);
     const size_t qidx = ((size_t)img * tg.nqt + qt0) * TC_BM + row;
-    const float4 t4 = EXACT ? __ldg(thr4 + qidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 t4 = MODE == 1 ? __ldg(thr4 + qidx) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float tA = (t4.x + t4.y) * t4.z, tB = t4.w;             // T = mu * gamma - beta (dagl.py:256), mu from two column halves
     float m[RM_QT][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};      // four chains per row: a single one is latency-bound
+    float sel[MODE == 2 ? TOPK_MAX : 1];                                   // MODE 2: the row's largest scores so far (unordered)
+    int nsel = 0, imin = 0;
+    float vmin = 0.f;
     for (int st = 0; st < nsteps; ++st) {
       const int db = st % RM_DBUF;
       mbar_wait(d_full + db, (uint32_t)(st / RM_DBUF) & 1u);
@@ -474,11 +519,26 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
           for (int i = 0; i < 16; ++i) v[c0 + i] = t16[i];
         }
         tmem_wait_ld();
-        if (EXACT) {
+        if (MODE == 2) {
+          const unsigned long long vb = __ldg(tilemask + (size_t)img * tg.NT + t_begin + st);
+#pragma unroll 1
+          for (int i = 0; i < TC_BN; ++i) {
+            if (!((vb >> i) & 1ull)) continue;                             // dummy key slot
+            const float x = __uint_as_float(v[i]);
+            if (nsel < topk) {
+              sel[nsel++] = x;
+              if (nsel == topk) { vmin = sel[0]; imin = 0; for (int j = 1; j < topk; ++j) if (sel[j] < vmin) { vmin = sel[j]; imin = j; } }
+            } else if (x > vmin) {
+              sel[imin] = x;
+              vmin = sel[0]; imin = 0;
+              for (int j = 1; j < topk; ++j) if (sel[j] < vmin) { vmin = sel[j]; imin = j; }
+            }
+          }
+        } else if (EXACT) {
           // dummy key slots are zero rows: S = 0, logit 0 <= the maximum (logits are >= 0)
 #pragma unroll
           for (int i = 0; i < TC_BN; ++i)
-            m[qi][i & 3] = fmaxf(m[qi][i & 3], row_logit_log2(__uint_as_float(v[i]) * inv_s, tA, tB, sm_scale_log2));
+            m[qi][i & 3] = fmaxf(m[qi][i & 3], row_logit_log2(__uint_as_float(v[i]) * inv_s, tA, tB, sm_scale_log2, topk));
         } else {
 #pragma unroll
           for (int i = 0; i < TC_BN; ++i) m[qi][i & 3] = fmaxf(m[qi][i & 3], __uint_as_float(v[i]));
@@ -488,11 +548,16 @@ rowmax_tc_kernel(TcGeom tg, const uint8_t* __restrict__ Qp, const uint8_t* __res
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty + db);
     }
+    if (MODE == 2) {
+      float* dst = lists + ((((size_t)img * tg.nqt + qt0) * TC_BM + row) * gridDim.y + split) * TOPK_MAX;
+      for (int j = 0; j < TOPK_MAX; ++j) dst[j] = j < nsel ? sel[j] : -1.f;
+    } else {
 #pragma unroll
-    for (int qi = 0; qi < QT; ++qi)
-      if (qi < nq_here)
-        atomicMax((EXACT ? smax2 : smax) + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row,
-                  __float_as_uint(fmaxf(fmaxf(m[qi][0], m[qi][1]), fmaxf(m[qi][2], m[qi][3]))));
+      for (int qi = 0; qi < QT; ++qi)
+        if (qi < nq_here)
+          atomicMax((EXACT ? smax2 : smax) + ((size_t)img * tg.nqt + qt0 + qi) * TC_BM + row,
+                    __float_as_uint(fmaxf(fmaxf(m[qi][0], m[qi][1]), fmaxf(m[qi][2], m[qi][3]))));
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -516,7 +581,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float4* __restrict__ thr4 /*per query row: mu partials (x, y), gamma, beta*/,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
-                  float sm_scale_log2,
+                  float sm_scale_log2, int topk,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   pdl_prologue();
@@ -720,7 +785,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     // fixed softmax reference: logit of an upper bound of the row maximum, minus 12: P is stored as fp16, so the row
     // maximum is placed near 2^12 (fp16 max is 2^16) to keep the long tail of small weights (which carries real mass in
     // dense rows) out of the fp16 subnormal range
-    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2);
+    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2, topk);
     float l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
@@ -758,7 +823,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
           for (int u = 0; u < 2; ++u) {
             const float sc = sv[k + u] * inv_s;             // exact: inv_s is a power of two
             const float rl = fmaxf((sc - tA) + tB, 0.f);    // relu(S - mu*gamma + beta), dagl.py:256
-            const float pe = ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref));
+            const float pe = ex2_approx(fmaf(logit_factor(sc, rl, topk), sm_scale_log2, neg_ref));
             p[u] = (rl != 0.f) ? pe : 0.f;                  // numerator: neighbours only (mask_b, dagl.py:257)
             if (rl == 0.f) psum += pe;                      // denominator: every key ...
           }
@@ -777,7 +842,7 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
             const float sc = sv[k + u] * inv_s;
             const float rl = fmaxf((sc - tA) + tB, 0.f);
             const bool valid = (vbits >> (k + u)) & 1u;
-            const float pe = valid ? ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref)) : 0.f;   // dummy key slots contribute nothing
+            const float pe = valid ? ex2_approx(fmaf(logit_factor(sc, rl, topk), sm_scale_log2, neg_ref)) : 0.f;   // dummy key slots contribute nothing
             const bool nb = valid && (rl != 0.f);
             if (nb) mk |= 1u << (k + u);
             p[u] = nb ? pe : 0.f;
@@ -924,7 +989,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const uint8_t* __restrict__ Thp, const unsigned long long* __restrict__ tilemask,
                   const float4* __restrict__ thr4 /*per query row: mu partials (x, y), gamma, beta*/,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
-                  float sm_scale_log2,
+                  float sm_scale_log2, int topk,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][Nq]: summed over the cluster*/,
                   uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
   pdl_prologue();
@@ -1244,7 +1309,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                                pow2_scale(absmax[img * AMAX_STRIDE + AMAX_K], 14));
     const int q = qt * TC_BM + row;
     const bool qvalid = q < g.Nq;
-    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2);
+    const float ref = row_softmax_ref(__ldg(smax + qidx), __ldg(smax2 + qidx), inv_s, tA, tB, sm_scale_log2, topk);
     float l_run = 0.f;
     int cnt = 0;
     const int nwords = (g.Nk + 31) / 32;
@@ -1289,7 +1354,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
           for (int u = 0; u < 2; ++u) {
             const float sc = sv[k + u] * inv_s;
             const float rl = fmaxf((sc - tA) + tB, 0.f);
-            const float pe = ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref));
+            const float pe = ex2_approx(fmaf(logit_factor(sc, rl, topk), sm_scale_log2, neg_ref));
             p[u] = (rl != 0.f) ? pe : 0.f;
             if (rl == 0.f) psum += pe;
           }
@@ -1306,7 +1371,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
             const float sc = sv[k + u] * inv_s;
             const float rl = fmaxf((sc - tA) + tB, 0.f);
             const bool valid = (vbits >> (k + u)) & 1u;
-            const float pe = valid ? ex2_approx(fmaf(sc * rl, sm_scale_log2, neg_ref)) : 0.f;
+            const float pe = valid ? ex2_approx(fmaf(logit_factor(sc, rl, topk), sm_scale_log2, neg_ref)) : 0.f;
             const bool nb = valid && (rl != 0.f);
             if (nb) mk |= 1u << (k + u);
             p[u] = nb ? pe : 0.f;
@@ -1452,8 +1517,9 @@ static int tc_splits(const Geom& g, const TcGeom& tg, int nqt_range, int csize =
   return best;
 }
 
+constexpr int TOPK_LISTS = 2;                                // key splits of the top-k selection pass
 struct TcWs {
-  size_t absmax, Qp, Kp, Thp, tilemask, thr4, smax, colsum, kbar, Opart, lpart, coef, total;
+  size_t absmax, Qp, Kp, Thp, tilemask, thr4, smax, colsum, kbar, lists, Opart, lpart, coef, total;
   int nsplit;
 };
 
@@ -1478,6 +1544,7 @@ static TcWs tc_ws(const Geom& g, const TcGeom& tg, int nqt_range = 0) {
   w.smax = take(2 * (size_t)g.B * tg.nqt * TC_BM * 4);      // pre-pass maxima | exact maxima of refined rows
   w.colsum = take((size_t)g.B * tg.NT * ED * 4);
   w.kbar = take((size_t)g.B * ED * 4);
+  w.lists = take((size_t)g.B * tg.nqt * TC_BM * TOPK_LISTS * TOPK_MAX * 4);      // legacy top-k variant only
   const size_t rows = (size_t)g.B * w.nsplit * g.Nq;
   w.Opart = take(rows * VD * 4);
   w.lpart = take(4 * rows * 4);                 // one row-sum partial per cluster rank
@@ -1585,35 +1652,52 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
 
   const float sm_scale_log2 = a.scale * 1.4426950408889634f;
   dim3 grid((qt_end - qt_begin) * (variant == 4 ? 4 : 2), w.nsplit, g.B);
+  const int topk = a.topk > 0 ? a.topk : 0;
+  if (topk > TOPK_MAX) {
+    call_state().err = "legacy top-k: at most 64 edges per query";
+    return -2;
+  }
+  if (topk > 0) {
+    // legacy fixed-top-k variant: exact scores once more -> per-row k largest per key split -> per-row threshold into thr4
+    float* lists = reinterpret_cast<float*>(base + w.lists);
+    const int nl = tg.NT < TOPK_LISTS ? tg.NT : TOPK_LISTS;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RMX_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<2>, dim3(qt_end - qt_begin, nl, g.B), RM_THREADS, RMX_SM_TOTAL, st, tg, Qp, Kp, nl, qt_begin,
+                            qt_end, (unsigned*)nullptr, thr4, absmax, 0.f, topk, (unsigned*)nullptr, tilemask, lists));
+    DAGL_LAUNCH_CHECK();
+    const int nrows = g.B * tg.nqt * TC_BM;
+    DAGL_CUDA_OK(launch_pdl(topk_merge_kernel, (nrows + 127) / 128, 128, 0, st, g, tg, nl, topk, lists, absmax, thr4));
+    DAGL_LAUNCH_CHECK();
+  }
   // pre-pass: row maxima of the scores (Qh.Kh only) ...
   const int nqg = (qt_end - qt_begin + RM_QT - 1) / RM_QT;
   int pre_split = 148 / (nqg * g.B);
   if (pre_split < 1) pre_split = 1;
   const int max_split = tg.NT;
   if (pre_split > max_split) pre_split = max_split;
-  DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
-  DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<false>, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin,
-                          qt_end, smax, thr4, absmax, sm_scale_log2, smax2));
+  DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SM_TOTAL));
+  DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<0>, dim3(nqg, pre_split, g.B), RM_THREADS, RM_SM_TOTAL, st, tg, Qp, Kp, pre_split, qt_begin,
+                          qt_end, smax, thr4, absmax, sm_scale_log2, topk, smax2, tilemask, (float*)nullptr));
   DAGL_LAUNCH_CHECK();
   // ... made exact for query tiles with huge logits (normally every CTA exits at once)
   {
     int xsplit = 148 / ((qt_end - qt_begin) * g.B);
     if (xsplit < 1) xsplit = 1;
     if (xsplit > max_split) xsplit = max_split;
-    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RMX_SM_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<true>, dim3(qt_end - qt_begin, xsplit, g.B), RM_THREADS, RMX_SM_TOTAL, st, tg, Qp, Kp, xsplit,
-                            qt_begin, qt_end, smax, thr4, absmax, sm_scale_log2, smax2));
+    DAGL_CUDA_OK(cudaFuncSetAttribute(rowmax_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RMX_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(rowmax_tc_kernel<1>, dim3(qt_end - qt_begin, xsplit, g.B), RM_THREADS, RMX_SM_TOTAL, st, tg, Qp, Kp, xsplit,
+                            qt_begin, qt_end, smax, thr4, absmax, sm_scale_log2, topk, smax2, tilemask, (float*)nullptr));
     DAGL_LAUNCH_CHECK();
   }
   if (int rc = prof_begin(st)) return rc;
   if (variant == 4) {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
     DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
-                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+                            sm_scale_log2, topk, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
   } else {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
     DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
-                            sm_scale_log2, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+                            sm_scale_log2, topk, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
   }
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;

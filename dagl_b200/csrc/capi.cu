@@ -131,12 +131,17 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
   int rc;
   for (int h = 0; h < nh; ++h) {
     if ((rc = check_weights(heads[h]))) return rc;
-    if (heads[h]->in_channels != heads[0]->in_channels || heads[h]->softmax_scale != heads[0]->softmax_scale) {
-      call_state().err = "heads of one batched stage call must share in_channels and softmax_scale";
+    if (heads[h]->in_channels != heads[0]->in_channels || heads[h]->softmax_scale != heads[0]->softmax_scale ||
+        heads[h]->legacy_topk != heads[0]->legacy_topk) {
+      call_state().err = "heads of one batched stage call must share in_channels, softmax_scale and legacy_topk";
       return DAGL_ERR_INVALID_ARG;
     }
   }
   const DaglCEWeights* w = heads[0];
+  if (w->legacy_topk < 0 || w->legacy_topk > 64 || (w->legacy_topk > 0 && impl == DAGL_IMPL_SIMT)) {
+    call_state().err = "legacy_topk must be in [0, 64] and needs a tensor-core impl";
+    return DAGL_ERR_UNSUPPORTED;
+  }
   rc = check_shape(B * nh, H, W);
   if (rc) return rc;
   if (!b || (!y && !rows_out) || !ws) {
@@ -224,6 +229,7 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
   a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
   a.k_packed = k_packed;
+  a.topk = w->legacy_topk;
   a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
   a.rows_out = rows_out; a.qt_begin = qt_begin; a.qt_end = qt_end;
   return run_attend(g, a, impl, absmax, st);
@@ -285,7 +291,8 @@ int32_t dagl_ces_heads_forward_f32(const DaglCEWeights* const* heads, int32_t n_
   bool batch_ok = impl != DAGL_IMPL_SIMT && n_heads > 1 && heads[0]->in_channels == 64 &&
                   workspace_bytes >= dagl_ces_workspace_bytes(n_heads, B, heads[0]->in_channels, H, W);
   for (int h = 1; h < n_heads && batch_ok; ++h)
-    batch_ok = heads[h]->in_channels == heads[0]->in_channels && heads[h]->softmax_scale == heads[0]->softmax_scale;
+    batch_ok = heads[h]->in_channels == heads[0]->in_channels && heads[h]->softmax_scale == heads[0]->softmax_scale &&
+               heads[h]->legacy_topk == heads[0]->legacy_topk;
   if (batch_ok) {
     for (int h0 = 0; h0 < n_heads; h0 += MAX_HEADS) {
       const int nh = n_heads - h0 < MAX_HEADS ? n_heads - h0 : MAX_HEADS;

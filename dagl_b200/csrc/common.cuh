@@ -178,6 +178,7 @@ struct AttendArgs {
   // full forward: every operand of the graph kernel (key / query tiles, theta image, tile masks, threshold terms, Kbar) was
   // already written into its workspace by the epilogues of the prologue kernels; Q, K, Kbar, gamma, beta, theta are unused
   bool k_packed = false;
+  int topk = 0;        // > 0: the legacy fixed-top-k neighbour selection (k edges per query) instead of the adaptive threshold
 };
 // operand buffers inside the tensor-core graph kernel's workspace that the prologue epilogues write directly
 struct AttendBuffers {

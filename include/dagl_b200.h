@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DAGL_ABI_VERSION 3
+#define DAGL_ABI_VERSION 4
 
 enum {
   DAGL_OK = 0,
@@ -64,6 +64,11 @@ typedef struct DaglCEWeights {
   float softmax_scale;      /* reference default 10   */
   const void* packed_fc;    /* optional (may be NULL): fc1/fc2 and g/theta pre-packed by dagl_ce_pack_weights_f32
                                for the tensor-core kernels; saves the per-call weight packing at inference   */
+  int32_t legacy_topk;      /* 0: the shipping CE (adaptive per-query threshold, dagl.py:256-257; thr/bias are used).
+                               k in [1, 64]: the neighbour selection of the reference's legacy fixed-top-k variant
+                               (DN_Gray/model/.ipynb_checkpoints/GReccR2b_3mh_1-checkpoint.py:243-250): the k keys with
+                               the largest scores, logits scale * S on them (thr / bias are ignored; ties at the k-th
+                               score are all kept).  Tensor-core impls only.                                     */
 } DaglCEWeights;
 
 int32_t dagl_abi_version(void);

@@ -212,6 +212,32 @@ def ce_forward_chunked(p: Params, b: torch.Tensor, chunk: int = 512, return_nnz:
     return (y, torch.stack(nnzs)) if return_nnz else y
 
 
+def ce_forward_topk(p: Params, b: torch.Tensor, k: int, return_mask: bool = False):
+    """The graph stage of the reference's LEGACY fixed-top-k variant
+    (DN_Gray/model/.ipynb_checkpoints/GReccR2b_3mh_1-checkpoint.py:196-262; no entry point of the reference imports it):
+    same patches / embeddings / fold as the shipping CE, but the neighbours of a query are its ``min(k, Nk)`` highest-scoring
+    keys (:243-247), the logits are ``scale * S`` on them and 0 elsewhere (:248-249), and there is no thr / bias branch.
+    Returns the folded, count-normalised aggregation (``zi / out_mask``, :255-260), i.e. without that variant's trailing
+    ``W`` conv and residual (:262-263), which the shipping ``CES`` applies outside ``CE``."""
+    B, C, H, W = b.shape
+    G, Th, _, _, qp, kp, vp, fold_pad = _prologue(p, b)
+    ys, masks = [], []
+    for i in range(B):
+        Q = F.relu(F.linear(qp[i].t(), p["fc1.0.weight"], p["fc1.0.bias"]))      # :236
+        K = F.relu(F.linear(kp[i].t(), p["fc2.0.weight"], p["fc2.0.bias"]))      # :237
+        S = torch.matmul(Q, K.t())                                                # :238
+        top_k = min(k, S.shape[1])                                                # :243
+        _, pred = torch.topk(S, top_k, dim=1)                                     # :244
+        mask = torch.zeros_like(S)
+        mask.scatter_(1, pred, 1.0)                                               # :245-247
+        yi = F.softmax((S * mask) * SOFTMAX_SCALE, dim=1) * mask                  # :248-250
+        O = torch.mm(yi, vp[i].t())                                               # :253
+        ys.append(_fold_normalise(O, H, W, fold_pad))                             # :255-260
+        masks.append(mask.bool())
+    y = torch.cat(ys, dim=0)
+    return (y, torch.stack(masks)) if return_mask else y
+
+
 # ---------------------------------------------------------------------------
 # Caller row (SURVEY §8 a12): CES = 3 stages x 4 heads + ResBlocks
 # ---------------------------------------------------------------------------

@@ -458,3 +458,40 @@ def test_large_ragged_cross_implementation_agreement(dev, rand_weights):
     assert rel_err(ys["tc"], ys["simt"]) <= REL_TOL
     assert rel_err(ys["tc4"], ys["simt"]) <= REL_TOL
     assert rel_err(ys["tc4"], ys["tc"]) <= 2e-4          # same operand precision, different schedules
+
+
+@pytest.mark.parametrize("impl", ["tc", "tc4"])
+def test_legacy_topk_mode(dev, rand_weights, impl):
+    """Opt-in legacy neighbour rule (fixed top-k, GReccR2b_3mh_1-checkpoint.py:243-250) against reference-made goldens and
+    the oracle: output within 1e-3, selected neighbour sets equal except at ties around the k-th score."""
+    import dagl_b200
+    g = load_npz("ce_topk_legacy.npz")
+    for tag in ("a", "b", "c"):
+        x, k = g[f"x_{tag}"], int(g[f"k_{tag}"])
+        ce = dagl_b200.CE(in_channels=64, impl=impl, legacy_topk=k)
+        ce.load_state_dict(rand_weights)
+        ce = ce.to(dev).eval()
+        with torch.no_grad():
+            y, bits, nnz = ce.forward_debug(x.to(dev))
+        assert rel_err(y.cpu(), g[f"y_{tag}"]) <= REL_TOL, tag
+        _, mask = O.ce_forward_topk(rand_weights, x, k, return_mask=True)
+        Nk = x.shape[-2] * x.shape[-1]
+        m_gpu = O.unpack_mask_bits(bits.cpu(), Nk)
+        kk = min(k, Nk)
+        assert int((nnz.cpu() < kk).sum()) == 0                      # at least k neighbours per query (more only at ties)
+        flips = int((m_gpu != mask).sum())
+        assert flips <= 2e-3 * mask.numel() / max(1, Nk // kk) + 4, (tag, flips)
+        with torch.no_grad():
+            assert torch.equal(ce(x.to(dev)), y)
+
+
+def test_legacy_topk_is_inference_only_and_needs_tensor_cores(dev, rand_weights):
+    import dagl_b200
+    ce = dagl_b200.CE(in_channels=64, impl="simt", legacy_topk=8)
+    ce.load_state_dict(rand_weights)
+    ce = ce.to(dev).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="legacy_topk"):
+        ce(torch.zeros(1, 64, 16, 16, device=dev))
+    ce2 = dagl_b200.CE(in_channels=64, legacy_topk=8).to(dev)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        ce2(torch.zeros(1, 64, 16, 16, device=dev, requires_grad=True))

@@ -172,3 +172,15 @@ def test_bench_workload_generator_matches_oracle_init():
     assert set(params) == set(ref)
     assert all(torch.equal(params[k], ref[k]) for k in ref)
     assert x.shape == (1, 64, 256, 256)
+
+
+def test_topk_oracle_matches_the_legacy_reference_class():
+    """oracle.ce_forward_topk against outputs of the reference's own leftover fixed-top-k class
+    (GReccR2b_3mh_1-checkpoint.py, run by oracle/make_golden_topk.py).  The golden is ``(b + W y)[:, :16] - b[:, :16]`` with a
+    selector W, so it carries one fp32 rounding of |b| + |y|: compared to 1e-5 of the output range, not bit for bit."""
+    g = load_npz("ce_topk_legacy.npz")
+    w = load_npz("ce_rand_w.npz")
+    for tag in ("a", "b", "c"):
+        y = O.ce_forward_topk(w, g[f"x_{tag}"], int(g[f"k_{tag}"]))
+        ref = g[f"y_{tag}"]
+        assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), tag
