@@ -19,6 +19,7 @@ EXPORTS = [
     "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
     "dagl_ces_heads_forward_f32", "dagl_ce_packed_weights_bytes", "dagl_ce_pack_weights_f32",
     "dagl_ces_workspace_bytes", "dagl_ce_rows_workspace_bytes",
+    "dagl_graph_attend_backward_workspace_bytes", "dagl_graph_attend_backward_f32",
 ]
 
 
@@ -81,6 +82,10 @@ def lib() -> C.CDLL:
     L.dagl_ces_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
     L.dagl_ce_fold_rows_f32.restype = i32
     L.dagl_ce_fold_rows_f32.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.dagl_graph_attend_backward_workspace_bytes.restype = sz
+    L.dagl_graph_attend_backward_workspace_bytes.argtypes = [i32, i32, i32]
+    L.dagl_graph_attend_backward_f32.restype = i32
+    L.dagl_graph_attend_backward_f32.argtypes = [vp] * 11 + [i32, i32, i32, C.c_float, vp, sz, vp]
     L.dagl_profile_enable.restype = i32
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32

@@ -1,11 +1,17 @@
 """Backward for ``dagl_b200.CE`` (the reference trains through plain autograd,
 DN_Gray/trainer.py:51-57; a forward-only head would silently break ``train.py``).
 
-The forward value comes from the CUDA path.  The backward re-evaluates the block with differentiable torch ops ON THE
-DEVICE and lets autograd differentiate that recompute (flash-attention style: nothing of the N_q x N_k score matrix is
-kept between forward and backward).  The recompute is written in the convolution form of SURVEY.md App. A (embeddings as
-7x7 convolutions, row mean taken per query chunk) and processes the queries in checkpointed chunks, so the memory of a
-backward is O(chunk x N_k) instead of the reference's ~20 N_q x N_k temporaries.
+The forward value comes from the CUDA path.  The backward (``CEFunction.backward``) has two parts:
+
+* the graph stage (scores, neighbour mask, softmax, aggregation, fold: dagl.py:250-272) is differentiated by hand-written
+  CUDA kernels, ``dagl_graph_attend_backward_f32`` (csrc/attend_bwd.cu): flash-attention style, nothing of the N_q x N_k
+  score matrix is kept between forward and backward; it is recomputed per chunk of query rows inside the workspace;
+* the plain convolutions / linears in front of it (g, theta, fc1, fc2, thr_conv, bias_conv: dagl.py:208-249) are re-evaluated
+  with differentiable torch ops on the device (convolution form of SURVEY.md App. A) and differentiated by autograd, fed
+  with the kernel's gradients of Q, K, theta, gamma, beta.
+
+``ce_recompute`` is the all-torch evaluation of the block; it pins the math on the CPU (tests/test_autograd.py) and is
+the checker of the CUDA backward, not a fallback of it.
 
 Gradient semantics are the reference's (dagl.py:250-264): the gradient flows through ``S``, through the row mean, through
 ``mask = relu(S - mu*gamma + beta)`` where it multiplies the logits, and through the softmax; the 0/1 factor ``mask_b``
@@ -32,6 +38,45 @@ def _rows(Qc, Kt, Vt, gamma_c, beta_c, scale: float):
     m = F.relu(S - mu * gamma_c.unsqueeze(1) + beta_c.unsqueeze(1))
     P = torch.softmax(S * m * scale, dim=1) * (m != 0).to(S.dtype)
     return P @ Vt
+
+
+def ce_prologue(b: torch.Tensor, p: Sequence[torch.Tensor], ksize: int = 7, stride_q: int = 4):
+    """Differentiable torch evaluation of everything in front of the graph stage (dagl.py:208-249, convolution form):
+    returns Q [B,Nq,196], K [B,Nk,196], theta [B,16,H,W], gamma, beta [B,Nq]."""
+    g_w, g_b, th_w, th_b, fc1_w, fc1_b, fc2_w, fc2_b, thr_w, thr_b, bias_w, bias_b = p
+    B, _, H, W = b.shape
+    ci = g_w.shape[0]
+    pad_k = ksize // 2
+    (pt, pb), (pl, pr) = _same_pad(H, ksize, stride_q), _same_pad(W, ksize, stride_q)
+    G = F.conv2d(b, g_w, g_b, padding=1)
+    Th = F.conv2d(b, th_w, th_b)
+    b4 = F.pad(b, (pl, pr, pt, pb))
+    gamma = F.conv2d(b4, thr_w, thr_b, stride=stride_q).flatten(1)
+    beta = F.conv2d(b4, bias_w, bias_b, stride=stride_q).flatten(1)
+    e = fc1_w.shape[0]
+    Q = F.relu(F.conv2d(F.pad(G, (pl, pr, pt, pb)), fc1_w.view(e, ci, ksize, ksize), fc1_b, stride=stride_q))
+    K = F.relu(F.conv2d(G, fc2_w.view(e, ci, ksize, ksize), fc2_b, padding=pad_k))
+    return (Q.flatten(2).transpose(1, 2).contiguous(), K.flatten(2).transpose(1, 2).contiguous(), Th.contiguous(),
+            gamma.contiguous(), beta.contiguous())
+
+
+def graph_stage_backward(Q, K, Th, gamma, beta, dy, scale: float):
+    """Gradients of the graph stage with respect to (Q, K, theta, gamma, beta): one call through the C-ABI
+    (``dagl_graph_attend_backward_f32``)."""
+    from . import _lib
+    from .ce import _workspace
+    L = _lib.lib()
+    B, _, H, W = Th.shape
+    dev = Q.device
+    outs = [torch.empty_like(t) for t in (Q, K, Th, gamma, beta)]
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, L.dagl_graph_attend_backward_workspace_bytes(B, H, W))
+        dy = dy.contiguous()
+        rc = L.dagl_graph_attend_backward_f32(Q.data_ptr(), K.data_ptr(), Th.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                              dy.data_ptr(), *[o.data_ptr() for o in outs], B, H, W, float(scale),
+                                              ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "dagl_graph_attend_backward_f32")
+    return outs
 
 
 def ce_recompute(b: torch.Tensor, p: Sequence[torch.Tensor], ksize: int = 7, stride_q: int = 4, scale: float = 10.0,
@@ -95,9 +140,12 @@ class CEFunction(torch.autograd.Function):
         try:
             with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
                 leaves = [t.detach().requires_grad_(bool(n)) for t, n in zip([b] + params, need)]
-                y = ce_recompute(leaves[0], leaves[1:], ksize=m.ksize, stride_q=m.stride_1, scale=float(m.softmax_scale))
                 wanted = [t for t in leaves if t.requires_grad]
-                grads = list(torch.autograd.grad(y, wanted, dy.contiguous(), allow_unused=True))
+                # graph stage: CUDA kernels; the convolutions / linears in front of it: torch autograd
+                mids = ce_prologue(leaves[0], leaves[1:], ksize=m.ksize, stride_q=m.stride_1)
+                with torch.no_grad():
+                    dmids = graph_stage_backward(*[t.detach() for t in mids], dy, float(m.softmax_scale))
+                grads = list(torch.autograd.grad(list(mids), wanted, dmids, allow_unused=True))
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_mm
         out = [grads.pop(0) if t.requires_grad else None for t in leaves]

@@ -156,6 +156,18 @@ int32_t dagl_graph_attend_f32(const float* Q, const float* K, const float* Kbar,
                               int32_t impl, void* stream,
                               uint32_t* mask_bits, int32_t* nnz);
 
+/* Backward of the fused graph stage (the reference trains through plain autograd, DN_Gray/trainer.py:51-57, i.e. through
+ * dagl.py:250-272).  Inputs: the embeddings Q [B][Nq][196], K [B][Nk][196] (post-ReLU), theta [B][16][H][W], gamma, beta
+ * [B][Nq] and dy [B][16][H][W]; outputs the gradients with respect to the first five (same shapes), with the reference's
+ * gradient semantics: through S, the row mean, relu(S - mu*gamma + beta) where it multiplies the logits and the softmax;
+ * none through the 0/1 neighbour indicator.  fp32 CUDA-core kernels, deterministic.  The convolutions / linears in front
+ * of the graph stage are differentiated by the caller (dagl_b200/autograd.py uses PyTorch for them).               */
+size_t dagl_graph_attend_backward_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int32_t dagl_graph_attend_backward_f32(const float* Q, const float* K, const float* theta, const float* gamma,
+                                       const float* beta, const float* dy, float* dQ, float* dK, float* dtheta,
+                                       float* dgamma, float* dbeta, int32_t B, int32_t H, int32_t W, float softmax_scale,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Intermediate views inside the workspace after dagl_ce_forward_* (device
  * pointers, valid until the workspace is reused): which = 0 G [B,16,H,W],
  * 1 theta [B,16,H,W], 2 gamma [B,Nq], 3 beta [B,Nq], 4 Q [B,Nq,196],

@@ -72,3 +72,50 @@ def test_backward_through_the_cuda_forward(impl):
     out = ces(torch.randn(1, 64, 12, 12, device=dev))
     out.mean().backward()
     assert ces.c1_1.fc1[0].weight.grad is not None and torch.isfinite(ces.c1_1.fc1[0].weight.grad).all()
+
+
+def _graph_stage_torch(Q, K, Th, gamma, beta, scale=10.0):
+    """Reference-order graph stage (dagl.py:250-272) on explicit (Q, K, theta, gamma, beta) with plain torch ops."""
+    import torch.nn.functional as F
+    B, _, H, W = Th.shape
+    ys = []
+    V = F.unfold(Th, 7, padding=3).transpose(1, 2)                    # [B, Nk, 784] in (c, ky, kx) order
+    for i in range(B):
+        S = Q[i] @ K[i].t()
+        mu = S.mean(dim=1, keepdim=True)
+        m = F.relu(S - mu * gamma[i].unsqueeze(1) + beta[i].unsqueeze(1))
+        P = torch.softmax(S * m * scale, dim=1) * (m != 0).to(S.dtype)
+        O = (P @ V[i]).t().unsqueeze(0)
+        y = F.fold(O, (H, W), 7, padding=3, stride=4)
+        cnt = F.fold(F.unfold(torch.ones(1, 1, H, W, dtype=S.dtype, device=S.device), 7, padding=3, stride=4), (H, W), 7, padding=3, stride=4)
+        ys.append(y / cnt)
+    return torch.cat(ys, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,force_rc", [((2, 20, 24), None), ((1, 64, 64), None), ((3, 36, 41), "64")])
+def test_graph_stage_backward_kernels(shape, force_rc, monkeypatch):
+    """dagl_graph_attend_backward_f32 against fp64 autograd through the reference-order graph stage on the same
+    (Q, K, theta, gamma, beta): the CUDA kernels alone, incl. several row chunks / image groups (force_rc)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dagl_b200.autograd import graph_stage_backward
+    if force_rc:
+        monkeypatch.setenv("DAGL_BWD_RC", force_rc)
+    B, H, W = shape
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    nq, nk = ((H + 3) // 4) * ((W + 3) // 4), H * W
+    Q = torch.relu(torch.randn(B, nq, 196, generator=gen)) * 0.12
+    K = torch.relu(torch.randn(B, nk, 196, generator=gen)) * 0.12
+    Th = torch.randn(B, 16, H, W, generator=gen)
+    gamma = torch.rand(B, nq, generator=gen) * 0.8
+    beta = (torch.rand(B, nq, generator=gen) - 0.5) * 0.4
+    dy = torch.randn(B, 16, H, W, generator=gen)
+    leaves = [t.double().requires_grad_(True) for t in (Q, K, Th, gamma, beta)]
+    y = _graph_stage_torch(*leaves)
+    ref = torch.autograd.grad(y, leaves, dy.double())
+    got = graph_stage_backward(*[t.to(dev) for t in (Q, K, Th, gamma, beta)], dy.to(dev), 10.0)
+    for name, g, r in zip(("dQ", "dK", "dtheta", "dgamma", "dbeta"), got, ref):
+        assert torch.isfinite(g).all(), name
+        assert _rel(g.cpu().double(), r) <= 2e-3, (name, _rel(g.cpu().double(), r))
