@@ -957,6 +957,9 @@ constexpr int V4_PD = V4_PDEPTH;                            // P tiles a produce
 constexpr int V4_PSLOTS = 4 * V4_PD;                        // P slots: (producer rank) + 4 * (own-tile index mod V4_PD)
 constexpr int V4_TSEG_BYTES = (TC_BN + TH_SEG_PIX) * 32;    // one dy row of theta for a pair of tiles: 112 pixels = 3584 B
 constexpr int V4_TSTAGE_BYTES = V4_TSLOTS * V4_TSEG_BYTES;  // one stage of rank 3 = 4 theta rows of a tile pair: 14336
+#ifndef V4_PAR_ISSUE
+#define V4_PAR_ISSUE 1                                      // theta rows / P forwards of a tile issued by parallel lanes
+#endif
 #ifndef V4_TASYM
 #define V4_TASYM 0                                          // ranks 0..2 need only 2 theta rows per pair: twice the ring depth in the same smem
 #endif
@@ -1049,6 +1052,27 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+#if V4_PAR_ISSUE
+    {
+      // one lane per theta row: the 2 (rank 3: 4) copies of a tile pair are issued together
+      const int lane = tid & 31;
+      const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
+      const int nhalf = (ntiles + 1) >> 1;
+      for (int h = 0; h < nhalf; ++h) {
+        const int s = h % tst;
+        if (lane == 0) {
+          mbar_wait(t_empty + s, ((uint32_t)(h / tst) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(t_full + s, (uint32_t)nslots * V4_TSEG_BYTES);
+        }
+        __syncwarp();
+        const int k0 = (t_begin + 2 * h) * TC_BN;            // multiple of 8, and so is Wp
+        if (lane < nslots)
+          bulk_g2s(smem + S4_T + s * tstage_bytes + lane * V4_TSEG_BYTES, thp + (size_t)(k0 + c_rows4[rank][lane] * tg.Wp) * 32,
+                   V4_TSEG_BYTES, t_full + s);
+        __syncwarp();
+      }
+    }
+#else
     if (elect_one()) {
       const uint8_t* thp = Thp + (size_t)img * tg.NP * 32;
       // theta rows of the tile pair (2h, 2h+1): 96 consecutive key slots + the 64-pixel window, ONE copy per row
@@ -1071,6 +1095,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         TL(h >> 1, 20);
       }
     }
+#endif
   } else if (warp == TC_THREADS / 32 + 2) {
     // ===================== K loader: own key tiles (local tile 4i + rank) =====================
     if (elect_one()) {
@@ -1236,6 +1261,25 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
     }
   } else if (warp == TC_THREADS / 32) {
     // ===================== P forwarder: one bulk DSMEM copy per peer =====================
+    // A thread needs ~100 cycles per dependent bulk-copy issue (tools/bulk_copy_probe.cu): lanes 0..2 each own one peer, so
+    // the three forwards of a tile leave together instead of one after the other.
+#if V4_PAR_ISSUE
+    {
+      const int lane = tid & 31;
+      const uint32_t src0 = smem_u32(smem + S4_P + rank * P_SLOT_BYTES);
+      const uint32_t peer = (uint32_t)((rank + 1 + (lane < 3 ? lane : 0)) & 3);
+      const uint32_t dst = mapa(src0, peer), rbar = mapa(smem_u32(p_full + rank), peer);
+      for (int i = 0; i < n_own; ++i) {
+        const uint32_t par = (uint32_t)(i % V4_PD);                        // slot rank + 4*par
+        mbar_wait(p_full + rank + 4 * par, (uint32_t)(i / V4_PD) & 1u);
+        if (lane < 3)
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst + par * 4 * P_SLOT_BYTES), "r"(src0 + par * 4 * P_SLOT_BYTES), "r"((uint32_t)P_SLOT_BYTES),
+                         "r"(rbar + par * 32) : "memory");
+        __syncwarp();
+      }
+    }
+#else
     if (elect_one()) {
       const uint32_t src0 = smem_u32(smem + S4_P + rank * P_SLOT_BYTES);
       uint32_t dst[3], rbar[3];
@@ -1262,6 +1306,7 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
         TL(i, 18);
       }
     }
+#endif
   } else {
     // ===================== softmax / epilogue warps =====================
     const int quad = warp & 3;

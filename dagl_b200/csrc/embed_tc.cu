@@ -51,7 +51,10 @@ constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
 constexpr int EB_MU_BYTES = 2 * EB_M * 8;            // query launch: the two epilogue warps of a row exchange their partial mu (doubles)
 constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // mbarriers + TMEM base (384 B), bias vectors [heads][208], mu exchange
 constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // query launch
-constexpr int EB_THREADS = 384;                    // warps 0, 7 weight taps (even / odd), 1 MMA issuer, 2-5 + 8-11 epilogue, 6 G halos
+#ifndef EB_NPROD
+#define EB_NPROD 2                                 // producer warps of the weight-tap ring (0, 7, then 12, 13)
+#endif
+constexpr int EB_THREADS = 384 + 32 * (EB_NPROD - 2);   // warps 0, 7 (12, 13) weight taps, 1 MMA issuer, 2-5 + 8-11 epilogue, 6 G halos
 constexpr int EB_ACC_COLS = 2 * EB_N0;             // one accumulator buffer: main (hi.hi) at +0, cross terms at +112
 constexpr int EB_TMEM_COLS = 512;                  // two accumulator buffers (448 columns used)
 static_assert(EB_SM_W % 1024 == 0, "weight ring alignment");
@@ -186,10 +189,12 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
     bias_all[e] = (e % EB_N) < ED ? __ldg(static_cast<const float*>(bias_h.p[e / EB_N]) + (e % EB_N)) : 0.f;
   __syncthreads();
 
-  if (warp == 0 || warp == 7) {
+  if (warp == 0 || warp == 7 || warp >= 12) {
     // ===================== producers: weight taps (one ring that runs across items) =====================
-    // A single thread issues a tap (try_wait + expect_tx + bulk copy) every ~300 cycles, more than the tap's three MMAs
-    // take (176), so two warps share the taps (even / odd); every stage still sees its fills in order.
+    // A single thread issues a tap (try_wait + expect_tx + bulk copy) every ~306 cycles whatever the copy size (measured:
+    // tools/bulk_copy_probe.cu, profiles/r2/r2p_bulk_probe.log), more than the tap's three MMAs take (176), so EB_NPROD
+    // warps share the taps round-robin; every stage still sees its fills in order.
+    const int pidx = warp == 0 ? 0 : warp == 7 ? 1 : warp - 10;
     if (elect_one()) {
       int it = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -198,7 +203,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         const uint32_t tap_bytes = eh ? EB_WTAP1_BYTES : EB_WTAP0_BYTES;
         const uint8_t* wsrc = static_cast<const uint8_t*>(wp_h.p[g.head(img)]) + (eh ? EB_WHALF1_OFF : 0);
         const uint8_t* asrc = QG ? ghi + ((size_t)img * eg.nqt + tile) * (size_t)(KK * EB_QA_BYTES) : nullptr;
-        for (int t = (warp == 0 ? 0 : 1); t < KK; t += 2) {
+        for (int t = pidx; t < KK; t += EB_NPROD) {
           const int s = t % EB_WSTAGES;
           const uint32_t use = (uint32_t)(it * eb_stage_uses(s) + t / EB_WSTAGES);      // how often stage s was filled before
           mbar_wait(w_empty + s, (use & 1u) ^ 1u);

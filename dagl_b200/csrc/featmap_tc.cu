@@ -32,7 +32,7 @@ constexpr int FT_WTAP_BYTES = 2 * FT_WPART_BYTES;   // hi | lo
 constexpr int FT_SM_A = 0;                          // [group][hi|lo][ky] segments
 constexpr int FT_SM_W = FT_GROUPS * 2 * 3 * FT_SEG_BYTES;            // 110592 = 108 * 1024
 constexpr int FT_SM_BAR = FT_SM_W + FT_VTAPS * FT_WTAP_BYTES;        // + 73728
-constexpr int FT_SM_TOTAL = FT_SM_BAR + 64;
+constexpr int FT_SM_TOTAL = FT_SM_BAR + 128;
 constexpr int FT_THREADS = 192;                     // warp 0 loads, warp 1 issues, warps 2-5 epilogue
 static_assert(FT_SM_W % 1024 == 0, "weight image alignment");
 
@@ -71,8 +71,10 @@ __global__ void absmax_img_kernel(const float* __restrict__ x, size_t n_per_img,
   if ((threadIdx.x & 31) == 0) atomicMax(bmax + img, __float_as_uint(m));
 }
 
-// g weight [16][64][3][3], theta weight [16][64] -> per virtual tap (group, tap): [hi|lo][2 k-chunks][32 rows][8 ch] fp16,
-// rows 0..15 = g outputs, rows 16..31 = theta outputs (zero except at the centre tap); wmax[0] = max |w| (float bits).
+// g weight [16][64][3][3], theta weight [16][64] -> per virtual tap (group, tap): [2 k-chunks][64 rows][8 ch] fp16, rows =
+// g hi | g lo | theta hi | theta lo (16 each; theta is zero except at the centre tap): the hi and lo parts of the weights are
+// stacked along N, so ONE MMA forms both b_hi.W_hi (main accumulator columns) and b_hi.W_lo (cross-term columns).
+// wmax[0] = max |w| (float bits).
 __global__ void __launch_bounds__(256)
 pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ g_b, const float* __restrict__ th_w,
                   const float* __restrict__ th_b, uint8_t* __restrict__ out, unsigned* __restrict__ wmax) {
@@ -128,9 +130,11 @@ pack_featw_kernel(const float* __restrict__ g_w, const float* __restrict__ g_b, 
       hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    uint8_t* base = out + (size_t)v * FT_WTAP_BYTES + (size_t)(kc * FT_N + e) * 16;
-    *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + FT_WPART_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    // rows of the virtual tap's B operand: [g hi 0..15 | g lo 16..31 | theta hi 32..47 | theta lo 48..63], K-major no swizzle
+    const int row_hi = e < CI ? e : 2 * CI + (e - CI), row_lo = row_hi + CI;
+    uint8_t* base = out + (size_t)v * FT_WTAP_BYTES + (size_t)kc * (2 * FT_N) * 16;
+    *reinterpret_cast<uint4*>(base + (size_t)row_hi * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)row_lo * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -219,11 +223,11 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FT_SM_BAR);
   uint64_t* w_full = bars + 0;      // weights resident
-  uint64_t* a_full = bars + 1;      // halo of the current item
-  uint64_t* a_empty = bars + 2;     // its MMAs have completed
-  uint64_t* d_full = bars + 3;      // [2]
-  uint64_t* d_empty = bars + 5;     // [2] 4 arrivals (one per epilogue warp)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* a_full = bars + 1;      // [2] halo of channel groups {0,1} / {2,3} of the current item: the two halves are a 2-stage
+  uint64_t* a_empty = bars + 3;     // [2] ring, so the load of one half overlaps the MMAs of the other (its MMAs have completed)
+  uint64_t* d_full = bars + 5;      // [2]
+  uint64_t* d_empty = bars + 7;     // [2] 4 arrivals (one per epilogue warp)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
@@ -233,9 +237,7 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
 
   if (tid == 0) {
     mbar_init(w_full, 1);
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<128>(tmem_ptr);
@@ -250,43 +252,59 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
     int it = 0, cur_head = -1;
     for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
       const int head = w / per_head, img = (w / eg.ntile) % (g.B / g.NH), p0 = (w % eg.ntile) * FT_M;   // img: REAL image
-      if (lane == 0) {
-        mbar_wait(a_empty, ((uint32_t)it & 1u) ^ 1u);        // the MMAs of the previous item are complete: halo AND weights are free
-        if (head != cur_head) mbar_arrive_expect_tx(w_full, FT_VTAPS * FT_WTAP_BYTES);
-        mbar_arrive_expect_tx(a_full, FT_GROUPS * 2 * 3 * FT_SEG_BYTES);
+      if (head != cur_head) {
+        // new weights: every MMA of the previous item (both halves) must have completed
+        if (lane == 0) {
+          mbar_wait(a_empty + 1, ((uint32_t)it & 1u) ^ 1u);
+          mbar_arrive_expect_tx(w_full, FT_VTAPS * FT_WTAP_BYTES);
+        }
+        __syncwarp();
+        if (lane == FT_GROUPS * 2 * 3)
+          bulk_g2s(smem + FT_SM_W, static_cast<const uint8_t*>(wpack.p[head]), FT_VTAPS * FT_WTAP_BYTES, w_full);
+        cur_head = head;
       }
-      __syncwarp();
-      if (head != cur_head && lane == FT_GROUPS * 2 * 3)
-        bulk_g2s(smem + FT_SM_W, static_cast<const uint8_t*>(wpack.p[head]), FT_VTAPS * FT_WTAP_BYTES, w_full);
-      cur_head = head;
-      if (lane < FT_GROUPS * 2 * 3) {
-        const int gq = lane / 6, part = (lane / 3) & 1, ky = lane % 3;
-        const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
-        const int first = (p0 + (ky + 2) * eg.Wp) & ~7;                 // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
-        bulk_g2s(smem + FT_SM_A + ((gq * 2 + part) * 3 + ky) * FT_SEG_BYTES, src + (size_t)first * 32, FT_SEG_BYTES, a_full);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (lane == 0) {
+          mbar_wait(a_empty + half, ((uint32_t)it & 1u) ^ 1u);          // the MMAs that read this half of the previous item are complete
+          mbar_arrive_expect_tx(a_full + half, (FT_GROUPS / 2) * 2 * 3 * FT_SEG_BYTES);
+        }
+        __syncwarp();
+        if (lane / 12 == half && lane < FT_GROUPS * 2 * 3) {
+          const int gq = lane / 6, part = (lane / 3) & 1, ky = lane % 3;
+          const uint8_t* src = bimg + ((size_t)(img * FT_GROUPS + gq) * 2 + part) * (size_t)eg.NPG * 32;
+          const int first = (p0 + (ky + 2) * eg.Wp) & ~7;                 // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
+          bulk_g2s(smem + FT_SM_A + ((gq * 2 + part) * 3 + ky) * FT_SEG_BYTES, src + (size_t)first * 32, FT_SEG_BYTES, a_full + half);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t abase = smem_u32(smem + FT_SM_A), wbase = smem_u32(smem + FT_SM_W);
+      constexpr uint32_t id64 = instr_desc(FT_M, 64, FMT_F16, FMT_F16, 0, 0);
       constexpr uint32_t id32 = instr_desc(FT_M, 32, FMT_F16, FMT_F16, 0, 0);
       constexpr uint32_t id16 = instr_desc(FT_M, 16, FMT_F16, FMT_F16, 0, 0);
       int it = 0, cur_head = -1, nloads = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
         const int p0 = (w % eg.ntile) * FT_M, ab = it & 1, head = w / per_head;
-        const uint32_t d_main = tbase + ab * 64, d_cross = d_main + 32;
+        const uint32_t d_main = tbase + ab * 64;
         if (head != cur_head) { mbar_wait(w_full, (uint32_t)nloads & 1u); ++nloads; cur_head = head; }
-        mbar_wait(a_full, (uint32_t)it & 1u);
         mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        // The centre tap carries the theta outputs (N = 32) and goes first in every group, so that the very first MMA
-        // initialises all 32 accumulator columns; the other taps only touch the 16 g columns.
+        // Accumulator columns: [g main | g cross | theta main | theta cross] (16 each).  Per virtual tap TWO MMAs instead of
+        // three: b_hi x [W_hi | W_lo] (N = 32; centre tap N = 64 incl. theta) and b_lo x W_hi (N = 16) into the cross
+        // columns (these small-N MMAs cost ~36-48 cycles each whatever N is, so the count is what matters).  The centre tap
+        // goes first in every group, so that the very first MMA initialises all 64 columns.
         const int order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
         bool first = true;
 #pragma unroll 1
-        for (int gq = 0; gq < FT_GROUPS; ++gq) {
+        for (int half = 0; half < 2; ++half) {               // channel groups {0,1} / {2,3}: the two halves of the halo ring
+          mbar_wait(a_full + half, (uint32_t)it & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int gq = 2 * half; gq < 2 * half + 2; ++gq) {
 #pragma unroll
           for (int i = 0; i < 9; ++i) {
             const int t = order[i], ky = t / 3, kx = t % 3;
@@ -298,19 +316,26 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
                                    ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
             const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
                                    ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
-            const uint32_t w_hi = wbase + (gq * 9 + t) * FT_WTAP_BYTES;
-            const uint64_t db_hi = smem_desc(w_hi, FT_N * 16, 128);
-            const uint64_t db_lo = smem_desc(w_hi + FT_WPART_BYTES, FT_N * 16, 128);
-            const uint32_t idesc = (t == 4) ? id32 : id16;
+            const uint32_t wv = wbase + (gq * 9 + t) * FT_WTAP_BYTES;
+            const uint64_t db_all = smem_desc(wv, 2 * FT_N * 16, 128);                 // rows 0..: g hi, g lo, theta hi, theta lo
+            const uint64_t db_thi = smem_desc(wv + 2 * CI * 16, 2 * FT_N * 16, 128);   // rows 32..47: theta hi
             const uint32_t acc = first ? 0u : 1u;
-            mma_f16_ss_a_fill(d_main, da_hi, db_hi, idesc, acc);             // bh.Wh  -> main accumulator
-            mma_f16_ss_a_lastuse(d_cross, da_hi, db_lo, idesc, acc);         // bh.Wl  -> cross accumulator
-            mma_f16_ss(d_cross, da_lo, db_hi, idesc, 1);                     // bl.Wh
+            if (t == 4) {
+              mma_f16_ss(d_main, da_hi, db_all, id64, acc);                     // b_hi . [Wg_hi | Wg_lo | Wt_hi | Wt_lo]
+              mma_f16_ss(d_main + CI, da_lo, db_all, id16, 1);                  // b_lo . Wg_hi -> g cross
+              mma_f16_ss(d_main + 3 * CI, da_lo, db_thi, id16, 1);              // b_lo . Wt_hi -> theta cross
+            } else {
+              mma_f16_ss(d_main, da_hi, db_all, id32, acc);                     // b_hi . [Wg_hi | Wg_lo]
+              mma_f16_ss(d_main + CI, da_lo, db_all, id16, 1);                  // b_lo . Wg_hi -> g cross
+            }
             first = false;
           }
+          }
+          // unconditional on purpose: a uniform-predicated tcgen05.commit whose (unused) address operand is misaligned
+          // still faults ("misaligned address")
+          mma_commit(a_empty + half);                        // this half of the halo may be refilled (next item)
         }
         mma_commit(d_full + ab);
-        mma_commit(a_empty);
       }
     }
   } else {
@@ -344,9 +369,9 @@ featmap_tc_kernel(Geom g, FtGeom eg, const uint8_t* __restrict__ bimg, HeadPtrs 
       mbar_wait(d_full + ab, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       uint32_t v[2][16], vc[2][16];
-      tmem_ld16(trow, v[0]);
-      tmem_ld16(trow + 16, v[1]);
-      tmem_ld16(trow + 32, vc[0]);
+      tmem_ld16(trow, v[0]);                             // g main | g cross | theta main | theta cross
+      tmem_ld16(trow + 16, vc[0]);
+      tmem_ld16(trow + 32, v[1]);
       tmem_ld16(trow + 48, vc[1]);
       tmem_wait_ld();
       tc_fence_before();
