@@ -135,10 +135,13 @@ class CEFunction(torch.autograd.Function):
         # The forward's scores are fp32-accurate (3-term split-fp16 MMAs).  The recompute must be too, whatever the training
         # script set globally: TF32 convolutions OR TF32 matmuls (`allow_tf32` / set_float32_matmul_precision) would flip
         # neighbours relative to the forward and put ~1e-3 of error into the gradients.
-        prev_mm = torch.backends.cuda.matmul.allow_tf32
+        # (the two flags are saved / restored by hand: ``torch.backends.cudnn.flags(allow_tf32=False)`` would also switch cuDNN
+        # OFF — its ``enabled`` argument defaults to False — and the convolutions below would take the slow native kernels.)
+        prev_mm, prev_cd = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
         try:
-            with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=False):
+            with torch.enable_grad():
                 leaves = [t.detach().requires_grad_(bool(n)) for t, n in zip([b] + params, need)]
                 wanted = [t for t in leaves if t.requires_grad]
                 # graph stage: CUDA kernels; the convolutions / linears in front of it: torch autograd
@@ -148,5 +151,6 @@ class CEFunction(torch.autograd.Function):
                 grads = list(torch.autograd.grad(list(mids), wanted, dmids, allow_unused=True))
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_mm
+            torch.backends.cudnn.allow_tf32 = prev_cd
         out = [grads.pop(0) if t.requires_grad else None for t in leaves]
         return (None, *out)

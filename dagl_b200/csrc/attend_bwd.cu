@@ -13,7 +13,7 @@
 //   dQ = dS K + dmu Kbar^T        dK = dS^T Q + (1/Nk) 1 (sum_q dmu_q Q_q)^T        dV = P^T dO  ->  dtheta = fold of dV
 // Every product is a dense GEMM over a chunk of query rows whose [rows x Nk] score / probability / dP matrices live in
 // the workspace (bounded by the caller's workspace: the chunk shrinks for large images), so the kernels are one generic
-// tiled fp32 GEMM with operand loaders (plain, transposed, and the Toeplitz view of theta for V) plus row-wise passes.
+// tiled fp32 GEMM (128 x 128 x 8, 8 x 8 per thread) with operand loaders (plain, transposed, and the Toeplitz view of theta for V) plus row-wise passes.
 // The convolutions / linears in front of the graph stage are differentiated by PyTorch (dagl_b200/autograd.py).
 #include <math.h>
 #include <stdlib.h>
@@ -22,7 +22,7 @@
 
 namespace dagl {
 
-constexpr int GB_M = 64, GB_N = 64, GB_K = 16, GB_THREADS_ = 256;
+constexpr int GB_M = 128, GB_N = 128, GB_K = 8, GB_THREADS_ = 256;
 constexpr int TP = PADK;                         // theta is zero-padded by 3 on every side (dagl.py:224-230)
 
 struct BwdGeom {
@@ -66,48 +66,50 @@ __device__ __forceinline__ float load_b(const BwdGeom& g, const BwdPtrs& p, int 
   return __ldg(p.dO + ((size_t)img * g.Nq + g.r0 + k) * VD + n);                      // BW_DV
 }
 
-// C[M x N] (+)= A[M x K] B[K x N], 64 x 64 x 16 tiles, 4 x 4 outputs per thread.  AFK / BFK: the operand's k index is the
-// contiguous one in memory (so consecutive threads take consecutive k), else its m / n index is.
+// C[M x N] (+)= A[M x K] B[K x N]: 128 x 128 x 8 tiles, 8 x 8 outputs per thread (64 FMAs per 4 shared-memory loads).
+// AFK / BFK: the operand's k index is the contiguous one in memory (consecutive threads take consecutive k), else its m / n
+// index is.
 template <int MODE>
 __global__ void __launch_bounds__(GB_THREADS_)
 bwd_gemm_kernel(BwdGeom g, BwdPtrs p, int M, int N, int K, int accumulate) {
   constexpr bool AFK = (MODE == BW_S || MODE == BW_DP || MODE == BW_DQ);
   constexpr bool BFK = (MODE == BW_S || MODE == BW_DP);
-  __shared__ float As[GB_K][GB_M + 4];
-  __shared__ float Bs[GB_K][GB_N + 4];
+  __shared__ __align__(16) float As[GB_K][GB_M + 4];
+  __shared__ __align__(16) float Bs[GB_K][GB_N + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N, z = blockIdx.z;
-  float acc[4][4] = {};
+  float acc[8][8] = {};
   for (int k0 = 0; k0 < K; k0 += GB_K) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < (GB_M * GB_K) / GB_THREADS_; ++r) {
       const int i = tid + r * GB_THREADS_;
-      const int ak = AFK ? (i & 15) : (i >> 6), am = AFK ? (i >> 4) : (i & 63);
+      const int ak = AFK ? (i & (GB_K - 1)) : (i / GB_M), am = AFK ? (i / GB_K) : (i & (GB_M - 1));
       As[ak][am] = load_a<MODE>(g, p, z, m0 + am, k0 + ak, M, K);
-      const int bk = BFK ? (i & 15) : (i >> 6), bn = BFK ? (i >> 4) : (i & 63);
+      const int bk = BFK ? (i & (GB_K - 1)) : (i / GB_N), bn = BFK ? (i / GB_K) : (i & (GB_N - 1));
       Bs[bk][bn] = load_b<MODE>(g, p, z, k0 + bk, n0 + bn, K, N);
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GB_K; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
   const long long img = g.img0 + z;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx * 8 + j;
       if (n >= N) continue;
       float* dst;
       if (MODE == BW_S) dst = p.S + ((size_t)z * g.rc + m) * g.Nk + n;

@@ -41,3 +41,14 @@ with torch.no_grad():
 print(f"{B}x64x{HW}x{HW}: forward (CUDA path) {fwd:.3f} ms")
 print(f"  forward + backward, CUDA graph-stage backward kernels + torch prologue autograd: {t(step_cuda):.3f} ms")
 print(f"  forward + backward, all-torch recompute (fp32 matmuls, the round-1 backward):   {t(step_torch):.3f} ms")
+
+# breakdown of the CUDA-path backward
+from dagl_b200.autograd import ce_prologue, graph_stage_backward
+torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+xs = x.detach().requires_grad_(True)
+def pro():
+    return ce_prologue(xs, leaves)
+mids = pro()
+dmids = graph_stage_backward(*[m.detach() for m in mids], w, 10.0)
+print(f"  breakdown: torch prologue forward {t(pro):.3f} ms; CUDA graph-stage backward {t(lambda: graph_stage_backward(*[m.detach() for m in mids], w, 10.0)):.3f} ms; "
+      f"torch autograd through the prologue {t(lambda: torch.autograd.grad(list(pro()), [xs] + leaves, dmids, allow_unused=True)):.3f} ms (incl. its forward)")
