@@ -43,14 +43,20 @@ constexpr int EB_WSTAGES = KS;                     // 7 = one row of taps: tap (
                                                    // constant in the unrolled issue loop) and every stage completes 7 phases per item.
                                                    // (14 stages measured no faster: the kernel is bound by the L2 -> SM stream of the
                                                    // weight taps, 343 KB per 128-pixel item, not by its latency.)
-__host__ __device__ constexpr int eb_stage_uses(int) { return KS; }
+#ifndef EB_QSTAGES
+#define EB_QSTAGES 14                              // query launch: deeper ring (no halo stages there, and its loop tap -> commit -> refill
+#endif                                             // -> data is latency-bound: 20 us per item whatever the number of items)
+constexpr int EB_WSTAGES_Q = EB_QSTAGES;
+// how often stage s of a WST-deep ring is filled per item (49 taps)
+__host__ __device__ constexpr int eb_stage_uses(int s, int wst) { return (KK - s + wst - 1) / wst; }
 constexpr int EB_SM_G = 0;                                           // two halo stages
 constexpr int EB_SM_W = 2 * EB_G_BYTES;                              // 129024 = 126 * 1024
 constexpr int EB_SM_CSUM = EB_SM_W + EB_WSTAGES * EB_WSTAGE_BYTES;   // column-sum exchange [4][112] floats
 constexpr int EB_SM_BAR = EB_SM_CSUM + 4 * EB_N0 * 4;
 constexpr int EB_MU_BYTES = 2 * EB_M * 8;            // query launch: the two epilogue warps of a row exchange their partial mu (doubles)
 constexpr int EB_SM_TOTAL = EB_SM_BAR + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // mbarriers + TMEM base (384 B), bias vectors [heads][208], mu exchange
-constexpr int EB_SMQ_TOTAL = EB_WSTAGES * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // query launch
+constexpr int EB_SMQ_TOTAL = EB_WSTAGES_Q * EB_QSTAGE_BYTES + 4 * EB_N0 * 4 + 384 + MAX_HEADS * EB_N * 4 + EB_MU_BYTES;   // query launch
+static_assert(EB_SMQ_TOTAL <= 232448, "query embed kernel exceeds the 227 KB dynamic shared memory limit");
 #ifndef EB_NPROD
 #define EB_NPROD 2                                 // producer warps of the weight-tap ring (0, 7, then 12, 13)
 #endif
@@ -156,16 +162,18 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
   constexpr int STAGE = QG ? EB_QSTAGE_BYTES : EB_WSTAGE_BYTES;      // QG: [A hi 4 KB | A lo 4 KB | weight tap]
   constexpr int W_OFF = QG ? EB_QA_BYTES : 0;
   constexpr int SM_W = QG ? 0 : EB_SM_W;                             // queries: no halo stages
-  constexpr int SM_CSUM = SM_W + EB_WSTAGES * STAGE;
+  constexpr int WST = QG ? EB_WSTAGES_Q : EB_WSTAGES;               // depth of the tap ring
+  constexpr int SM_CSUM = SM_W + WST * STAGE;
   constexpr int SM_BAR = SM_CSUM + 4 * EB_N0 * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* g_full = bars + 0;                   // [2]
   uint64_t* g_empty = bars + 2;                  // [2]
   uint64_t* d_full = bars + 4;                   // [2]
   uint64_t* d_empty = bars + 6;                  // [2] 8 arrivals (one per epilogue warp)
-  uint64_t* w_full = bars + 8;                   // [EB_WSTAGES]
-  uint64_t* w_empty = bars + 8 + EB_WSTAGES;     // [EB_WSTAGES]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * EB_WSTAGES);
+  uint64_t* w_full = bars + 8;                   // [WST]
+  uint64_t* w_empty = bars + 8 + WST;            // [WST]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * WST);
+  static_assert((8 + 2 * WST) * 8 + 4 <= 384, "barrier area");
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
@@ -176,7 +184,7 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
       mbar_init(g_full + i, 1); mbar_init(g_empty + i, 1);
       mbar_init(d_full + i, 1); mbar_init(d_empty + i, 8);
     }
-    for (int i = 0; i < EB_WSTAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < WST; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc<EB_TMEM_COLS>(tmem_ptr);
@@ -204,8 +212,8 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         const uint8_t* wsrc = static_cast<const uint8_t*>(wp_h.p[g.head(img)]) + (eh ? EB_WHALF1_OFF : 0);
         const uint8_t* asrc = QG ? ghi + ((size_t)img * eg.nqt + tile) * (size_t)(KK * EB_QA_BYTES) : nullptr;
         for (int t = pidx; t < KK; t += EB_NPROD) {
-          const int s = t % EB_WSTAGES;
-          const uint32_t use = (uint32_t)(it * eb_stage_uses(s) + t / EB_WSTAGES);      // how often stage s was filled before
+          const int s = t % WST;
+          const uint32_t use = (uint32_t)(it * eb_stage_uses(s, WST) + t / WST);        // how often stage s was filled before
           mbar_wait(w_empty + s, (use & 1u) ^ 1u);
           mbar_arrive_expect_tx(w_full + s, tap_bytes + (QG ? EB_QA_BYTES : 0));
           if (QG) bulk_g2s(smem + SM_W + s * STAGE, asrc + (size_t)t * EB_QA_BYTES, EB_QA_BYTES, w_full + s);
@@ -264,11 +272,11 @@ embed_tc_kernel(Geom g, EmbGeom eg, const uint8_t* __restrict__ ghi /*QG: the ga
         const uint64_t b_bits = ((uint64_t)(((uint32_t)(ncols / 8) * 128) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         const uint32_t w_row = smem_u32(smem + SM_W) >> 4;
         const uint32_t w_lo = (uint32_t)(ncols * 32) >> 4;        // lo part follows the hi part
-        const uint32_t par0 = (uint32_t)(it * eb_stage_uses(0));
+
 #pragma unroll
         for (int t = 0; t < KK; ++t) {
-          const int ky = t / KS, kx = t % KS, st = t % EB_WSTAGES;    // compile-time after unrolling
-          mbar_wait(w_full + st, (par0 + t / EB_WSTAGES) & 1u);
+          const int ky = t / KS, kx = t % KS, st = t % WST;           // compile-time after unrolling
+          mbar_wait(w_full + st, (uint32_t)(it * eb_stage_uses(st, WST) + t / WST) & 1u);
           tc_fence_after();
           const uint32_t a_hi = QG ? w_row + st * (STAGE >> 4) : a_row[ky] + kx * 2;
           const uint64_t da_hi = a_bits | (uint64_t)(a_hi & 0x3FFF);
