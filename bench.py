@@ -258,6 +258,22 @@ def other_configs(ce, dev, flush, peaks):
     # the ResBlocks / 1x1 merges of CES are plain cuDNN convolutions under torch's defaults (TF32 allowed), as they are when the
     # reference runs on this GPU; only the twelve heads are this repo's kernels
     shape_line("CES.forward 1x64x64x64 (12 heads as 3 stage calls + 8 cuDNN ResBlocks)", 1, 64, 64, 20, fn=ces, heads=12)
+    # the same forward captured in a CUDA graph by the caller (the library allocates nothing and never synchronises)
+    try:
+        xg = torch.randn(1, C_IN, 64, 64, generator=gen).to(dev)
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    ces(xg)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                ces(xg)
+        shape_line("CES.forward 1x64x64x64, replay of a caller-side CUDA graph", 1, 64, 64, 20, fn=lambda _x: graph.replay(), heads=12)
+    except Exception as e:                                            # a bench extra, never fatal
+        out.append({"workload": "CES.forward 1x64x64x64, CUDA graph", "error": str(e)[:200]})
     shape_line("CES.forward 64x64x72x72 (chop batch)", 64, 72, 72, 3, fn=ces, heads=12)
     shape_line("CES.forward 1x64x256x256 (direct)", 1, 256, 256, 5, fn=ces, heads=12)
     return out

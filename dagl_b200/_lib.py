@@ -19,7 +19,7 @@ EXPORTS = [
     "dagl_ce_num_query_tiles", "dagl_ce_forward_rows_f32", "dagl_ce_fold_rows_f32",
     "dagl_ces_heads_forward_f32", "dagl_ce_packed_weights_bytes", "dagl_ce_pack_weights_f32",
     "dagl_ces_workspace_bytes", "dagl_ce_rows_workspace_bytes",
-    "dagl_graph_attend_backward_workspace_bytes", "dagl_graph_attend_backward_f32",
+    "dagl_graph_attend_backward_workspace_bytes", "dagl_graph_attend_backward_f32", "dagl_ce_workspace_bytes_ex",
 ]
 
 
@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
     L.dagl_last_launch_count.restype = i32
     L.dagl_ce_workspace_bytes.restype = sz
     L.dagl_ce_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.dagl_ce_workspace_bytes_ex.restype = sz
+    L.dagl_ce_workspace_bytes_ex.argtypes = [i32, i32, i32, i32, i32, i32]
     L.dagl_ce_host_staging_bytes.restype = sz
     L.dagl_ce_host_staging_bytes.argtypes = [i32, i32, i32, i32]
     L.dagl_ce_forward_f32.restype = i32

@@ -172,7 +172,7 @@ class CE(nn.Module):
         B, Cc, H, W = b.shape
         with torch.cuda.device(b.device):
             y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
-            nbytes = L.dagl_ce_workspace_bytes(B, Cc, H, W)
+            nbytes = L.dagl_ce_workspace_bytes_ex(B, Cc, H, W, _lib.IMPL_BY_NAME[self.impl], 0)
             ws = _workspace(b.device, nbytes)
             w, keep = self._weights(b.device)
             stream = torch.cuda.current_stream(b.device).cuda_stream
@@ -310,7 +310,8 @@ class CE(nn.Module):
             raise RuntimeError(f"forward_host: y_host must be a contiguous fp32 host tensor of shape "
                                f"{(B, self.inter_channels, H, W)}")
         with torch.cuda.device(device):
-            nbytes = L.dagl_ce_workspace_bytes(B, Cc, H, W) + L.dagl_ce_host_staging_bytes(B, Cc, H, W)
+            nbytes = L.dagl_ce_workspace_bytes_ex(B, Cc, H, W, _lib.IMPL_BY_NAME[self.impl], 0) + \
+                L.dagl_ce_host_staging_bytes(B, Cc, H, W)
             ws = _workspace(device, nbytes)
             w, keep = self._weights(device)
             stream = torch.cuda.current_stream(device).cuda_stream

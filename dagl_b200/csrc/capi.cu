@@ -35,25 +35,23 @@ int prof_end(cudaStream_t st) {
 
 // Workspace carve-up shared by workspace_bytes / forward / workspace_view.
 struct WsLayout {
-  size_t G, Th, gamma, beta, Q, K, kpart, Kbar, absmax, packw, feat, embed, attend, total;
-  int kblocks_simt, kblocks_tc;
+  size_t gamma, beta, Kbar, absmax, packw, feat, embed, attend, lean_total;   // what the tensor-core forward needs
+  size_t G, Th, Q, K, kpart, total;                                            // + fp32 intermediates (CUDA-core prologue, debug entry)
+  int kblocks_simt;
 };
 
+// The fp32 copies of G, theta, Q, K come LAST: the tensor-core forward never touches them (every kernel writes the next
+// one's fp16 operands from its epilogue), so a caller that only runs the product path can hand in `lean_total` bytes
+// (dagl_ce_workspace_bytes_ex); the debug entry and the CUDA-core prologue need `total`.  All other offsets are the same
+// in both cases.
 static WsLayout ws_layout(const Geom& g, int nqt_range = 0) {
   WsLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const size_t f = sizeof(float);
   L.kblocks_simt = embed_num_blocks(g.Nk);
-  L.kblocks_tc = embed_tc_num_tiles(g);
-  const int kblocks = L.kblocks_simt > L.kblocks_tc ? L.kblocks_simt : L.kblocks_tc;
-  L.G = take((size_t)g.B * CI * g.Nk * f);
-  L.Th = take((size_t)g.B * CI * g.Nk * f);
   L.gamma = take((size_t)g.B * g.Nq * f);
   L.beta = take((size_t)g.B * g.Nq * f);
-  L.Q = take((size_t)g.B * g.Nq * ED * f);
-  L.K = take((size_t)g.B * g.Nk * ED * f);
-  L.kpart = take((size_t)g.B * kblocks * ED * f);
   L.Kbar = take((size_t)g.B * ED * f);
   L.absmax = take((size_t)g.B * AMAX_STRIDE * sizeof(unsigned));
   L.packw = take((size_t)g.NH * (embed_tc_packed_weights_bytes() + feature_maps_tc_packed_weights_bytes()));   // per-call weight packing
@@ -62,6 +60,12 @@ static WsLayout ws_layout(const Geom& g, int nqt_range = 0) {
   L.attend = off;
   const size_t a_simt = attend_simt_workspace_bytes(g), a_tc = attend_tc_workspace_bytes(g, nqt_range);
   off += align_up(a_simt > a_tc ? a_simt : a_tc);
+  L.lean_total = off;
+  L.G = take((size_t)g.B * CI * g.Nk * f);
+  L.Th = take((size_t)g.B * CI * g.Nk * f);
+  L.Q = take((size_t)g.B * g.Nq * ED * f);
+  L.K = take((size_t)g.B * g.Nk * ED * f);
+  L.kpart = take((size_t)g.B * L.kblocks_simt * ED * f);
   L.total = off;
   return L;
 }
@@ -161,7 +165,9 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
     g.y_img_stride = y_img_stride;
   }
   const WsLayout L = ws_layout(g, rows_out ? qt_end - qt_begin : 0);
-  if (ws_bytes < L.total) {
+  const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
+  const bool tc_prologue = impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g);
+  if (ws_bytes < ((tc_prologue && !debug) ? L.lean_total : L.total)) {
     call_state().err = "workspace too small";
     return DAGL_ERR_WORKSPACE;
   }
@@ -186,8 +192,6 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
   }
 
   bool k_packed = false;
-  const bool debug = (mask_bits != nullptr) || (nnz != nullptr);
-  const bool tc_prologue = impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g);
   DAGL_CUDA_OK(cudaMemsetAsync(absmax, 0, (size_t)g.B * AMAX_STRIDE * sizeof(unsigned), st));
   if (tc_prologue) {
     // Tensor-core prologue: every kernel writes the next one's operands from its epilogue.  feature maps -> fp16 images of G
@@ -227,7 +231,7 @@ static int forward_impl(const DaglCEWeights* const* heads, int nh, const float* 
   AttendArgs a;
   a.Q = Q; a.K = K; a.Kbar = Kbar; a.gamma = gamma; a.beta = beta; a.theta = Th; a.y = y;
   a.scale = w->softmax_scale; a.mask_bits = mask_bits; a.nnz = nnz;
-  a.ws = base + L.attend; a.ws_bytes = ws_bytes - L.attend;
+  a.ws = base + L.attend; a.ws_bytes = L.lean_total - L.attend;
   a.k_packed = k_packed;
   a.topk = w->legacy_topk;
   a.kbar_out = reinterpret_cast<float*>(base + L.Kbar);     // keeps dagl_ce_workspace_view(…, 6) valid on every path
@@ -251,15 +255,25 @@ size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
   return ws_layout(make_geom(B, C, H, W)).total;
 }
 
+size_t dagl_ce_workspace_bytes_ex(int32_t B, int32_t C, int32_t H, int32_t W, int32_t impl, int32_t debug) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  const Geom g = make_geom(B, C, H, W);
+  const WsLayout L = ws_layout(g);
+  return (impl != DAGL_IMPL_SIMT && feature_maps_tc_supported(g) && !debug) ? L.lean_total : L.total;
+}
+
 size_t dagl_ce_rows_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W, int32_t q_tile_begin, int32_t q_tile_end) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || q_tile_end <= q_tile_begin) return 0;
-  return ws_layout(make_geom(B, C, H, W), q_tile_end - q_tile_begin).total;
+  const Geom g = make_geom(B, C, H, W);
+  const WsLayout L = ws_layout(g, q_tile_end - q_tile_begin);
+  return feature_maps_tc_supported(g) ? L.lean_total : L.total;
 }
 
 size_t dagl_ces_workspace_bytes(int32_t n_heads, int32_t B, int32_t C, int32_t H, int32_t W) {
   if (n_heads <= 0 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
   const int nh = n_heads < MAX_HEADS ? n_heads : MAX_HEADS;
-  const size_t batched = ws_layout(make_geom(B, C, H, W, nh)).total, single = ws_layout(make_geom(B, C, H, W)).total;
+  // the batched route only exists on the tensor-core path (lean layout); the serial per-head route may be the CUDA-core one
+  const size_t batched = ws_layout(make_geom(B, C, H, W, nh)).lean_total, single = ws_layout(make_geom(B, C, H, W)).total;
   return batched > single ? batched : single;
 }
 
@@ -358,7 +372,7 @@ int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, fl
     return DAGL_ERR_INVALID_ARG;
   }
   const int C = w->in_channels;
-  const size_t need = dagl_ce_workspace_bytes(B, C, H, W);
+  const size_t need = dagl_ce_workspace_bytes_ex(B, C, H, W, impl, 0);     // staging buffers follow the forward's own workspace
   const size_t stage = dagl_ce_host_staging_bytes(B, C, H, W);
   if (workspace_bytes < need + stage) {
     call_state().err = "workspace too small for host entry (need workspace_bytes + host_staging_bytes)";

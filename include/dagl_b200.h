@@ -79,6 +79,9 @@ const char* dagl_last_error(void);
 /* Bytes of device workspace dagl_ce_forward_* needs for a [B,C,H,W] input (sized for the launch of the whole image:
  * a query-sharded rows call has its own query, dagl_ce_rows_workspace_bytes). */
 size_t dagl_ce_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+/* The same for one given impl: the tensor-core forward keeps no fp32 intermediates (G, theta, Q, K), so without the debug
+ * outputs it needs ~35 % less (`debug` != 0: the size dagl_ce_forward_debug_f32 / dagl_ce_workspace_view need). */
+size_t dagl_ce_workspace_bytes_ex(int32_t B, int32_t C, int32_t H, int32_t W, int32_t impl, int32_t debug);
 
 /* y[B,16,H,W] = CE.forward(b[B,C,H,W])          — replaces dagl.py:207-275. */
 int32_t dagl_ce_forward_f32(const DaglCEWeights* w, const float* b, float* y,
@@ -121,8 +124,8 @@ int32_t dagl_ce_forward_debug_f32(const DaglCEWeights* w, const float* b, float*
 
 /* Host-buffer entry: b_host / y_host are HOST pointers (pinned for async
  * copies); the H2D copy of b, the forward and the D2H copy of y are all
- * enqueued on `stream`.  Needs dagl_ce_workspace_bytes() +
- * dagl_ce_host_staging_bytes() of device workspace.                          */
+ * enqueued on `stream`.  Needs dagl_ce_workspace_bytes_ex(.., impl, 0) +
+ * dagl_ce_host_staging_bytes() of device workspace (dagl_ce_workspace_bytes() + staging is always enough).   */
 size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
 int32_t dagl_ce_forward_host_f32(const DaglCEWeights* w, const float* b_host, float* y_host,
                                  int32_t B, int32_t H, int32_t W,
