@@ -46,6 +46,14 @@ FLOPS_ALG = 2.0 * NQ * NK * (196 + 784)                       # 5
 BYTES_ALG = 4.0 * (NQ * 196 + NK * 196 + 196 + 2 * NQ + 32 * NK)  # 63.0 MB / image
 
 
+def workload_config():
+    """The `config` object: identical in the product arm and in the reference arm (same workload, same per-GPU unit)."""
+    return {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} per GPU (one graph block, direct/no-chop), random-init head",
+            "Nq": NQ, "Nk": NK,
+            "l2": "GPU arm: L2 flushed between timed iterations (256 MiB memset); CPU arm: n/a",
+            "timing": "GPU arm: CUDA events per step, summed, max over ranks; CPU arm: perf_counter around the timed steps"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -190,8 +198,7 @@ def run_reference_arm(args):
         "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} (one graph block, direct/no-chop), random-init head",
-                   "Nq": NQ, "Nk": NK},
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample}; {args.steps} steps after {args.warmup} warm-up, oracle port (reference op order, torch CPU)"},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -448,9 +455,7 @@ def main():
             "dtype": "f32 io; split-fp16 x3 MMAs (fp32-accurate) for feature maps / embeddings / scores, fp16 P.V, fp32 accumulate"
                      if impl_used != "simt" else "f32",
             "data": "synthetic",
-            "config": {"workload": f"CE.forward {B_PER_GPU}x{C_IN}x{H}x{W} per GPU (one graph block, direct/no-chop), random-init head",
-                       "Nq": NQ, "Nk": NK, "impl": impl_used, "l2": "flushed between timed iterations (256 MiB memset)",
-                       "timing": "CUDA events per step, summed; max over ranks"},
+            "config": workload_config(), "impl_used": impl_used,
             "ms_per_graph_block": ms_per_step, "pairs_per_s": world * B_PER_GPU * NQ * NK / (ms_per_step * 1e-3),
             "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": B_PER_GPU * C_IN * H * W * 4,

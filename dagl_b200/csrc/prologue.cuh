@@ -31,18 +31,22 @@ __device__ __forceinline__ void gamma_beta_body(const Geom& g, const float* __re
 #pragma unroll
   for (int k = 0; k < KS; ++k) { rok[k] = live && (y0 + k >= 0) && (y0 + k < g.H); cok[k] = (x0 + k >= 0) && (x0 + k < g.W); }
   float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};              // two chains per output: the FMA latency is the bound
+  // All 49 loads of a channel are issued before the first FMA (written as two loops on purpose: with the load next to its FMA
+  // the compiler keeps only a handful of loads in flight and the kernel becomes a chain of L2 round trips).
   for (int ci = grp; ci < g.C; ci += GB_GROUPS) {
     const float* bc = bi + (size_t)ci * g.Nk + y0 * g.W + x0;
     const float2* wc = w_s + ci * KK;
+    float v[KK];
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const float v = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
-        const float2 w = wc[ky * KS + kx];
-        a0[(ky * KS + kx) & 1] = fmaf(v, w.x, a0[(ky * KS + kx) & 1]);
-        a1[(ky * KS + kx) & 1] = fmaf(v, w.y, a1[(ky * KS + kx) & 1]);
-      }
+      for (int kx = 0; kx < KS; ++kx) v[ky * KS + kx] = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      const float2 w = wc[t];
+      a0[t & 1] = fmaf(v[t], w.x, a0[t & 1]);
+      a1[t & 1] = fmaf(v[t], w.y, a1[t & 1]);
+    }
   }
   red[grp * 32 + lane] = make_float2(a0[0] + a0[1], a1[0] + a1[1]);
   __syncthreads();
@@ -88,18 +92,20 @@ __device__ __forceinline__ void gamma_beta_heads_body(const Geom& g, const float
   for (int ci = grp; ci < g.C; ci += GB_GROUPS) {
     const float* bc = bi + (size_t)ci * g.Nk + y0 * g.W + x0;
     const float2* wc = w_s + (size_t)ci * KK * NH;
+    float v[KK];                                                      // all loads of the channel first (see gamma_beta_body)
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const float v = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
+      for (int kx = 0; kx < KS; ++kx) v[ky * KS + kx] = (rok[ky] && cok[kx]) ? __ldg(bc + ky * g.W + kx) : 0.f;
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          const float2 w = wc[(ky * KS + kx) * NH + h];
-          a0[h][(ky * KS + kx) & 1] = fmaf(v, w.x, a0[h][(ky * KS + kx) & 1]);
-          a1[h][(ky * KS + kx) & 1] = fmaf(v, w.y, a1[h][(ky * KS + kx) & 1]);
-        }
+    for (int t = 0; t < KK; ++t) {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float2 w = wc[t * NH + h];
+        a0[h][t & 1] = fmaf(v[t], w.x, a0[h][t & 1]);
+        a1[h][t & 1] = fmaf(v[t], w.y, a1[h][t & 1]);
       }
+    }
   }
 #pragma unroll
   for (int h = 0; h < NH; ++h) red[(grp * 32 + lane) * NH + h] = make_float2(a0[h][0] + a0[h][1], a1[h][0] + a1[h][1]);
