@@ -20,6 +20,8 @@ EXPORTS = [
     "dagl_ces_heads_forward_f32", "dagl_ce_packed_weights_bytes", "dagl_ce_pack_weights_f32",
     "dagl_ces_workspace_bytes", "dagl_ce_rows_workspace_bytes",
     "dagl_graph_attend_backward_workspace_bytes", "dagl_graph_attend_backward_f32", "dagl_ce_workspace_bytes_ex",
+    "dagl_resblock_packed_weights_bytes", "dagl_resblock_pack_weights_f32", "dagl_resblocks_workspace_bytes",
+    "dagl_resblocks_forward_f32",
 ]
 
 
@@ -30,6 +32,11 @@ class DaglCEWeights(C.Structure):
         ("in_channels", C.c_int32), ("inter_channels", C.c_int32), ("ksize", C.c_int32),
         ("stride_q", C.c_int32), ("stride_k", C.c_int32), ("softmax_scale", C.c_float),
         ("packed_fc", C.c_void_p), ("legacy_topk", C.c_int32)]
+
+
+class DaglResBlockWeights(C.Structure):
+    _fields_ = [("conv1_w", C.c_void_p), ("conv1_b", C.c_void_p), ("prelu_w", C.c_void_p), ("prelu_n", C.c_int32),
+                ("conv2_w", C.c_void_p), ("conv2_b", C.c_void_p), ("res_scale", C.c_float), ("packed", C.c_void_p)]
 
 
 _lib = None
@@ -88,11 +95,19 @@ def lib() -> C.CDLL:
     L.dagl_graph_attend_backward_workspace_bytes.argtypes = [i32, i32, i32]
     L.dagl_graph_attend_backward_f32.restype = i32
     L.dagl_graph_attend_backward_f32.argtypes = [vp] * 11 + [i32, i32, i32, C.c_float, vp, sz, vp]
+    L.dagl_resblock_packed_weights_bytes.restype = sz
+    L.dagl_resblock_packed_weights_bytes.argtypes = []
+    L.dagl_resblock_pack_weights_f32.restype = i32
+    L.dagl_resblock_pack_weights_f32.argtypes = [C.POINTER(DaglResBlockWeights), vp, sz, vp]
+    L.dagl_resblocks_workspace_bytes.restype = sz
+    L.dagl_resblocks_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.dagl_resblocks_forward_f32.restype = i32
+    L.dagl_resblocks_forward_f32.argtypes = [C.POINTER(DaglResBlockWeights), i32, vp, vp, i32, i32, i32, i32, vp, sz, i32, vp]
     L.dagl_profile_enable.restype = i32
     L.dagl_profile_enable.argtypes = [i32]
     L.dagl_profile_read.restype = i32
     L.dagl_profile_read.argtypes = [C.POINTER(C.c_float), i32]
-    if L.dagl_abi_version() != 4:
+    if L.dagl_abi_version() != 5:
         raise RuntimeError("libdagl_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .resblock import ResBlock, fuse_sequential, patch_resblocks
 
 _WS_CACHE: Dict[Tuple[int, int], torch.Tensor] = {}
 _WS_LOCK = threading.Lock()
@@ -360,26 +361,15 @@ def stage_heads_forward(heads, x: torch.Tensor) -> torch.Tensor:
     return ycat
 
 
-class _ResBlock(nn.Module):
-    """conv3x3 - PReLU - conv3x3, + x  (reference common.ResBlock, common.py:59-79,
-    same parameter names: body.0 / body.1 / body.2)."""
-
-    def __init__(self, n_feats: int):
-        super().__init__()
-        self.body = nn.Sequential(nn.Conv2d(n_feats, n_feats, 3, padding=1), nn.PReLU(),
-                                  nn.Conv2d(n_feats, n_feats, 3, padding=1))
-
-    def forward(self, x):
-        return self.body(x) + x
-
-
 class CES(nn.Module):
     """3 stages x 4 CE heads (dagl.py:74-119); state_dict-compatible with the reference CES."""
 
     def __init__(self, in_channels: int, num: int = 4, impl: str = "auto"):
         super().__init__()
-        self.RBS1 = nn.Sequential(*[_ResBlock(in_channels) for _ in range(num)])
-        self.RBS2 = nn.Sequential(*[_ResBlock(in_channels) for _ in range(num)])
+        self.RBS1 = nn.Sequential(*[ResBlock(in_channels) for _ in range(num)])
+        self.RBS2 = nn.Sequential(*[ResBlock(in_channels) for _ in range(num)])
+        fuse_sequential(self.RBS1)        # 64 channels: each chain of four is one dagl_resblocks_forward_f32 call
+        fuse_sequential(self.RBS2)
         for s in (1, 2, 3):
             for h in (1, 2, 3, 4):
                 setattr(self, f"c{s}_{h}", CE(in_channels=in_channels, impl=impl))
@@ -410,13 +400,16 @@ def _ces_stage_forward(self, x):
     return out
 
 
-def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = True) -> int:
+def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = True, fuse_resblocks: bool = True) -> int:
     """Replace every reference ``CE`` instance inside ``module`` (e.g. an ``RR``
     or ``CES`` built by the unmodified reference code) with a ``dagl_b200.CE``
     that *shares* the same Parameters.  Returns the number of heads swapped.
 
     ``fuse_stages``: also rebind ``forward`` of every reference ``CES`` instance whose twelve heads were swapped, so that
-    the four heads of a stage go through ONE stage call instead of four head calls + ``torch.cat`` (same values)."""
+    the four heads of a stage go through ONE stage call instead of four head calls + ``torch.cat`` (same values).
+
+    ``fuse_resblocks``: also route every run of reference ``ResBlock``s inside an ``nn.Sequential`` (``CES.RBS1`` / ``RBS2``,
+    ``RR.body``; common.py:59-79) through the tensor-core chain kernel (``dagl_b200.resblock``; fp32-accurate)."""
     import types
     n = 0
     for parent in module.modules():
@@ -437,6 +430,8 @@ def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = T
             if type(m).__name__ == "CES" and not isinstance(m, CES) and \
                     all(isinstance(getattr(m, h, None), CE) for h in heads) and hasattr(m, "RBS1") and hasattr(m, "c3_c"):
                 m.forward = types.MethodType(_ces_stage_forward, m)
+    if fuse_resblocks:
+        patch_resblocks(module)
     return n
 
 

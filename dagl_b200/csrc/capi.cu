@@ -356,6 +356,56 @@ int32_t dagl_ce_pack_weights_f32(const DaglCEWeights* w, void* packed, size_t pa
   return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
 }
 
+// ---- ResBlock chains (common.py:59-79) ----------------------------------------------------------------------
+size_t dagl_resblock_packed_weights_bytes(void) { return resblock_packed_weights_bytes(); }
+
+int32_t dagl_resblock_pack_weights_f32(const DaglResBlockWeights* w, void* packed, size_t packed_bytes, void* stream) {
+  call_state().launches = 0;
+  if (!w || !w->conv1_w || !w->conv2_w || !packed) {
+    call_state().err = "null pointer";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  const int rc = launch_pack_resblock_weights(w->conv1_w, w->conv1_b, w->conv2_w, w->conv2_b, packed, packed_bytes,
+                                              static_cast<cudaStream_t>(stream));
+  return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
+}
+
+size_t dagl_resblocks_workspace_bytes(int32_t n_blocks, int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (n_blocks <= 0 || B <= 0 || C != 64 || H <= 0 || W <= 0) return 0;
+  return resblocks_workspace_bytes(B, H, W, n_blocks);
+}
+
+int32_t dagl_resblocks_forward_f32(const DaglResBlockWeights* blocks, int32_t n_blocks, const float* x, float* y,
+                                   int32_t B, int32_t C, int32_t H, int32_t W,
+                                   void* workspace, size_t workspace_bytes, int32_t mode, void* stream) {
+  call_state().launches = 0;
+  call_state().impl = "none";
+  if (!blocks || !x || !y || !workspace || n_blocks <= 0 || B <= 0 || H <= 0 || W <= 0) {
+    call_state().err = "null pointer or non-positive size";
+    return DAGL_ERR_INVALID_ARG;
+  }
+  if (C != 64 || n_blocks > 64 || mode < 0 || mode > 2) {
+    call_state().err = "ResBlock chain: built for 64 channels, at most 64 blocks, mode 0 / 1 / 2";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  if ((size_t)B * H * W >= ((size_t)1 << 31) / 64) {
+    call_state().err = "ResBlock chain: tensor too large";
+    return DAGL_ERR_UNSUPPORTED;
+  }
+  ResBlockParams rb[64];
+  for (int i = 0; i < n_blocks; ++i) {
+    const DaglResBlockWeights& w = blocks[i];
+    if (!w.conv1_w || !w.conv2_w || !w.prelu_w || (w.prelu_n != 1 && w.prelu_n != 64)) {
+      call_state().err = "ResBlock chain: null weight or PReLU parameter count not 1 / 64";
+      return DAGL_ERR_INVALID_ARG;
+    }
+    rb[i] = ResBlockParams{w.conv1_w, w.conv1_b, w.prelu_w, w.prelu_n, w.conv2_w, w.conv2_b, w.res_scale, w.packed};
+  }
+  const int rc = launch_resblocks(B, H, W, x, y, n_blocks, rb, workspace, workspace_bytes, mode, static_cast<cudaStream_t>(stream));
+  if (rc == 0) call_state().impl = mode == 0 ? "resblock_tc_pair" : mode == 1 ? "resblock_tc" : "resblock_tc_auto";
+  return rc == -3 ? DAGL_ERR_WORKSPACE : rc;
+}
+
 size_t dagl_ce_host_staging_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
   return align_up((size_t)B * C * H * W * sizeof(float)) + align_up((size_t)B * CI * H * W * sizeof(float));

@@ -206,4 +206,20 @@ size_t attend_tc_workspace_bytes(const Geom& g, int nqt_range = 0);   // nqt_ran
 // variant 2: 2-CTA clusters sharing P (DSMEM); variant 4: 4-CTA clusters, query tile resident in TMEM
 int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax, int variant, cudaStream_t st);
 
+// ResBlock chains (resblock_tc.cu): common.ResBlock, common.py:59-79
+struct ResBlockParams {
+  const float *w1, *b1;        // body.0  Conv2d(64,64,3,pad 1)
+  const float* slope;          // body.1  PReLU weight
+  int slope_n;                 // 1 or 64
+  const float *w2, *b2;        // body.2
+  float res_scale;
+  const void* packed;          // nullable: launch_pack_resblock_weights image
+};
+size_t resblock_packed_weights_bytes();
+int launch_pack_resblock_weights(const float* w1, const float* b1, const float* w2, const float* b2, void* packed,
+                                 size_t packed_bytes, cudaStream_t st);
+size_t resblocks_workspace_bytes(int B, int H, int W, int nblocks);
+int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks, const ResBlockParams* blocks, void* ws,
+                     size_t ws_bytes, int mode, cudaStream_t st);
+
 }  // namespace dagl

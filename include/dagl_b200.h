@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DAGL_ABI_VERSION 4
+#define DAGL_ABI_VERSION 5
 
 enum {
   DAGL_OK = 0,
@@ -170,6 +170,33 @@ int32_t dagl_graph_attend_backward_f32(const float* Q, const float* K, const flo
                                        const float* beta, const float* dy, float* dQ, float* dK, float* dtheta,
                                        float* dgamma, float* dbeta, int32_t B, int32_t H, int32_t W, float softmax_scale,
                                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- ResBlock chains: the callers either side of the graph blocks -----------------------------------------------
+ * common.ResBlock (DN_Gray/model/common.py:59-79): y = conv2(PReLU(conv1(x))) * res_scale + x with two
+ * Conv2d(64,64,3,padding 1) (common.default_conv, common.py:8-11).  CES.RBS1 / RBS2 (dagl.py:86-101, 115, 117) are chains
+ * of four, RR.body (dagl.py:27-34) holds two chains of eight around the CES module.
+ * dagl_resblocks_forward_f32 runs a whole chain: every convolution is one tcgen05 kernel (split-fp16 x3, fp32-accurate)
+ * whose epilogue applies bias / PReLU / residual and writes the next convolution's operand image, so no elementwise
+ * kernel and no fp32 re-pack runs inside the chain.  Borrowed device pointers in the reference's state_dict layout:
+ *   body.0.weight [64][64][3][3]  body.0.bias [64] (NULL: no bias)
+ *   body.1.weight [1] or [64]     (PReLU)
+ *   body.2.weight [64][64][3][3]  body.2.bias [64] (NULL: no bias)                                                     */
+typedef struct DaglResBlockWeights {
+  const float* conv1_w; const float* conv1_b;
+  const float* prelu_w; int32_t prelu_n;
+  const float* conv2_w; const float* conv2_b;
+  float res_scale;          /* ResBlock.res_scale (common.py:73,76) */
+  const void* packed;       /* optional (may be NULL): dagl_resblock_pack_weights_f32 image; saves the per-call packing */
+} DaglResBlockWeights;
+
+size_t dagl_resblock_packed_weights_bytes(void);
+int32_t dagl_resblock_pack_weights_f32(const DaglResBlockWeights* w, void* packed, size_t packed_bytes, void* stream);
+size_t dagl_resblocks_workspace_bytes(int32_t n_blocks, int32_t B, int32_t C, int32_t H, int32_t W);
+/* x, y: fp32 [B][C][H][W] (C must be 64; y may alias x).  mode 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel,
+ * 2: chosen by size (the default of the Python binding). */
+int32_t dagl_resblocks_forward_f32(const DaglResBlockWeights* blocks, int32_t n_blocks, const float* x, float* y,
+                                   int32_t B, int32_t C, int32_t H, int32_t W,
+                                   void* workspace, size_t workspace_bytes, int32_t mode, void* stream);
 
 /* Intermediate views inside the workspace after dagl_ce_forward_* (device
  * pointers, valid until the workspace is reused): which = 0 G [B,16,H,W],

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_sizes():
     from dagl_b200 import _lib
     L = _lib.lib()
-    assert L.dagl_abi_version() == 4
+    assert L.dagl_abi_version() == 5
     small = L.dagl_ce_workspace_bytes(1, 64, 64, 64)
     big = L.dagl_ce_workspace_bytes(1, 64, 256, 256)
     assert 0 < small < big < 2 ** 33

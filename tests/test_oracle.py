@@ -1,11 +1,14 @@
 """CPU tests: pin the oracle (oracle/ce_oracle.py) to the golden fixtures that
 oracle/make_golden.py produced by running the UNMODIFIED reference, and — when
 the reference is mounted (build container only) — to the live reference."""
+import os
+
 import pytest
 import torch
 
 from conftest import have_reference, import_reference, load_npz
 from oracle import ce_oracle as O
+from oracle import ref_loader as R
 
 
 def test_same_pad_rule():
@@ -184,3 +187,67 @@ def test_topk_oracle_matches_the_legacy_reference_class():
         y = O.ce_forward_topk(w, g[f"x_{tag}"], int(g[f"k_{tag}"]))
         ref = g[f"y_{tag}"]
         assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), tag
+
+
+# ---- ResBlock chain oracle (common.py:59-79) ---------------------------------------------------------------------
+def _resblock_golden():
+    import numpy as np
+    from oracle import resblock_oracle as RB
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "resblock_chain.npz"))
+    for tag in ("a", "b"):
+        nb = int(z[f"{tag}_nb"])
+        blocks = [RB.init_resblock_params(100 * ord(tag) + i) for i in range(nb)]
+        wsum = sum(float(v.double().abs().sum()) for p in blocks for v in p.values())
+        assert abs(wsum - float(z[f"{tag}_wsum"])) <= 1e-9 * wsum, "seeded weights differ from the ones the fixture was made with"
+        yield tag, blocks, torch.from_numpy(z[f"{tag}_x"]), torch.from_numpy(z[f"{tag}_y"]), float(z[f"{tag}_res_scale"])
+
+
+def test_resblock_oracle_matches_golden():
+    """oracle/resblock_oracle.py reproduces the outputs the UNMODIFIED reference ResBlock chain produced (bit-exact)."""
+    from oracle import resblock_oracle as RB
+    n = 0
+    for tag, blocks, x, y, rs in _resblock_golden():
+        assert torch.equal(RB.chain_forward(blocks, x, rs), y), tag
+        n += 1
+    assert n == 2
+
+
+@pytest.mark.skipif(not R.available("DN_Gray"), reason="reference sources not present")
+def test_resblock_oracle_matches_reference():
+    """Live: the reference's own common.ResBlock (built as CES builds it, dagl.py:86-101) vs the oracle, torch.equal."""
+    import torch.nn as nn
+    from oracle import resblock_oracle as RB
+    common = R.load_task("DN_Gray").common
+    for prelu_n, rs in ((1, 1), (1, 0.1)):
+        blocks = [RB.init_resblock_params(7 + i, prelu_n) for i in range(2)]
+        seq = nn.Sequential(*[common.ResBlock(common.default_conv, n_feats=64, kernel_size=3, act=nn.PReLU(prelu_n), res_scale=rs)
+                              for _ in blocks]).eval()
+        for blk, p in zip(seq, blocks):
+            blk.load_state_dict(p)
+        x = torch.randn(1, 64, 11, 13, generator=torch.Generator().manual_seed(3))
+        with torch.no_grad():
+            assert torch.equal(seq(x), RB.chain_forward(blocks, x, rs))
+
+
+@pytest.mark.skipif(not R.available("DN_Gray"), reason="reference sources not present")
+def test_patch_resblocks_finds_every_reference_resblock_and_keeps_cpu_path():
+    """patch_reference(..., fuse_resblocks=True) rebinds the nn.Sequential containers that hold ResBlocks (RR.body: 16,
+    CES.RBS1 / RBS2: 4 + 4); with a CPU input the fused containers run the reference's own modules (bit-identical)."""
+    import dagl_b200
+    from dagl_b200 import resblock as DR
+    ref = R.load_task("DN_Gray")
+    torch.manual_seed(0)
+    net = ref.dagl.RR(R.rr_args("DN_Gray")).eval()
+    x = torch.randn(1, 64, 8, 8)
+    with torch.no_grad():
+        want = net.body[0](x).clone()
+        assert DR.patch_resblocks(net) == 24
+        assert sum(1 for m in net.modules() if DR.is_resblock(m)) == 24
+        got = net.body[0](x)
+        ces = net.body[8]
+        assert type(ces).__name__ == "CES"
+        y = x
+        for blk in ces.RBS1:                                   # the container's own modules, one by one
+            y = blk(y)
+        assert torch.equal(ces.RBS1(x), y)                     # the rebound Sequential.forward on a CPU input
+    assert torch.equal(got, want)
