@@ -262,9 +262,9 @@ def other_configs(ce, dev, flush, peaks):
     shape_line("cfg3/cfg5 head: CE.forward 1x64x512x512", 1, 512, 512, 5)
     torch.manual_seed(5)
     ces = dagl_b200.CES(in_channels=C_IN).to(dev).eval()
-    # the ResBlocks / 1x1 merges of CES are plain cuDNN convolutions under torch's defaults (TF32 allowed), as they are when the
-    # reference runs on this GPU; only the twelve heads are this repo's kernels
-    shape_line("CES.forward 1x64x64x64 (12 heads as 3 stage calls + 8 cuDNN ResBlocks)", 1, 64, 64, 20, fn=ces, heads=12)
+    # CES = twelve heads (3 stage calls) + RBS1 / RBS2 (two chains of four ResBlocks on the tcgen05 convolution kernel) + three
+    # 1x1 merge convolutions (cuDNN)
+    shape_line("CES.forward 1x64x64x64 (12 heads as 3 stage calls + 2 ResBlock chain calls)", 1, 64, 64, 20, fn=ces, heads=12)
     # the same forward captured in a CUDA graph by the caller (the library allocates nothing and never synchronises)
     try:
         xg = torch.randn(1, C_IN, 64, 64, generator=gen).to(dev)
@@ -283,6 +283,42 @@ def other_configs(ce, dev, flush, peaks):
         out.append({"workload": "CES.forward 1x64x64x64, CUDA graph", "error": str(e)[:200]})
     shape_line("CES.forward 64x64x72x72 (chop batch)", 64, 72, 72, 3, fn=ces, heads=12)
     shape_line("CES.forward 1x64x256x256 (direct)", 1, 256, 256, 5, fn=ces, heads=12)
+
+    # the callers either side of the graph blocks: a chain of four ResBlocks (CES.RBS1; common.py:59-79), this repo's tcgen05
+    # convolution (fp32-accurate) next to torch / cuDNN under its TF32 default and with TF32 off (what "fp32" means to cuDNN)
+    def chain_line(B, Hh, Ww, iters):
+        x = torch.randn(B, C_IN, Hh, Ww, generator=gen).to(dev)
+        seq = ces.RBS1
+        plain = lambda t: torch.nn.Sequential.forward(seq, t)                     # the container's own modules: cuDNN
+        rec = {"workload": f"4-ResBlock chain {B}x64x{Hh}x{Ww} (8 convolutions 64->64 3x3 + PReLU + residual)"}
+        with torch.no_grad():
+            rec["ms"] = time_call(lambda: seq(x), iters, flush)
+            rec["ms_cudnn_tf32"] = time_call(lambda: plain(x), iters, flush)
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                rec["ms_cudnn_fp32"] = time_call(lambda: plain(x), iters, flush)
+                ref = plain(x)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+            rec["rel_err_vs_cudnn_fp32"] = float((seq(x) - ref).abs().max() / ref.abs().max())
+        flops = 8 * 2.0 * B * Hh * Ww * 64 * 64 * 9
+        rec["tflops_alg"] = flops / (rec["ms"] * 1e-3) / 1e12
+        out.append(rec)
+
+    chain_line(1, 256, 256, 10)
+    chain_line(64, 72, 72, 5)
+    # the whole network (dagl.py:10-54; random init): head conv, 8 ResBlocks, CES, 8 ResBlocks, conv, tail conv, global skip
+    try:
+        torch.manual_seed(6)
+        rr = dagl_b200.RR().to(dev).eval()
+        xi = torch.rand(1, 1, 256, 256, generator=gen).to(dev)
+        with torch.no_grad():
+            ms = time_call(lambda: rr(xi), 5, flush)
+        out.append({"workload": "RR.forward 1x1x256x256 (BASELINE cfg2 shape, direct; 12 heads + 24 ResBlocks + 3 plain convolutions)", "ms": ms,
+                    "images_per_s": 1.0 / (ms * 1e-3)})
+    except Exception as e:                                            # a bench extra, never fatal
+        out.append({"workload": "RR.forward 1x1x256x256", "error": str(e)[:200]})
     return out
 
 

@@ -58,7 +58,7 @@ def wsum(net):
     return float(sum(v.double().abs().sum() for v in net.state_dict().values()))
 
 
-def build_rr(task, dev, trained=True, seed=None, fuse_stages=True):
+def build_rr(task, dev, trained=True, seed=None, fuse_stages=True, fuse_resblocks=True):
     """The unmodified reference network with its heads swapped for the CUDA head."""
     import dagl_b200
     ref = need_ref(task)
@@ -67,8 +67,9 @@ def build_rr(task, dev, trained=True, seed=None, fuse_stages=True):
     net = ref.dagl.RR(R.rr_args(task)).eval()
     if trained:
         net.load_state_dict(torch.load(R.checkpoint(task), map_location="cpu"))
-    n = dagl_b200.patch_reference(net, fuse_stages=fuse_stages)
+    n = dagl_b200.patch_reference(net, fuse_stages=fuse_stages, fuse_resblocks=fuse_resblocks)
     assert n == 12, n
+    assert any("_dagl_resblock_mode" in m.__dict__ for m in net.modules()) == fuse_resblocks
     assert all(type(m).__module__.startswith("dagl_b200") for m in net.modules() if type(m).__name__ == "CE")
     return net.to(dev)
 
@@ -109,6 +110,30 @@ def test_rr_cfg2_dn_gray_256_direct(dev):
     with torch.no_grad():
         out2 = net2(g["noisy"].to(dev))
     assert rel_err(out, out2) <= 1e-5
+
+
+def test_rr_mirror_cfg2_and_resblock_fusion(dev):
+    """dagl_b200.RR (the package's own assembly of dagl.py:10-54; no reference code at run time) loads the shipped
+    checkpoint and reproduces the reference output of BASELINE cfg2; and inside the unmodified reference RR the fused
+    ResBlock chains (tensor-core kernel) and the reference's own cuDNN fp32 ResBlocks give the same network output."""
+    import dagl_b200
+    ck = R.checkpoint("DN_Gray") if R.available("DN_Gray") else None
+    if ck is None:
+        pytest.skip("baseline/_ref/DN_Gray checkpoint not present")
+    g = load_npz("rr_cfg2_dn256.npz")
+    net = dagl_b200.RR().eval()
+    net.load_state_dict(torch.load(ck, map_location="cpu"))
+    net = net.to(dev)
+    with torch.no_grad():
+        out = net(g["noisy"].to(dev))
+    assert dagl_b200._lib.lib().dagl_last_impl().decode() != "none"
+    check_network(out.cpu(), g["out"], g["noisy"])
+    ref_net = build_rr("DN_Gray", dev, fuse_resblocks=False)
+    with torch.no_grad():
+        out_unfused = ref_net(g["noisy"].to(dev))
+    e = rel_err(out, out_unfused)
+    print(f"   fused ResBlock chains vs cuDNN fp32 ResBlocks, network output: {e:.2e}")
+    assert e <= 2e-5
 
 
 def test_rr_cfg2_through_reference_wrapper_chop(dev):
