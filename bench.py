@@ -289,7 +289,10 @@ def other_configs(ce, dev, flush, peaks):
     def chain_line(B, Hh, Ww, iters):
         x = torch.randn(B, C_IN, Hh, Ww, generator=gen).to(dev)
         seq = ces.RBS1
-        plain = lambda t: torch.nn.Sequential.forward(seq, t)                     # the container's own modules: cuDNN
+        def plain(t):                                                             # the reference's ResBlock.forward (common.py:75-79) on cuDNN
+            for blk in seq:
+                t = blk.body(t).mul(blk.res_scale) + t
+            return t
         rec = {"workload": f"4-ResBlock chain {B}x64x{Hh}x{Ww} (8 convolutions 64->64 3x3 + PReLU + residual)"}
         with torch.no_grad():
             rec["ms"] = time_call(lambda: seq(x), iters, flush)

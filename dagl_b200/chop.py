@@ -115,6 +115,28 @@ def forward_x8(model: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor) -
     return torch.stack(outs, dim=0).mean(dim=0)
 
 
+def forward_x8_flips(forward_function: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """``Model.forward_x8`` of the Demosaic / DN_Real wrappers (Demosaic/model/__init__.py:265-299), the ``self_ensemble``
+    branch of ``Model.forward`` (:107-114): the 8 inputs are built by successively appending the W-flip ('v'), H-flip ('h')
+    and transpose ('t') of everything so far; output i is un-transposed if i > 3, un-H-flipped if i % 4 > 1, un-W-flipped
+    if i is odd; the result is the mean over the concatenated batch axis (so, as in the reference, one image per call).
+    ``forward_function`` is the network or ``lambda t: forward_chop(net, t, shave_size_max=12)``."""
+    tf = {"v": lambda t: torch.flip(t, dims=(3,)), "h": lambda t: torch.flip(t, dims=(2,)),
+          "t": lambda t: t.transpose(2, 3)}
+    lr = [x]
+    for op in ("v", "h", "t"):
+        lr.extend([tf[op](t).contiguous() for t in lr])
+    sr = [forward_function(t) for t in lr]
+    for i in range(len(sr)):
+        if i > 3:
+            sr[i] = tf["t"](sr[i])
+        if i % 4 > 1:
+            sr[i] = tf["h"](sr[i])
+        if (i % 4) % 2 == 1:
+            sr[i] = tf["v"](sr[i])
+    return torch.cat(sr, dim=0).mean(dim=0, keepdim=True)
+
+
 # ---- the scheduler ---------------------------------------------------------------------------------
 def forward_chop(model: Callable[[torch.Tensor], torch.Tensor], x: torch.Tensor, ensemble: bool = False,
                  shave_size_max: int = 24, shave_scale: int = 4, min_size: int = 10000,

@@ -157,3 +157,29 @@ def test_chop_over_cuda_ces_equals_tile_by_tile():
     # cuDNN picks other algorithms for the ResBlock / 1x1 convs at another batch size; those ~1e-6 differences move a few
     # threshold-tie neighbours in the following heads, i.e. the usual CES-level bar applies.
     assert (y_batched - y_single).abs().max().item() <= 4e-3 * y_single.abs().max().item()
+
+
+# ---- Demosaic / DN_Real wrapper variants (Demosaic/model/__init__.py:107-114, 179-235, 265-299) ------------------
+def test_demosaic_wrapper_shave12_matches_reference():
+    """forward_chop with shave_size_max = 12 against outputs of the UNMODIFIED Demosaic wrapper
+    (oracle/make_golden_chop_demosaic.py), bit-exact incl. a batch of two 3-colour images."""
+    z = load_npz("chop_probe_demosaic.npz")
+    for i in range(2):
+        x, yref = z[f"x{i}"], z[f"y{i}"]
+        for tb in (None, 3):
+            y = chop.forward_chop(probe_net, x, shave_size_max=12, tile_batch=tb, distributed=False)
+            assert torch.equal(y, yref), (i, tb, float((y - yref).abs().max()))
+        # the DN_Gray value gives a different tiling: the parameter is what distinguishes the two wrappers
+        assert not torch.equal(chop.forward_chop(probe_net, x, shave_size_max=24, distributed=False), yref)
+
+
+def test_demosaic_wrapper_self_ensemble_matches_reference():
+    """The wrapper's own 8-fold ensemble (Model.forward_x8: flip / flip / transpose lists, mean over the batch axis) around
+    forward_chop, and around the bare network."""
+    z = load_npz("chop_probe_demosaic.npz")
+    x = z["xe"]
+    y = chop.forward_x8_flips(lambda t: chop.forward_chop(probe_net, t, shave_size_max=12, distributed=False), x)
+    assert y.shape == z["ye"].shape
+    assert torch.allclose(y, z["ye"], rtol=0, atol=2e-6 * float(z["ye"].abs().max()))    # mean of 8: summation order only
+    y2 = chop.forward_x8_flips(probe_net, x[:, :, :40, :52])
+    assert torch.allclose(y2, z["ye_direct"], rtol=0, atol=2e-6 * float(z["ye_direct"].abs().max()))
