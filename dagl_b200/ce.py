@@ -400,6 +400,19 @@ def _ces_stage_forward(self, x):
     return out
 
 
+_FUSED_CES = {}
+
+
+def _fused_ces_class(cls):
+    """A cached subclass of the reference's own CES class whose ``forward`` makes stage calls.  The instance is switched to
+    it in place (same object, sub-modules, state_dict); a class-level override, unlike an instance-bound method, survives
+    ``nn.DataParallel``'s module replication (the reference wrapper's multi-GPU path, model/__init__.py:101-103)."""
+    if cls not in _FUSED_CES:
+        _FUSED_CES[cls] = type(cls.__name__, (cls,), {"forward": _ces_stage_forward, "__module__": cls.__module__,
+                                                      "_dagl_fused_stages": True})
+    return _FUSED_CES[cls]
+
+
 def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = True, fuse_resblocks: bool = True) -> int:
     """Replace every reference ``CE`` instance inside ``module`` (e.g. an ``RR``
     or ``CES`` built by the unmodified reference code) with a ``dagl_b200.CE``
@@ -410,7 +423,6 @@ def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = T
 
     ``fuse_resblocks``: also route every run of reference ``ResBlock``s inside an ``nn.Sequential`` (``CES.RBS1`` / ``RBS2``,
     ``RR.body``; common.py:59-79) through the tensor-core chain kernel (``dagl_b200.resblock``; fp32-accurate)."""
-    import types
     n = 0
     for parent in module.modules():
         for name, child in list(parent.named_children()):
@@ -427,9 +439,9 @@ def patch_reference(module: nn.Module, impl: str = "auto", fuse_stages: bool = T
     if fuse_stages:
         heads = [f"c{s}_{h}" for s in (1, 2, 3) for h in (1, 2, 3, 4)]
         for m in module.modules():
-            if type(m).__name__ == "CES" and not isinstance(m, CES) and \
+            if type(m).__name__ == "CES" and not isinstance(m, CES) and not getattr(type(m), "_dagl_fused_stages", False) and \
                     all(isinstance(getattr(m, h, None), CE) for h in heads) and hasattr(m, "RBS1") and hasattr(m, "c3_c"):
-                m.forward = types.MethodType(_ces_stage_forward, m)
+                m.__class__ = _fused_ces_class(type(m))
     if fuse_resblocks:
         patch_resblocks(module)
     return n

@@ -11,7 +11,6 @@ The fused path is the inference path (no autograd graph): when a gradient is req
 from __future__ import annotations
 
 import ctypes as C
-import types
 from typing import Sequence
 
 import torch
@@ -133,13 +132,43 @@ def _sequential_forward(self, x):
     return x
 
 
+class ChainSequential(nn.Sequential):
+    """``nn.Sequential`` whose runs of consecutive ResBlocks are chain calls.  Containers are switched to this class in
+    place (``seq.__class__ = ChainSequential``): same object, same sub-modules, same state_dict; being a class-level
+    override it also survives ``nn.DataParallel``'s module replication (an instance-bound ``forward`` would not: the
+    replica would call the original's sub-modules)."""
+    _dagl_resblock_mode = "auto"
+
+    def forward(self, x):
+        return _sequential_forward(self, x)
+
+
+_FUSED_SUBCLASS = {}
+
+
+def _chain_class(cls):
+    """ChainSequential for plain containers, a cached dynamic subclass for user-defined Sequential subclasses."""
+    if cls is nn.Sequential:
+        return ChainSequential
+    if cls not in _FUSED_SUBCLASS:
+        _FUSED_SUBCLASS[cls] = type(cls.__name__, (cls,), {"forward": _sequential_forward, "__module__": cls.__module__,
+                                                           "_dagl_resblock_mode": "auto", "_dagl_chain": True})
+    return _FUSED_SUBCLASS[cls]
+
+
+def is_fused(seq: nn.Module) -> bool:
+    return isinstance(seq, ChainSequential) or getattr(type(seq), "_dagl_chain", False)
+
+
 def fuse_sequential(seq: nn.Sequential, mode: str = "auto") -> bool:
-    """Rebind ``seq.forward`` (an ``nn.Sequential`` that holds ResBlocks) to the chained version.  Same sub-modules and
-    parameters; returns whether anything was fused."""
+    """Switch ``seq`` (an ``nn.Sequential`` that holds ResBlocks) to the chained forward, in place.  Same sub-modules and
+    parameters; returns whether the container holds anything to fuse."""
     if not isinstance(seq, nn.Sequential) or not any(is_resblock(m) for m in seq):
         return False
-    seq._dagl_resblock_mode = mode
-    seq.forward = types.MethodType(_sequential_forward, seq)
+    if not is_fused(seq):
+        seq.__class__ = _chain_class(type(seq))
+    if mode != "auto":
+        seq._dagl_resblock_mode = mode
     return True
 
 

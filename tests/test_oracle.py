@@ -249,5 +249,16 @@ def test_patch_resblocks_finds_every_reference_resblock_and_keeps_cpu_path():
         y = x
         for blk in ces.RBS1:                                   # the container's own modules, one by one
             y = blk(y)
-        assert torch.equal(ces.RBS1(x), y)                     # the rebound Sequential.forward on a CPU input
+        assert torch.equal(ces.RBS1(x), y)                     # the chained Sequential.forward on a CPU input
+        # the overrides are class-level, so nn.DataParallel's replication (reference wrapper, model/__init__.py:101-103)
+        # keeps them AND binds them to the replica's own sub-modules
+        dagl_b200.patch_reference(net, fuse_resblocks=True)
+        rep_ces = ces._replicate_for_data_parallel()
+        rep_seq = ces.RBS1._replicate_for_data_parallel()
+        assert type(rep_ces).forward is type(ces).forward and getattr(type(rep_ces), "_dagl_fused_stages", False)
+        assert DR.is_fused(rep_seq) and "forward" not in rep_seq.__dict__ and "forward" not in rep_ces.__dict__
+        assert type(ces).__name__ == "CES" and isinstance(ces, ref.dagl.CES)
+        n_before = len(net.state_dict())
+        dagl_b200.patch_reference(net)                         # idempotent: no second subclass layer
+        assert type(ces).__mro__[1] is ref.dagl.CES and len(net.state_dict()) == n_before
     assert torch.equal(got, want)

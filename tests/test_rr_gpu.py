@@ -69,7 +69,8 @@ def build_rr(task, dev, trained=True, seed=None, fuse_stages=True, fuse_resblock
         net.load_state_dict(torch.load(R.checkpoint(task), map_location="cpu"))
     n = dagl_b200.patch_reference(net, fuse_stages=fuse_stages, fuse_resblocks=fuse_resblocks)
     assert n == 12, n
-    assert any("_dagl_resblock_mode" in m.__dict__ for m in net.modules()) == fuse_resblocks
+    from dagl_b200.resblock import is_fused
+    assert any(is_fused(m) for m in net.modules()) == fuse_resblocks
     assert all(type(m).__module__.startswith("dagl_b200") for m in net.modules() if type(m).__name__ == "CE")
     return net.to(dev)
 
