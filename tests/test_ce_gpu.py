@@ -288,8 +288,12 @@ def test_ces_caller_row(dev, impl):
             y = ces(x.to(dev))
     finally:
         torch.backends.cudnn.allow_tf32 = prev
-    # 12 heads in 3 dependent stages: the per-head error (<= REL_TOL, typically 4e-4 for tc) compounds
-    assert rel_err(y.cpu(), yref) <= (REL_TOL if impl == "simt" else 4 * REL_TOL)
+    # 12 heads in 3 dependent stages: the per-head error (<= REL_TOL, typically 4e-4 for tc) compounds; a random-init CES is
+    # the hard case (its stage-2/3 logits are huge: near one-hot softmax rows); the trained module is held to REL_TOL in
+    # tests/test_rr_gpu.py::test_trained_ces_module_vs_oracle
+    e = rel_err(y.cpu(), yref)
+    print(f"   CES caller row [{impl}]: rel err {e:.2e}")
+    assert e <= (REL_TOL if impl == "simt" else 2.5 * REL_TOL)      # measured: simt 9.2e-5, tc / tc4 1.8e-3
 
 
 @pytest.mark.parametrize("impl", ["tc", "tc4"])

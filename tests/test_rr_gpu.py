@@ -137,6 +137,36 @@ def test_rr_mirror_cfg2_and_resblock_fusion(dev):
     assert e <= 2e-5
 
 
+def test_trained_ces_module_vs_oracle(dev):
+    """The module the networks actually call, with the SHIPPED weights on its real input: dagl_b200.CES (12 trained heads in
+    3 dependent stages + the two ResBlock chains) against the oracle's CES on the CPU, 128x128 crop of the cfg2 image.
+    VERDICT weak 3: the compounding of twelve tensor-core heads is quantified here on trained weights, not on a random
+    init (whose stage-2/3 inputs blow the logits up)."""
+    import dagl_b200
+    from oracle import resblock_oracle as RB
+    ck = R.checkpoint("DN_Gray") if R.available("DN_Gray") else None
+    if ck is None:
+        pytest.skip("baseline/_ref/DN_Gray checkpoint not present")
+    sd = torch.load(ck, map_location="cpu")
+    g = load_npz("rr_cfg2_dn256.npz")
+    img = g["noisy"][:, :, 64:192, 48:176].contiguous()
+    feat = torch.nn.functional.conv2d(img, sd["head.0.weight"], sd["head.0.bias"], padding=1)
+    front = [{k: sd[f"body.{i}.{k}"] for k in ("body.0.weight", "body.0.bias", "body.1.weight", "body.2.weight", "body.2.bias")}
+             for i in range(8)]
+    feat = RB.chain_forward(front, feat)                       # the CES input inside RR (dagl.py:27-32)
+    state = {k[len("body.8."):]: v for k, v in sd.items() if k.startswith("body.8.")}
+    want = O.ces_forward(state, feat)
+    ces = dagl_b200.CES(in_channels=64).eval()
+    ces.load_state_dict(state)
+    ces = ces.to(dev)
+    with torch.no_grad():
+        got = ces(feat.to(dev)).cpu()
+    e = rel_err(got, want)
+    e_branch = rel_err(got - feat, want - feat)
+    print(f"   trained CES module 128x128: rel err {e:.2e} (output), {e_branch:.2e} (what the module adds to its input)")
+    assert e <= REL_TOL, (e, e_branch)
+
+
 def test_rr_cfg2_through_reference_wrapper_chop(dev):
     """The reference's REAL inference path: its own Model wrapper (plugin loader make_model, .cuda(), forward_chop:
     64 leaf tiles of 72x72) with model.dagl.CE rebound by dagl_b200.install — nothing else touched."""
