@@ -10,6 +10,8 @@
 // pixels is then a pixel- and channel-shifted view of a 144-record row segment held in smem, and a whole halo row (all 64
 // channels of one part) arrives with ONE bulk copy of 18 KB: 6 copies per tile (a copy costs ~300 cycles to issue whatever
 // its size; the first version used the 16-channel-group images of featmap_tc.cu, 24 copies per tile, and was bound by that).
+// Tiles are walked in RUNS down 128-wide strips where the image width fills them (see CvGeom): inside a run every tile
+// needs ONE new halo row, the ring keeps the other two (a third of the L2 -> SM traffic of independent tiles).
 // The epilogue of a convolution writes the NEXT convolution's images directly (bias, PReLU or residual add fused), so inside
 // a chain no fp32 activation is re-packed and no elementwise kernel runs; the fp32 NCHW tensor is only written at ResBlock
 // outputs (it is the exact fp32 residual of the next block and the chain's result).
@@ -27,6 +29,7 @@
 //   PAIR = false  one CTA computes 32 output channels of one tile (even CTAs channels 0-31, odd CTAs 32-63).  A/B aid.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_utils.cuh"
 
@@ -45,25 +48,28 @@ constexpr int CV_VTAPS = 9 * CV_GROUPS;              // 36 virtual taps of K = 1
 constexpr int CV_WTAP_BYTES = 2 * CV_HALF * 32;      // 2048: K-major no-swizzle [2 k-chunks][64 rows: hi 32 | lo 32][16 B]
 constexpr int CV_WHALF_BYTES = CV_VTAPS * CV_WTAP_BYTES;                 // 73728
 constexpr int CV_STG_BYTES = 2 * CV_M * CV_REC;      // pair kernel: per epilogue group 128 output records (16 KB) staged for a bulk store
-// smem: [halo ring: STAGES x (hi | lo) rows][weights of 32 output channels][pair: output staging][barriers, bias, slope]
-template <bool PAIR> struct CvSmem {
-  static constexpr int STAGES = PAIR ? 3 : 4;        // ring over (tile, ky)
-  static constexpr int A = 0;
-  static constexpr int W = STAGES * CV_STAGE_BYTES;
-  static constexpr int STG = W + CV_WHALF_BYTES;
-  static constexpr int BAR = STG + (PAIR ? CV_STG_BYTES : 0);
-  static constexpr int PAR = BAR + 256;              // bias [64] | slope [64]
-  static constexpr int TOTAL = PAR + 512;
-  static_assert(W % 1024 == 0 && STG % 1024 == 0 && CV_SEG_BYTES % 1024 == 0, "swizzle pattern alignment");
-  static_assert(TOTAL <= 227 * 1024, "smem budget");
-};
+// smem: [halo ring: nst x (hi | lo) rows][weights of 32 output channels][pair / flat tiles: output staging][barriers, bias, slope]
+// nst = 4 stages, or 3 stages + the 32 KB output staging of the pair kernel's bulk stores
+constexpr int CV_SM_BAR = 4 * CV_STAGE_BYTES + CV_WHALF_BYTES;          // 221184 (>= 3 stages + weights + staging = 217088)
+constexpr int CV_SM_PAR = CV_SM_BAR + 256;                              // bias [64] | slope [64]
+constexpr int CV_SM_TOTAL = CV_SM_PAR + 512;
+static_assert(CV_SEG_BYTES % 1024 == 0 && CV_STAGE_BYTES % 1024 == 0 && CV_WHALF_BYTES % 1024 == 0, "swizzle pattern alignment");
+static_assert(3 * CV_STAGE_BYTES + CV_WHALF_BYTES + CV_STG_BYTES <= CV_SM_BAR, "staging fits below the barriers");
+static_assert(CV_SM_TOTAL <= 227 * 1024, "smem budget");
 constexpr int CV_THREADS = 320;                      // warp 0 loads, warp 1 issues (or relays), warps 2-5 / 6-9: two epilogue groups
 constexpr int CV_PADK = 3;                           // frame of the packed images (shared with featmap_tc.cu / embed_tc.cu)
 #ifndef CV_EXP
 #define CV_EXP 0      // development experiments (wrong results): 1 no x_lo MMA, 2 no epilogue stores, 4 no halo copies, 8 no MMAs
 #endif
 
-struct CvGeom { int B, H, W, Wp, NkP, ntile, ntile2, NPG, Npix; };
+// Work decomposition.  A RUN is a column of `RL` vertically adjacent tiles (tile i = 128 pixel slots starting at
+// p0 + i Wp): tile i needs halo rows i, i+1, i+2 of the run's RL + 2 rows, so inside a run every tile loads ONE new row
+// and the ring keeps the other two.
+//   strip = 0 ("flat")  runs of one tile, tiles = consecutive 128-slot ranges of the padded-flat enumeration (every tile
+//                        loads its three rows).  For narrow images (chop leaves: W = 72 -> 1.6 image rows per tile).
+//   strip = 1            tile (y, c) = pixels (y, 128 c .. 128 c + 127); runs walk down a strip.  For images whose width
+//                        fills the 128-wide strips (W/128 rounded up wastes < 20 %): a third of the L2 -> SM traffic.
+struct CvGeom { int B, H, W, Wp, NkP, ntile, ntile2, NPG, Npix, strip, nstrip, RL, nyb, nst, staged; };
 static CvGeom cv_geom(int B, int H, int W) {
   CvGeom e;
   e.B = B; e.H = H; e.W = W; e.Npix = H * W;
@@ -74,7 +80,28 @@ static CvGeom cv_geom(int B, int H, int W) {
   const int np = (H + 2 * CV_PADK) * e.Wp;
   const int need = CV_M * e.ntile2 + 2 * CV_PADK * e.Wp + CV_SEG_PIX + 8;
   e.NPG = ((np > need ? np : need) + 7) & ~7;
+  e.nstrip = (W + CV_M - 1) / CV_M;
+  e.strip = (10 * W >= 8 * CV_M * e.nstrip && H >= 8) ? 1 : 0;
+  e.RL = 1; e.nyb = H; e.nst = 4; e.staged = 0;      // set per launch (cv_plan)
   return e;
+}
+// per-launch plan: rows per run, ring stages, output staging
+static void cv_plan(CvGeom& e, bool pair, int workers, int force_flat) {
+  if (force_flat) e.strip = 0;
+  if (!e.strip) {
+    e.RL = 1; e.nyb = 0; e.nst = pair ? 3 : 4; e.staged = pair ? 1 : 0;
+    return;
+  }
+  double best = 1e30;
+  for (int rl = 2; rl <= 64 && rl <= e.H; ++rl) {
+    const long long nruns = (long long)e.B * e.nstrip * ((e.H + rl - 1) / rl);
+    const long long items = pair ? (nruns + 1) / 2 : nruns;
+    const long long waves = (items + workers - 1) / workers;
+    const double cost = (double)waves * (rl + 3.0);                     // + 3: the run's two extra rows and its pipeline fill
+    if (cost <= best) { best = cost; e.RL = rl; }
+  }
+  e.nyb = (e.H + e.RL - 1) / e.RL;
+  e.nst = 4; e.staged = 0;
 }
 static inline size_t cv_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline size_t cv_image_bytes(const CvGeom& e) { return cv_align((size_t)e.B * 2 * e.NPG * CV_REC); }
@@ -258,56 +285,90 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Persistent.  Accumulator set s (two sets alternate; epilogue group s drains set s, so the epilogue of an item overlaps the
+// border records of a packed image that no convolution epilogue writes in strip mode (frame rows 0-2 and H+3.., the
+// columns left and right of the pixels): zero, once per chain call, for the rotating output images
+__global__ void __launch_bounds__(256)
+cv_zero_borders_kernel(CvGeom eg, uint8_t* __restrict__ img_a, uint8_t* __restrict__ img_b) {
+  pdl_prologue();
+  const int rec = blockIdx.x * 256 + threadIdx.x;
+  if (rec >= eg.NPG) return;
+  const int R = rec / eg.Wp, Cc = rec % eg.Wp;
+  if (R >= CV_PADK && R < eg.H + CV_PADK && Cc >= CV_PADK && Cc < eg.W + CV_PADK) return;   // a pixel
+  const int img = blockIdx.y >> 1, part = blockIdx.y & 1;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const size_t off = (((size_t)img * 2 + part) * (size_t)eg.NPG + rec) * CV_REC;
+  uint4* da = reinterpret_cast<uint4*>(img_a + off);
+  uint4* db = reinterpret_cast<uint4*>(img_b + off);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { da[k] = z; db[k] = z; }
+}
+
+// Persistent.  Accumulator set s (two sets alternate; epilogue group s drains set s, so the epilogue of a tile overlaps the
 // MMAs and the epilogue of the next):
 //   PAIR   columns s*128 + [0,128): x_hi . [W_hi | W_lo] = [main | cross] of CTA 0's channels (0-31), then of CTA 1's (32-63);
 //          x_lo . W_hi (N = 64: channels 0-31 from CTA 0, 32-63 from CTA 1) accumulates onto columns [32,96), i.e. onto the
 //          cross columns of channels 0-31 and the main columns of 32-63: the epilogue adds main + cross per channel anyway
 //   !PAIR  columns s*64 + [0,64): [main | cross] of this CTA's 32 channels; x_lo . W_hi accumulates onto the cross columns
-// Work: CTA (or pair) k of n walks items k, k + n, ...; item = (image, tile) (pair: (image, tile pair), CTA r takes tile 2i + r).
+// Work: CTA (or pair) k of n walks items k, k + n, ...; item = one run (pair: two runs, CTA r takes run 2 i + r); see CvGeom.
+// Ring: halo row j of a run sits at ring position n0 + j (stage = position % nst); tile i reads positions n0 + i .. + 2 and
+// frees position n0 + i (the last tile of a run frees all three).
 // Everything that does not depend on the previous kernel of the stream (barriers, TMEM, the weights, bias, slope) is set up
 // BEFORE griddepcontrol.wait, i.e. while the previous convolution is still running (programmatic dependent launch).
 template <bool PAIR>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvArgs a) {
-  using SM = CvSmem<PAIR>;
-  constexpr int STAGES = SM::STAGES;
+  constexpr int MAXST = 4;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CV_SM_BAR);
   uint64_t* w_full = bars + 0;                    // weights resident
-  uint64_t* a_full = bars + 1;                    // [STAGES] halo row (hi | lo) resident
-  uint64_t* a_empty = a_full + STAGES;            // [STAGES] the MMAs that read it have completed
-  uint64_t* pa_full = a_empty + STAGES;           // [STAGES] pair leader: the peer's halo row is resident
-  uint64_t* d_full = pa_full + STAGES;            // [2] accumulator set complete
+  uint64_t* a_full = bars + 1;                    // [nst] halo row (hi | lo) resident
+  uint64_t* a_empty = a_full + MAXST;             // [nst] the MMAs that read it have completed
+  uint64_t* pa_full = a_empty + MAXST;            // [nst] pair leader: the peer's halo row is resident
+  uint64_t* d_full = pa_full + MAXST;             // [2] accumulator set complete
   uint64_t* d_empty = d_full + 2;                 // [2] accumulator set drained: 4 arrivals (epilogue warps); pair leader: 8
   uint64_t* pw_full = d_empty + 2;                // pair leader: the peer's weights are resident
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pw_full + 1);
   float* bound_s = reinterpret_cast<float*>(pw_full + 2);    // [0] max(1, max|slope|)
-  float* bias_s = reinterpret_cast<float*>(smem + SM::PAR);  // [64]
-  float* slope_s = bias_s + CV_C;                            // [64]
+  float* bias_s = reinterpret_cast<float*>(smem + CV_SM_PAR);  // [64]
+  float* slope_s = bias_s + CV_C;                              // [64]
 
   constexpr uint32_t TCOLS = PAIR ? 256 : 128;
   constexpr uint32_t SET = PAIR ? 128 : 64, D2OFF = 32;
+  const uint32_t nst = (uint32_t)eg.nst;
+  const int sm_w = eg.nst * CV_STAGE_BYTES, sm_stg = sm_w + CV_WHALF_BYTES;
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const uint32_t rank = PAIR ? cluster_ctarank() : (blockIdx.x & 1u);       // = the channel half whose weights this CTA holds
-  const int ntp = eg.ntile2 / 2;
-  const int nwork = PAIR ? eg.B * ntp : eg.B * eg.ntile;
+  const int RL = eg.RL;
+  const int nruns = eg.strip ? eg.B * eg.nstrip * eg.nyb : (PAIR ? eg.B * eg.ntile2 : eg.B * eg.ntile);
+  const int nwork = PAIR ? (nruns + 1) / 2 : nruns;
   const int w0 = (int)(blockIdx.x >> 1), wstep = (int)(gridDim.x >> 1);
-  auto decode = [&](int w, int& img, int& tile) {
-    if (PAIR) { img = w / ntp; tile = 2 * (w % ntp) + (int)rank; }
-    else { img = w / eg.ntile; tile = w % eg.ntile; }
+  // item -> this CTA's run: image, first pixel slot p0, first image row y0 (strip), dummy = nothing to write
+  auto decode = [&](int w, int& img, int& p0, int& y0, bool& dummy) {
+    int q = PAIR ? 2 * w + (int)rank : w;
+    dummy = q >= nruns;
+    if (dummy) q = nruns - 1;
+    if (eg.strip) {
+      const int per_img = eg.nstrip * eg.nyb;
+      img = q / per_img;
+      const int c = (q / eg.nyb) % eg.nstrip;
+      y0 = (q % eg.nyb) * RL;
+      p0 = y0 * eg.Wp + c * CV_M;
+    } else {
+      const int nt = PAIR ? eg.ntile2 : eg.ntile;
+      img = q / nt; p0 = (q % nt) * CV_M; y0 = 0;
+    }
   };
 
   if (tid == 0) {
     mbar_init(w_full, 1);
     mbar_init(pw_full, 1);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(pa_full + i, 1); }
+    for (int i = 0; i < MAXST; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(pa_full + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, PAIR ? 8 : 4); }
     mbar_init_fence();
     // the weights are constant inputs: fetch them before waiting for the previous kernel
     mbar_arrive_expect_tx(w_full, CV_WHALF_BYTES);
-    bulk_g2s(smem + SM::W, a.wpack + (size_t)rank * CV_WHALF_BYTES, CV_WHALF_BYTES, w_full);
+    bulk_g2s(smem + sm_w, a.wpack + (size_t)rank * CV_WHALF_BYTES, CV_WHALF_BYTES, w_full);
     float sm = 1.f;
     if (a.slope != nullptr)
       for (int i = 0; i < a.slope_n; ++i) sm = fmaxf(sm, fabsf(__ldg(a.slope + i)));
@@ -330,26 +391,30 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
   if (warp == 0) {
     // ===================== producer: lanes 0 / 1 copy the hi / lo part of a halo row =========
     const int lane = tid & 31;
-    uint32_t n = 0;                                        // ring position: stage n % STAGES, use n / STAGES
+    // ring position -> (stage, phase) kept incrementally: these single-thread loops are the critical path of the kernel and a
+    // division by the run-time stage count costs more than the copy it guards
+    uint32_t s = 0, ph = 0;
     for (int w = w0; w < nwork; w += wstep) {
-      int img, tile;
-      decode(w, img, tile);
-      const int p0 = tile * CV_M;
+      int img, p0, y0; bool dummy;
+      decode(w, img, p0, y0, dummy);
 #pragma unroll 1
-      for (int ky = 0; ky < 3; ++ky, ++n) {
-        const uint32_t s = n % STAGES, use = n / STAGES;
+      for (int j = 0; j < RL + 2; ++j) {
         if (lane == 0) {
-          mbar_wait(a_empty + s, (use & 1u) ^ 1u);
-          if ((CV_EXP & 4) && use > 0) mbar_arrive(a_full + s); else
+          mbar_wait(a_empty + s, ph ^ 1u);
           mbar_arrive_expect_tx(a_full + s, CV_STAGE_BYTES);
         }
         __syncwarp();
-        if (lane < 2 && !((CV_EXP & 4) && use > 0)) {
+        if (lane < 2) {
           const uint8_t* src = a.in_img + ((size_t)img * 2 + lane) * (size_t)eg.NPG * CV_REC;
-          const int first = (p0 + (ky + 2) * eg.Wp) & ~7;               // 3x3 / pad 1 inside the pad-3 frame: rows y+ky+2
-          bulk_g2s(smem + SM::A + s * CV_STAGE_BYTES + lane * CV_SEG_BYTES, src + (size_t)first * CV_REC, CV_SEG_BYTES, a_full + s);
+          // 3x3 / pad 1 inside the pad-3 frame: halo row j of the run = frame row (first image row) + j + 2; rows below the
+          // image (runs padded to RL tiles) are clamped to a border row: loaded, never used by a valid pixel
+          int start = p0 + (j + 2) * eg.Wp;
+          if (eg.strip && y0 + j + 2 > eg.H + 4) start = p0 + (eg.H + 4 - y0) * eg.Wp;
+          const int first = start & ~7;
+          bulk_g2s(smem + s * CV_STAGE_BYTES + lane * CV_SEG_BYTES, src + (size_t)first * CV_REC, CV_SEG_BYTES, a_full + s);
         }
         __syncwarp();
+        if (++s == nst) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -357,74 +422,96 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
       // ===================== peer relay: tell the leader when this CTA's operands are resident ==========
       if (elect_one()) {
         const uint32_t l_pw = mapa(smem_u32(pw_full), 0);
-        uint32_t n = 0;
+        uint32_t s = 0, ph = 0;
+        bool first = true;
         for (int w = w0; w < nwork; w += wstep) {
-          if (n == 0) { mbar_wait(w_full, 0); fence_proxy_async_all(); mbar_arrive_cluster(l_pw); }
-          for (int ky = 0; ky < 3; ++ky, ++n) {
-            const uint32_t s = n % STAGES, use = n / STAGES;
-            mbar_wait(a_full + s, use & 1u);
+          if (first) { mbar_wait(w_full, 0); fence_proxy_async_all(); mbar_arrive_cluster(l_pw); first = false; }
+          for (int j = 0; j < RL + 2; ++j) {
+            mbar_wait(a_full + s, ph);
             fence_proxy_async_all();
             mbar_arrive_cluster(mapa(smem_u32(pa_full + s), 0));
+            if (++s == nst) { s = 0; ph ^= 1u; }
           }
         }
       }
     } else if (elect_one()) {
       // ===================== MMA issuer =====================
-      const uint32_t abase = smem_u32(smem + SM::A), wbase = smem_u32(smem + SM::W);
+      const uint32_t abase = smem_u32(smem), wbase = smem_u32(smem + sm_w);
       constexpr uint32_t id1 = PAIR ? instr_desc(256, 128, FMT_F16, FMT_F16, 0, 0) : instr_desc(CV_M, 64, FMT_F16, FMT_F16, 0, 0);
       constexpr uint32_t id2 = PAIR ? instr_desc(256, 64, FMT_F16, FMT_F16, 0, 0) : instr_desc(CV_M, 32, FMT_F16, FMT_F16, 0, 0);
-      uint32_t n = 0;
-      int it = 0;
-      for (int w = w0; w < nwork; w += wstep, ++it) {
-        int img, tile;
-        decode(w, img, tile);
-        // the leader's tile fixes the pixel shift; the peer's tile is 128 slots further: same (p0 + row offset) & 7
-        const int p0 = tile * CV_M, ab = it & 1;
-        const uint32_t d1 = tbase + ab * SET, d2 = d1 + D2OFF;
+      uint32_t sb = 0;                                     // stage of the current tile's first row
+      uint32_t sw_ = 0, phw = 0;                           // next row to wait for: stage, phase
+      int ahead = 0;                                       // rows already waited for beyond the current tile's first row
+      int it = 0;                                          // tile counter: accumulator set it & 1
+      for (int w = w0; w < nwork; w += wstep) {
+        int img, p0, y0; bool dummy;
+        decode(w, img, p0, y0, dummy);
+        // the leader's run fixes the pixel shift; the peer's run starts a multiple of 8 slots away: same (p0 & 7)
+        const int off = (p0 & 7) + 2;
         if (it == 0) {
           mbar_wait(w_full, 0);
           if (PAIR) mbar_wait_cluster(pw_full, 0);
         }
-        mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        tc_fence_after();
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky, ++n) {
-          const uint32_t s = n % STAGES, use = n / STAGES;
-          mbar_wait(a_full + s, use & 1u);
-          if (PAIR) mbar_wait_cluster(pa_full + s, use & 1u);
+        for (int i = 0; i < RL; ++i, ++it) {
+          const int ab = it & 1;
+          const uint32_t d1 = tbase + ab * SET, d2 = d1 + D2OFF;
+          mbar_wait(d_empty + ab, ((uint32_t)(it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const int off = ((p0 + (ky + 2) * eg.Wp) & 7) + 2;
-          const uint32_t row_hi = abase + s * CV_STAGE_BYTES + off * CV_REC, row_lo = row_hi + CV_SEG_BYTES;
+          const bool last = i == RL - 1;
+#pragma unroll 1
+          for (int ky = 0; ky < 3; ++ky) {
+            uint32_t s = sb + (uint32_t)ky;
+            if (s >= nst) s -= nst;
+            // rows are waited for just before their first use: inside a run only row ky = 2 is new, and the MMAs of rows
+            // 0 and 1 run while it lands
+            if (ahead <= ky) {
+              mbar_wait(a_full + sw_, phw);
+              if (PAIR) mbar_wait_cluster(pa_full + sw_, phw);
+              if (++sw_ == nst) { sw_ = 0; phw ^= 1u; }
+              ++ahead;
+              tc_fence_after();
+            }
+            const uint32_t row_hi = abase + s * CV_STAGE_BYTES + off * CV_REC, row_lo = row_hi + CV_SEG_BYTES;
 #pragma unroll
-          for (int gq = 0; gq < CV_GROUPS; ++gq) {
+            for (int gq = 0; gq < CV_GROUPS; ++gq) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              // A: K-major SWIZZLE_128B, rows (pixels) 128 B apart, 8-row groups 1024 B apart; the 16-channel group is a
-              // 32-byte step inside the row, the tap a whole-record step (the swizzle works on the address bits)
-              const uint32_t a_hi = row_hi + kx * CV_REC + gq * 32, a_lo = row_lo + kx * CV_REC + gq * 32;
-              const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-                                     ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-              const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-                                     ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-              const uint64_t db = smem_desc(wbase + (gq * 9 + ky * 3 + kx) * CV_WTAP_BYTES, 2 * CV_HALF * 16, 128);   // rows: hi 0-31 | lo 32-63
-              const uint32_t acc = (ky | gq | kx) ? 1u : 0u;
-              if (CV_EXP & 8) continue;
-              if (PAIR) {
-                mma_f16_ss_2cta(d1, da_hi, db, id1, acc);          // x_hi . [W_hi | W_lo]   (each CTA supplies its 64 rows)
-                if (!(CV_EXP & 1)) mma_f16_ss_2cta(d2, da_lo, db, id2, 1u);           // x_lo . W_hi            (each CTA supplies its first 32 rows)
-              } else {
-                mma_f16_ss(d1, da_hi, db, id1, acc);
-                if (!(CV_EXP & 1)) mma_f16_ss(d2, da_lo, db, id2, 1u);
+              for (int kx = 0; kx < 3; ++kx) {
+                // A: K-major SWIZZLE_128B, rows (pixels) 128 B apart, 8-row groups 1024 B apart; the 16-channel group is a
+                // 32-byte step inside the row, the tap a whole-record step (the swizzle works on the address bits)
+                const uint32_t a_hi = row_hi + kx * CV_REC + gq * 32, a_lo = row_lo + kx * CV_REC + gq * 32;
+                const uint64_t da_hi = (uint64_t)((a_hi >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                                       ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                const uint64_t da_lo = (uint64_t)((a_lo >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+                                       ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                const uint64_t db = smem_desc(wbase + (gq * 9 + ky * 3 + kx) * CV_WTAP_BYTES, 2 * CV_HALF * 16, 128);   // rows: hi 0-31 | lo 32-63
+                const uint32_t acc = (ky | gq | kx) ? 1u : 0u;
+                if (CV_EXP & 8) continue;
+                if (PAIR) {
+                  mma_f16_ss_2cta(d1, da_hi, db, id1, acc);          // x_hi . [W_hi | W_lo]   (each CTA supplies its 64 rows)
+                  if (!(CV_EXP & 1)) mma_f16_ss_2cta(d2, da_lo, db, id2, 1u);           // x_lo . W_hi            (each CTA supplies its first 32 rows)
+                } else {
+                  mma_f16_ss(d1, da_hi, db, id1, acc);
+                  if (!(CV_EXP & 1)) mma_f16_ss(d2, da_lo, db, id2, 1u);
+                }
               }
             }
+            // row ky of this tile is row ky - 1 of the next tile of the run: only the tile's first row is done with
+            // (all three after the run's last tile)
+            if (ky == 0 || last) {
+              if (PAIR) mma_commit_2cta(a_empty + s); else mma_commit(a_empty + s);
+            }
           }
-          if (PAIR) mma_commit_2cta(a_empty + s); else mma_commit(a_empty + s);
+          if (PAIR) mma_commit_2cta(d_full + ab); else mma_commit(d_full + ab);
+          // next tile: inside a run one row further (two of its rows are already here), after the run three
+          const uint32_t adv = last ? 3u : 1u;
+          sb += adv; if (sb >= nst) sb -= nst;
+          ahead -= (int)adv;
         }
-        if (PAIR) mma_commit_2cta(d_full + ab); else mma_commit(d_full + ab);
       }
     }
   } else {
-    // ===================== epilogue: two groups of 4 warps, group g takes the items with (it & 1) == g; thread = pixel slot ======
+    // ===================== epilogue: two groups of 4 warps, group g takes the tiles with (it & 1) == g; thread = pixel slot ======
     const int grp = (warp - 2) >> 2, quad = warp & 3, lane = tid & 31;
     const int r = quad * 32 + lane;
     const float* meta = reinterpret_cast<const float*>(a.wpack + CV_WMETA_OFF);
@@ -432,17 +519,25 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
     const uint32_t l_de = PAIR ? mapa(smem_u32(d_empty + grp), 0) : 0u;
     constexpr int NCHUNK = PAIR ? 4 : 2;                       // 16 output channels per chunk
     const int cbase = PAIR ? 0 : (int)rank * CV_HALF;          // first output channel this CTA writes
-    const bool staged = PAIR && a.out_img != nullptr;          // pair kernel: records via smem + bulk stores
-    uint8_t* stg = smem + SM::STG + grp * (CV_M * CV_REC);       // this group's staging buffer
+    const bool staged = PAIR && eg.staged && a.out_img != nullptr;   // records via smem + bulk stores
+    uint8_t* stg = smem + sm_stg + grp * (CV_M * CV_REC);      // this group's staging buffer
     int cur_img = -1;
-    float inv = 0.f, s_out = 0.f;
-    int it = grp;
-    for (int w = w0 + grp * wstep; w < nwork; w += 2 * wstep, it += 2) {
-      int img, tile;
-      decode(w, img, tile);
-      const int p = tile * CV_M + r;
+    float inv = 0.f, s_out = 0.f, bound_cur = 0.f;
+    int it = 0;
+    for (int w = w0; w < nwork; w += wstep) {
+      int img, p0, y0; bool dummy;
+      decode(w, img, p0, y0, dummy);
+#pragma unroll 1
+      for (int i = 0; i < RL; ++i, ++it) {
+      if ((it & 1) != grp) continue;
+      const int p = p0 + i * eg.Wp + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
-      const bool valid = (p < eg.NkP) && (x < eg.W);
+      // strip tiles: slots past the row end belong to the next row's strip 0 and rows past the image to nobody
+      const bool covered = !dummy && (!eg.strip || ((p0 % eg.Wp) + r < eg.Wp && y0 + i < eg.H));
+      const bool valid = covered && (p < eg.NkP) && (x < eg.W);
+      // flat tiles write zero records for their dummy slots (the borders between the rows); strip tiles only their pixels
+      // (cv_zero_borders_kernel zeroes the rest once per call)
+      const bool wr_rec = eg.strip ? valid : !dummy;
       const size_t pix = (size_t)y * eg.W + x;
       if (img != cur_img) {
         cur_img = img;
@@ -454,8 +549,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
         if (a.res != nullptr) bound = bound * fabsf(a.res_scale) + __uint_as_float(a.res_meas[img]);
         bound *= 1.0001f;
         s_out = cv_pow2_scale(bound, 14);
-        if (a.out_amax != nullptr && tile == 0 && r == 0 && rank == 0) a.out_amax[img] = __float_as_uint(bound);
+        bound_cur = bound;
       }
+      // one thread per image (pixel slot 0; the single-CTA kernel visits it once per channel half) publishes the bound
+      if (a.out_amax != nullptr && p == 0 && !dummy && (PAIR || rank == 0)) a.out_amax[img] = __float_as_uint(bound_cur);
       const uint32_t trow = tbase + ((uint32_t)(quad * 32) << 16) + grp * SET;
       const size_t rec = (size_t)p + 3 * eg.Wp + 3;
       const int sw = (int)rec & 7;
@@ -504,9 +601,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
         for (int c = 0; c < NCHUNK * 16; ++c) op[(size_t)c * eg.Npix] = v[c];
       }
       if (a.out_img != nullptr && !(CV_EXP & 2)) {
-        // every record between the head and the tail region is written here: dummy slots (x >= W, p >= NkP) are the zero
-        // borders of the rows.  Pair kernel: the tile's 128 records are contiguous in the image, so they go through a 16 KB
-        // staging buffer and ONE bulk store per part (hi, then lo through the same buffer) instead of 1024 16-byte stores.
+        // Flat pair tiles: the tile's 128 records are contiguous in the image, so they go through a 16 KB staging buffer and
+        // ONE bulk store per part (hi, then lo through the same buffer) instead of 1024 16-byte stores.
         if (staged) {                                          // the previous item's lo store has read the staging buffer
           if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           named_bar_sync(1 + grp, 128);
@@ -514,24 +610,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
           uint4* dst = reinterpret_cast<uint4*>(staged ? stg + r * CV_REC : (part ? ilo : ihi) + rec * CV_REC);
+          if (staged || wr_rec) {
 #pragma unroll
-          for (int ch = 0; ch < NCHUNK; ++ch) {
-            uint32_t g[8];
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+              uint32_t g[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a0 = v[ch * 16 + 2 * j] * s_out, a1 = v[ch * 16 + 2 * j + 1] * s_out;
-              __half2 h = __floats2half2_rn(a0, a1);                           // one packed conversion (F2FP), not two F2F
-              if (part) { const float2 f = __half22float2(h); h = __floats2half2_rn(a0 - f.x, a1 - f.y); }
-              g[j] = *reinterpret_cast<uint32_t*>(&h);
+              for (int j = 0; j < 8; ++j) {
+                const float a0 = v[ch * 16 + 2 * j] * s_out, a1 = v[ch * 16 + 2 * j + 1] * s_out;
+                __half2 h = __floats2half2_rn(a0, a1);                           // one packed conversion (F2FP), not two F2F
+                if (part) { const float2 f = __half22float2(h); h = __floats2half2_rn(a0 - f.x, a1 - f.y); }
+                g[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              const int k0 = ((cbase + ch * 16) >> 3) ^ sw;                        // swizzled 16-byte chunk positions
+              dst[k0] = make_uint4(g[0], g[1], g[2], g[3]);
+              dst[k0 ^ 1] = make_uint4(g[4], g[5], g[6], g[7]);
             }
-            const int k0 = ((cbase + ch * 16) >> 3) ^ sw;                        // swizzled 16-byte chunk positions
-            dst[k0] = make_uint4(g[0], g[1], g[2], g[3]);
-            dst[k0 ^ 1] = make_uint4(g[4], g[5], g[6], g[7]);
           }
           if (staged) {
             fence_async_smem();
             named_bar_sync(1 + grp, 128);
-            if (r == 0) {
+            if (r == 0 && !dummy) {
               bulk_s2g((part ? ilo : ihi) + rec * CV_REC, stg, CV_M * CV_REC);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               if (part == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -540,26 +638,27 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
           }
         }
       }
-      if (a.out_img != nullptr && (tile == 0 || tile == eg.ntile - 1)) {
-        // head (records before the first slot) and tail (after the last slot) are zero borders too: this CTA's channels
-        // (the 16-byte chunks cbase/8 .. of every record; the swizzle permutes them within the record's half)
+      if (!eg.strip && !dummy && a.out_img != nullptr && (p0 == 0 || p0 == (eg.ntile - 1) * CV_M)) {
+        // flat tiles: head (records before the first slot) and tail (after the last slot) are zero borders too: this CTA's
+        // channels (the 16-byte chunks cbase/8 .. of every record; the swizzle permutes them within the record's half)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         auto zero_range = [&](size_t i0, size_t i1) {
-          for (size_t i = i0 + r; i < i1; i += CV_M)
+          for (size_t q = i0 + r; q < i1; q += CV_M)
 #pragma unroll
             for (int k = 0; k < NCHUNK * 2; ++k) {
-              const int kk = ((cbase >> 3) + k) ^ ((int)i & 7);
-              reinterpret_cast<uint4*>(ihi + i * CV_REC)[kk] = z;
-              reinterpret_cast<uint4*>(ilo + i * CV_REC)[kk] = z;
+              const int kk = ((cbase >> 3) + k) ^ ((int)q & 7);
+              reinterpret_cast<uint4*>(ihi + q * CV_REC)[kk] = z;
+              reinterpret_cast<uint4*>(ilo + q * CV_REC)[kk] = z;
             }
         };
-        if (tile == 0) zero_range(0, (size_t)3 * eg.Wp + 3);
-        if (tile == eg.ntile - 1) zero_range((size_t)eg.ntile * CV_M + 3 * eg.Wp + 3, (size_t)eg.NPG);
+        if (p0 == 0) zero_range(0, (size_t)3 * eg.Wp + 3);
+        if (p0 == (eg.ntile - 1) * CV_M) zero_range((size_t)eg.ntile * CV_M + 3 * eg.Wp + 3, (size_t)eg.NPG);
       }
       if (a.out_meas != nullptr) {
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o2));
         if (lane == 0 && vmax > 0.f) atomicMax(a.out_meas + img, __float_as_uint(vmax));
+      }
       }
     }
     if (staged && r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // smem is read / the stores are done before the CTA exits
@@ -617,19 +716,25 @@ static CvWs cv_ws(const CvGeom& e, int nblocks) {
 }
 size_t resblocks_workspace_bytes(int B, int H, int W, int nblocks) { return cv_ws(cv_geom(B, H, W), nblocks).total; }
 
-static int launch_conv(const CvGeom& e, const CvArgs& a, bool pair, cudaStream_t st) {
-  int dev = 0, sms = 148;
+static int cv_sm_count(int* sms) {
+  int dev = 0;
+  *sms = 148;
   DAGL_CUDA_OK(cudaGetDevice(&dev));
-  DAGL_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DAGL_CUDA_OK(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+static int launch_conv(const CvGeom& e, const CvArgs& a, bool pair, int sms, cudaStream_t st) {
   // grid = 2 x (CTA pairs): in both kernels CTA 2k+r holds the weights of channel half r and walks items k, k + n, ...
-  const int nwork = pair ? e.B * (e.ntile2 / 2) : e.B * e.ntile;
+  const int nruns = e.strip ? e.B * e.nstrip * e.nyb : (pair ? e.B * e.ntile2 : e.B * e.ntile);
+  const int nwork = pair ? (nruns + 1) / 2 : nruns;
   const int ncl = nwork < sms / 2 ? nwork : sms / 2;
   if (pair) {
-    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem<true>::TOTAL));
-    DAGL_CUDA_OK(launch_pdl_cluster2(conv64_tc_kernel<true>, dim3(2 * ncl), CV_THREADS, CvSmem<true>::TOTAL, st, e, a));
+    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl_cluster2(conv64_tc_kernel<true>, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
   } else {
-    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CvSmem<false>::TOTAL));
-    DAGL_CUDA_OK(launch_pdl(conv64_tc_kernel<false>, dim3(2 * ncl), CV_THREADS, CvSmem<false>::TOTAL, st, e, a));
+    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(conv64_tc_kernel<false>, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
   }
   DAGL_LAUNCH_CHECK();
   return 0;
@@ -639,12 +744,14 @@ static int launch_conv(const CvGeom& e, const CvArgs& a, bool pair, cudaStream_t
 // pre-packed by launch_pack_resblock_weights.  mode: 0 = CTA-pair kernel, 1 = single-CTA kernel, 2 = by size.
 int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks, const ResBlockParams* blocks, void* ws,
                      size_t ws_bytes, int mode, cudaStream_t st) {
-  const CvGeom e = cv_geom(B, H, W);
+  CvGeom e = cv_geom(B, H, W);
   const CvWs L = cv_ws(e, nblocks);
   if (ws_bytes < L.total) {
     call_state().err = "ResBlock chain: workspace too small";
     return -3;
   }
+  int sms = 148;
+  if (cv_sm_count(&sms)) return -4;
   char* base = static_cast<char*>(ws);
   uint8_t* img[3] = {reinterpret_cast<uint8_t*>(base + L.img[0]), reinterpret_cast<uint8_t*>(base + L.img[1]),
                      reinterpret_cast<uint8_t*>(base + L.img[2])};
@@ -656,6 +763,8 @@ int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks,
   // auto: the pair kernel once there are enough tiles for ~7 items per CTA pair (measured: 512^2 and the chop batches;
   // below that the single-CTA kernel's shorter start-up wins)
   const bool pair = mode == 0 || (mode == 2 && (long long)B * e.ntile >= 1024);
+  static const int force_flat = getenv("DAGL_CONV_FLAT") != nullptr ? atoi(getenv("DAGL_CONV_FLAT")) : 0;   // A/B aid
+  cv_plan(e, pair, sms / 2, force_flat);
 
   DAGL_CUDA_OK(cudaMemsetAsync(slots, 0, (size_t)nl * 2 * B * sizeof(unsigned), st));
   for (int i = 0; i < nblocks; ++i)
@@ -671,6 +780,10 @@ int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks,
   DAGL_LAUNCH_CHECK();
   DAGL_CUDA_OK(launch_pdl(cv_pack_kernel, dim3(((e.NPG + 255) / 256) * CV_GROUPS * B), 256, 0, st, e, x, (const unsigned*)meas_of(0), img[0]));
   DAGL_LAUNCH_CHECK();
+  if (e.strip) {                                  // strip tiles write pixels only: the borders of the two rotating images once per call
+    DAGL_CUDA_OK(launch_pdl(cv_zero_borders_kernel, dim3((e.NPG + 255) / 256, 2 * B), 256, 0, st, e, img[1], img[2]));
+    DAGL_LAUNCH_CHECK();
+  }
 
   int cur = 0;                                   // packed image holding the current block's input
   const unsigned* cur_bound = meas_of(0);
@@ -686,7 +799,7 @@ int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks,
     c1.wpack = pw; c1.bias = rb.b1; c1.slope = rb.slope; c1.slope_n = rb.slope_n;
     c1.res_scale = 1.f; c1.res = nullptr; c1.res_meas = nullptr; c1.out = nullptr;
     c1.out_img = img[mid]; c1.out_amax = bound_of(2 * i + 1); c1.out_meas = meas_of(2 * i + 1);
-    int rc = launch_conv(e, c1, pair, st);
+    int rc = launch_conv(e, c1, pair, sms, st);
     if (rc) return rc;
     CvArgs c2{};
     c2.in_img = img[mid]; c2.in_amax = bound_of(2 * i + 1); c2.in_meas = meas_of(2 * i + 1);
@@ -694,7 +807,7 @@ int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks,
     c2.res_scale = rb.res_scale; c2.res = res; c2.res_meas = meas_of(2 * i);
     c2.out = last ? y : f32[i & 1];
     c2.out_img = last ? nullptr : img[nxt]; c2.out_amax = last ? nullptr : bound_of(2 * i + 2); c2.out_meas = last ? nullptr : meas_of(2 * i + 2);
-    rc = launch_conv(e, c2, pair, st);
+    rc = launch_conv(e, c2, pair, sms, st);
     if (rc) return rc;
     res = c2.out; cur = nxt; cur_bound = bound_of(2 * i + 2);
   }

@@ -61,10 +61,14 @@ def test_golden_chains(dev, mode):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("shape,nb", [((1, 64, 64, 64), 1), ((2, 64, 37, 41), 2), ((1, 64, 5, 3), 1), ((1, 64, 1, 1), 2),
-                                      ((3, 64, 72, 72), 4), ((1, 64, 3, 300), 1), ((1, 64, 131, 2), 1), ((1, 64, 128, 122), 1)])
+                                      ((3, 64, 72, 72), 4), ((1, 64, 3, 300), 1), ((1, 64, 131, 2), 1), ((1, 64, 128, 122), 1),
+                                      # strip tiles (rows walked down 128-wide strips, one new halo row per tile): ragged second
+                                      # strip, odd run counts (pair kernel: a dummy run), short / tall images, several per batch
+                                      ((2, 64, 40, 250), 2), ((1, 64, 9, 104), 1), ((3, 64, 17, 128), 2), ((1, 64, 33, 256), 1),
+                                      ((1, 64, 70, 384), 1)])
 def test_chain_vs_oracle(dev, mode, shape, nb):
     """Seeded chains at ragged / tiny / chop-leaf shapes (tile boundaries inside rows, single-tile images, one-pixel images,
-    W = 122: padded pitch exactly 128)."""
+    W = 122: padded pitch exactly 128; widths that fill 128-wide strips run the row-reuse decomposition)."""
     from dagl_b200.resblock import resblocks_forward
     params = [RB.init_resblock_params(31 * nb + i) for i in range(nb)]
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(shape[2] * 1000 + shape[3]))

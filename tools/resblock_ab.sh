@@ -1,7 +1,8 @@
 #!/bin/bash
-# per-launch timeline of the ResBlock chain for every library variant (development aid)
+# ResBlock chain: parity + timing for both kernels, strip (row reuse) vs flat decomposition (development aid)
 O=gpurun_out; TAG=${1:-rbab}
-for lib in dagl_b200/libdagl_b200.so dagl_b200/variants/libcv*.so; do
-  for m in single pair; do DAGL_B200_LIB=$PWD/$lib timeout 120 python tools/resblock_check.py $m timeline 2>&1 | grep "per-launch" >> $O/${TAG}.log; done
+for m in single pair; do
+  timeout 200 python tools/resblock_check.py $m time > $O/${TAG}_$m.log 2>&1; echo "$m rc=$?"; tail -16 $O/${TAG}_$m.log
+  DAGL_CONV_FLAT=1 timeout 200 python tools/resblock_check.py $m time 2>&1 | grep "chain" | sed 's/^/FLAT /' | tee -a $O/${TAG}_$m.log
+  timeout 120 python tools/resblock_check.py $m timeline 2>&1 | grep "per-launch" | tee -a $O/${TAG}_$m.log
 done
-cat $O/${TAG}.log

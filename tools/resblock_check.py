@@ -22,7 +22,7 @@ def ref64(blocks, x):            # fp64 on the CPU: ground truth
 
 
 ok = True
-CASES = [((1, 64, 64, 64), 1), ((2, 64, 37, 41), 2), ((1, 64, 5, 3), 1), ((3, 64, 72, 72), 4), ((1, 64, 256, 256), 4)]
+CASES = [((1, 64, 64, 64), 1), ((2, 64, 37, 41), 2), ((1, 64, 5, 3), 1), ((3, 64, 72, 72), 4), ((2, 64, 40, 250), 2), ((1, 64, 33, 128), 1), ((1, 64, 256, 256), 4)]
 if len(sys.argv) > 2 and sys.argv[2] == "timeline":
     CASES = []
 for (shape, nb) in CASES:
