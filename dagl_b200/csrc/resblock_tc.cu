@@ -193,8 +193,13 @@ __global__ void cv_absmax_kernel(const float* __restrict__ x, size_t n_per_img, 
 }
 
 // layout: [img][hi|lo][NPG records][128 B = 64 ch], SWIZZLE_128B pre-applied: 16-byte chunk c of record r sits at c ^ (r & 7)
+// One thread per (pixel record, 16-channel group).  (One thread per whole record — 64 loads, two contiguous 128-byte stores —
+// measured slower: 17 vs 15 us at 256², 88 vs 48 us at 64x72²: a quarter of the threads.)  Border records are written as
+// zeros; with `zb0` / `zb1` (strip tiles, whose epilogues write pixels only) the same border records of the two rotating
+// output images are zeroed as well.
 __global__ void __launch_bounds__(256)
-cv_pack_kernel(CvGeom eg, const float* __restrict__ x, const unsigned* __restrict__ amax, uint8_t* __restrict__ img_out) {
+cv_pack_kernel(CvGeom eg, const float* __restrict__ x, const unsigned* __restrict__ amax, uint8_t* __restrict__ img_out,
+               uint8_t* __restrict__ zb0, uint8_t* __restrict__ zb1) {
   pdl_prologue();
   const int pblocks = (eg.NPG + 255) / 256;
   const int pb = blockIdx.x;
@@ -214,19 +219,29 @@ cv_pack_kernel(CvGeom eg, const float* __restrict__ x, const unsigned* __restric
       a0 = __ldg(src + (size_t)(2 * j) * eg.Npix) * scale;
       a1 = __ldg(src + (size_t)(2 * j + 1) * eg.Npix) * scale;
     }
-    const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-    const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
-    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    __half2 hh = __floats2half2_rn(a0, a1);
+    const float2 f = __half22float2(hh);
+    __half2 ll = __floats2half2_rn(a0 - f.x, a1 - f.y);
+    h[j] = *reinterpret_cast<uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<uint32_t*>(&ll);
   }
-  const int sw = pix & 7;
-  uint8_t* base = img_out + ((size_t)img * 2) * (size_t)eg.NPG * CV_REC + (size_t)pix * CV_REC;
-  uint4* dh = reinterpret_cast<uint4*>(base);
-  uint4* dl = reinterpret_cast<uint4*>(base + (size_t)eg.NPG * CV_REC);
-  dh[(2 * gq) ^ sw] = make_uint4(h[0], h[1], h[2], h[3]);
-  dh[(2 * gq + 1) ^ sw] = make_uint4(h[4], h[5], h[6], h[7]);
-  dl[(2 * gq) ^ sw] = make_uint4(l[0], l[1], l[2], l[3]);
-  dl[(2 * gq + 1) ^ sw] = make_uint4(l[4], l[5], l[6], l[7]);
+  const int k0 = (2 * gq) ^ (pix & 7), k1 = k0 ^ 1;
+  const size_t rec_off = ((size_t)img * 2) * (size_t)eg.NPG * CV_REC + (size_t)pix * CV_REC;
+  uint4* dh = reinterpret_cast<uint4*>(img_out + rec_off);
+  uint4* dl = reinterpret_cast<uint4*>(img_out + rec_off + (size_t)eg.NPG * CV_REC);
+  dh[k0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dh[k1] = make_uint4(h[4], h[5], h[6], h[7]);
+  dl[k0] = make_uint4(l[0], l[1], l[2], l[3]);
+  dl[k1] = make_uint4(l[4], l[5], l[6], l[7]);
+  if (!inb && zb0 != nullptr) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* a0 = reinterpret_cast<uint4*>(zb0 + rec_off);
+    uint4* a1 = reinterpret_cast<uint4*>(zb0 + rec_off + (size_t)eg.NPG * CV_REC);
+    uint4* b0 = reinterpret_cast<uint4*>(zb1 + rec_off);
+    uint4* b1 = reinterpret_cast<uint4*>(zb1 + rec_off + (size_t)eg.NPG * CV_REC);
+    a0[k0] = z; a0[k1] = z; a1[k0] = z; a1[k1] = z;
+    b0[k0] = z; b0[k1] = z; b1[k0] = z; b1[k1] = z;
+  }
 }
 
 // ---- the convolution ------------------------------------------------------------------------------------------
@@ -283,24 +298,6 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// border records of a packed image that no convolution epilogue writes in strip mode (frame rows 0-2 and H+3.., the
-// columns left and right of the pixels): zero, once per chain call, for the rotating output images
-__global__ void __launch_bounds__(256)
-cv_zero_borders_kernel(CvGeom eg, uint8_t* __restrict__ img_a, uint8_t* __restrict__ img_b) {
-  pdl_prologue();
-  const int rec = blockIdx.x * 256 + threadIdx.x;
-  if (rec >= eg.NPG) return;
-  const int R = rec / eg.Wp, Cc = rec % eg.Wp;
-  if (R >= CV_PADK && R < eg.H + CV_PADK && Cc >= CV_PADK && Cc < eg.W + CV_PADK) return;   // a pixel
-  const int img = blockIdx.y >> 1, part = blockIdx.y & 1;
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  const size_t off = (((size_t)img * 2 + part) * (size_t)eg.NPG + rec) * CV_REC;
-  uint4* da = reinterpret_cast<uint4*>(img_a + off);
-  uint4* db = reinterpret_cast<uint4*>(img_b + off);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { da[k] = z; db[k] = z; }
 }
 
 // Persistent.  Accumulator set s (two sets alternate; epilogue group s drains set s, so the epilogue of a tile overlaps the
@@ -536,7 +533,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
       const bool covered = !dummy && (!eg.strip || ((p0 % eg.Wp) + r < eg.Wp && y0 + i < eg.H));
       const bool valid = covered && (p < eg.NkP) && (x < eg.W);
       // flat tiles write zero records for their dummy slots (the borders between the rows); strip tiles only their pixels
-      // (cv_zero_borders_kernel zeroes the rest once per call)
+      // (cv_pack_kernel zeroes the rest once per call)
       const bool wr_rec = eg.strip ? valid : !dummy;
       const size_t pix = (size_t)y * eg.W + x;
       if (img != cur_img) {
@@ -778,12 +775,10 @@ int launch_resblocks(int B, int H, int W, const float* x, float* y, int nblocks,
   const size_t n_img = (size_t)CV_C * e.Npix;
   DAGL_CUDA_OK(launch_pdl(cv_absmax_kernel, dim3(128, B), 256, 0, st, x, n_img, meas_of(0)));
   DAGL_LAUNCH_CHECK();
-  DAGL_CUDA_OK(launch_pdl(cv_pack_kernel, dim3(((e.NPG + 255) / 256) * CV_GROUPS * B), 256, 0, st, e, x, (const unsigned*)meas_of(0), img[0]));
+  // strip tiles write pixels only: the pack launch also zeroes the border records of the two rotating output images
+  DAGL_CUDA_OK(launch_pdl(cv_pack_kernel, dim3(((e.NPG + 255) / 256) * CV_GROUPS * B), 256, 0, st, e, x, (const unsigned*)meas_of(0), img[0],
+                          e.strip ? img[1] : (uint8_t*)nullptr, e.strip ? img[2] : (uint8_t*)nullptr));
   DAGL_LAUNCH_CHECK();
-  if (e.strip) {                                  // strip tiles write pixels only: the borders of the two rotating images once per call
-    DAGL_CUDA_OK(launch_pdl(cv_zero_borders_kernel, dim3((e.NPG + 255) / 256, 2 * B), 256, 0, st, e, img[1], img[2]));
-    DAGL_LAUNCH_CHECK();
-  }
 
   int cur = 0;                                   // packed image holding the current block's input
   const unsigned* cur_bound = meas_of(0);
