@@ -304,7 +304,9 @@ def other_configs(ce, dev, flush, peaks):
                 ref = plain(x)
             finally:
                 torch.backends.cudnn.allow_tf32 = prev
-            rec["rel_err_vs_cudnn_fp32"] = float((seq(x) - ref).abs().max() / ref.abs().max())
+            y = seq(x)
+            rec["impl"] = dagl_b200._lib.lib().dagl_last_impl().decode()
+            rec["rel_err_vs_cudnn_fp32"] = float((y - ref).abs().max() / ref.abs().max())
         flops = 8 * 2.0 * B * Hh * Ww * 64 * 64 * 9
         rec["tflops_alg"] = flops / (rec["ms"] * 1e-3) / 1e12
         out.append(rec)

@@ -311,7 +311,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // frees position n0 + i (the last tile of a run frees all three).
 // Everything that does not depend on the previous kernel of the stream (barriers, TMEM, the weights, bias, slope) is set up
 // BEFORE griddepcontrol.wait, i.e. while the previous convolution is still running (programmatic dependent launch).
-template <bool PAIR>
+// STRIP: runs down 128-wide strips (4 ring stages, direct stores) / flat tiles (runs of one; pair: 3 stages + output staging):
+// compile-time so that the flat kernels carry none of the run logic (their single-thread loops are the critical path)
+template <bool PAIR, bool STRIP>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvArgs a) {
   constexpr int MAXST = 4;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -331,13 +333,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
 
   constexpr uint32_t TCOLS = PAIR ? 256 : 128;
   constexpr uint32_t SET = PAIR ? 128 : 64, D2OFF = 32;
-  const uint32_t nst = (uint32_t)eg.nst;
-  const int sm_w = eg.nst * CV_STAGE_BYTES, sm_stg = sm_w + CV_WHALF_BYTES;
+  constexpr uint32_t nst = (PAIR && !STRIP) ? 3u : 4u;
+  constexpr int sm_w = (int)nst * CV_STAGE_BYTES, sm_stg = sm_w + CV_WHALF_BYTES;
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
   const uint32_t rank = PAIR ? cluster_ctarank() : (blockIdx.x & 1u);       // = the channel half whose weights this CTA holds
-  const int RL = eg.RL;
-  const int nruns = eg.strip ? eg.B * eg.nstrip * eg.nyb : (PAIR ? eg.B * eg.ntile2 : eg.B * eg.ntile);
+  const int RL = STRIP ? eg.RL : 1;
+  const int nruns = STRIP ? eg.B * eg.nstrip * eg.nyb : (PAIR ? eg.B * eg.ntile2 : eg.B * eg.ntile);
   const int nwork = PAIR ? (nruns + 1) / 2 : nruns;
   const int w0 = (int)(blockIdx.x >> 1), wstep = (int)(gridDim.x >> 1);
   // item -> this CTA's run: image, first pixel slot p0, first image row y0 (strip), dummy = nothing to write
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
     int q = PAIR ? 2 * w + (int)rank : w;
     dummy = q >= nruns;
     if (dummy) q = nruns - 1;
-    if (eg.strip) {
+    if (STRIP) {
       const int per_img = eg.nstrip * eg.nyb;
       img = q / per_img;
       const int c = (q / eg.nyb) % eg.nstrip;
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
           // 3x3 / pad 1 inside the pad-3 frame: halo row j of the run = frame row (first image row) + j + 2; rows below the
           // image (runs padded to RL tiles) are clamped to a border row: loaded, never used by a valid pixel
           int start = p0 + (j + 2) * eg.Wp;
-          if (eg.strip && y0 + j + 2 > eg.H + 4) start = p0 + (eg.H + 4 - y0) * eg.Wp;
+          if (STRIP && y0 + j + 2 > eg.H + 4) start = p0 + (eg.H + 4 - y0) * eg.Wp;
           const int first = start & ~7;
           bulk_g2s(smem + s * CV_STAGE_BYTES + lane * CV_SEG_BYTES, src + (size_t)first * CV_REC, CV_SEG_BYTES, a_full + s);
         }
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
     const uint32_t l_de = PAIR ? mapa(smem_u32(d_empty + grp), 0) : 0u;
     constexpr int NCHUNK = PAIR ? 4 : 2;                       // 16 output channels per chunk
     const int cbase = PAIR ? 0 : (int)rank * CV_HALF;          // first output channel this CTA writes
-    const bool staged = PAIR && eg.staged && a.out_img != nullptr;   // records via smem + bulk stores
+    const bool staged = PAIR && !STRIP && a.out_img != nullptr;     // records via smem + bulk stores
     uint8_t* stg = smem + sm_stg + grp * (CV_M * CV_REC);      // this group's staging buffer
     int cur_img = -1;
     float inv = 0.f, s_out = 0.f, bound_cur = 0.f;
@@ -530,11 +532,11 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
       const int p = p0 + i * eg.Wp + r;
       const int y = p / eg.Wp, x = p % eg.Wp;
       // strip tiles: slots past the row end belong to the next row's strip 0 and rows past the image to nobody
-      const bool covered = !dummy && (!eg.strip || ((p0 % eg.Wp) + r < eg.Wp && y0 + i < eg.H));
+      const bool covered = !dummy && (!STRIP || ((p0 % eg.Wp) + r < eg.Wp && y0 + i < eg.H));
       const bool valid = covered && (p < eg.NkP) && (x < eg.W);
       // flat tiles write zero records for their dummy slots (the borders between the rows); strip tiles only their pixels
       // (cv_pack_kernel zeroes the rest once per call)
-      const bool wr_rec = eg.strip ? valid : !dummy;
+      const bool wr_rec = STRIP ? valid : !dummy;
       const size_t pix = (size_t)y * eg.W + x;
       if (img != cur_img) {
         cur_img = img;
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv64_tc_kernel(CvGeom eg, CvA
           }
         }
       }
-      if (!eg.strip && !dummy && a.out_img != nullptr && (p0 == 0 || p0 == (eg.ntile - 1) * CV_M)) {
+      if (!STRIP && !dummy && a.out_img != nullptr && (p0 == 0 || p0 == (eg.ntile - 1) * CV_M)) {
         // flat tiles: head (records before the first slot) and tail (after the last slot) are zero borders too: this CTA's
         // channels (the 16-byte chunks cbase/8 .. of every record; the swizzle permutes them within the record's half)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -727,11 +729,13 @@ static int launch_conv(const CvGeom& e, const CvArgs& a, bool pair, int sms, cud
   const int nwork = pair ? (nruns + 1) / 2 : nruns;
   const int ncl = nwork < sms / 2 ? nwork : sms / 2;
   if (pair) {
-    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
-    DAGL_CUDA_OK(launch_pdl_cluster2(conv64_tc_kernel<true>, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
+    auto kern = e.strip ? conv64_tc_kernel<true, true> : conv64_tc_kernel<true, false>;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl_cluster2(kern, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
   } else {
-    DAGL_CUDA_OK(cudaFuncSetAttribute(conv64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
-    DAGL_CUDA_OK(launch_pdl(conv64_tc_kernel<false>, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
+    auto kern = e.strip ? conv64_tc_kernel<false, true> : conv64_tc_kernel<false, false>;
+    DAGL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SM_TOTAL));
+    DAGL_CUDA_OK(launch_pdl(kern, dim3(2 * ncl), CV_THREADS, CV_SM_TOTAL, st, e, a));
   }
   DAGL_LAUNCH_CHECK();
   return 0;

@@ -208,3 +208,31 @@ def test_trained_resblocks_from_checkpoint(dev):
             got = resblocks_forward(make_blocks(params, dev), feat.to(dev), "pair").cpu()
         e = rel_err(got, want)
         assert e <= 2 * CHAIN_TOL, (name, e)                   # chains of eight: twice the four-block budget
+
+
+def test_repeated_calls_overwrite_poisoned_outputs(dev):
+    """Back-to-back chain calls (no host synchronisation in between, alternating shapes / kernels, the output buffer poisoned
+    with NaN before every call): every call must fully overwrite its output with the same bits."""
+    from dagl_b200 import _lib
+    from dagl_b200.resblock import _struct
+    L = _lib.lib()
+    params = [RB.init_resblock_params(60 + i) for i in range(2)]
+    blocks = make_blocks(params, dev)
+    arr = (_lib.DaglResBlockWeights * 2)(*[_struct(b, None) for b in blocks])
+    st = torch.cuda.current_stream().cuda_stream
+    cases = []
+    for shape, mode in (((1, 64, 64, 72), 0), ((2, 64, 24, 128), 1), ((1, 64, 40, 250), 0), ((3, 64, 30, 30), 2)):
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(shape[3])).to(dev)
+        ws = torch.empty(L.dagl_resblocks_workspace_bytes(2, *shape), dtype=torch.uint8, device=dev)
+        cases.append((shape, mode, x, ws, torch.empty_like(x), RB.chain_forward(params, x.cpu())))
+    first = {}
+    for rep in range(12):
+        for i, (shape, mode, x, ws, y, want) in enumerate(cases):
+            y.fill_(float("nan"))
+            rc = L.dagl_resblocks_forward_f32(arr, 2, x.data_ptr(), y.data_ptr(), *shape, ws.data_ptr(), ws.numel(), mode, st)
+            assert rc == 0, L.dagl_last_error()
+            if rep == 0:
+                first[i] = y.clone()
+                assert rel_err(first[i].cpu(), want) <= CHAIN_TOL
+            else:
+                assert torch.equal(y, first[i]), (rep, shape, mode)
