@@ -167,12 +167,12 @@ class CE(nn.Module):
             return CEFunction.apply(self, b, *self._grad_params())
         return self._forward_cuda(b)
 
-    def _forward_cuda(self, b: torch.Tensor) -> torch.Tensor:
+    def _forward_cuda(self, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         L = _lib.lib()
         b = b.contiguous()
         B, Cc, H, W = b.shape
         with torch.cuda.device(b.device):
-            y = torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
+            y = out if out is not None else torch.empty(B, self.inter_channels, H, W, dtype=torch.float32, device=b.device)
             nbytes = L.dagl_ce_workspace_bytes_ex(B, Cc, H, W, _lib.IMPL_BY_NAME[self.impl], 0)
             ws = _workspace(b.device, nbytes)
             w, keep = self._weights(b.device)
@@ -292,6 +292,11 @@ class CE(nn.Module):
             _lib.check(rc, "dagl_ce_fold_rows_f32")
         return y
 
+    def host_pipeline(self, B: int, H: int, W: int, depth: int = 2, device: Optional[torch.device] = None) -> "HostPipeline":
+        """Streaming host entry (see ``HostPipeline``): overlaps the host<->device copies of consecutive requests with the
+        kernels."""
+        return HostPipeline(self, B, H, W, depth, device)
+
     def forward_host(self, b_host: torch.Tensor, y_host: Optional[torch.Tensor] = None,
                      device: Optional[torch.device] = None, sync: bool = True) -> torch.Tensor:
         """Host-buffer entry (``dagl_ce_forward_host_f32``): ``b_host`` is a CPU
@@ -324,6 +329,67 @@ class CE(nn.Module):
             if sync:
                 torch.cuda.current_stream(device).synchronize()
         return y_host
+
+
+class HostPipeline:
+    """Streaming host entry for a fixed input shape: requests are submitted with host buffers and come back in host buffers,
+    and consecutive requests overlap — the H2D copy of request i+1 and the D2H copy of result i-1 run on their own streams
+    while the kernels of request i run (``depth`` device slots).  Throughput approaches max(forward, H2D, D2H) per request
+    instead of their sum (``CE.forward_host``); the latency of one request is unchanged.
+
+        pipe = ce.host_pipeline(B, H, W)
+        for b_host, y_host in requests:        # pinned fp32 host tensors [B,C,H,W] / [B,16,H,W]
+            pipe.submit(b_host, y_host)        # asynchronous; returns the event that marks y_host complete
+        pipe.drain()
+    """
+
+    def __init__(self, ce: "CE", B: int, H: int, W: int, depth: int = 2, device: Optional[torch.device] = None):
+        if depth < 2:
+            raise ValueError("depth must be >= 2")
+        self.ce, self.depth, self.n = ce, depth, 0
+        self.device = device or ce.g.weight.device
+        if self.device.type != "cuda":
+            raise RuntimeError("dagl_b200.CE has no CPU path: move the module to a CUDA device first")
+        self.shape_in, self.shape_out = (B, ce.in_channels, H, W), (B, ce.inter_channels, H, W)
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+            self.b_dev = [torch.empty(self.shape_in, dtype=torch.float32, device=self.device) for _ in range(depth)]
+            self.y_dev = [torch.empty(self.shape_out, dtype=torch.float32, device=self.device) for _ in range(depth)]
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        cur = torch.cuda.current_stream(self.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+
+    def submit(self, b_host: torch.Tensor, y_host: torch.Tensor) -> "torch.cuda.Event":
+        for t, shape, name in ((b_host, self.shape_in, "b_host"), (y_host, self.shape_out, "y_host")):
+            if (not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shape or
+                    not t.is_contiguous()):
+                raise RuntimeError(f"HostPipeline.submit: {name} must be a contiguous fp32 host tensor of shape {shape}")
+        k, used = self.n % self.depth, self.n >= self.depth
+        with torch.no_grad():
+            with torch.cuda.stream(self.s_in):
+                if used:
+                    self.s_in.wait_event(self.ev_run[k])         # the previous request of this slot has consumed b_dev[k]
+                self.b_dev[k].copy_(b_host, non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[k])
+                if used:
+                    self.s_run.wait_event(self.ev_out[k])        # ... and its result has left y_dev[k]
+                self.ce._forward_cuda(self.b_dev[k], out=self.y_dev[k])
+                self.ev_run[k].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[k])
+                y_host.copy_(self.y_dev[k], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+        self.n += 1
+        return self.ev_out[k]
+
+    def drain(self) -> None:
+        self.s_out.synchronize()
+        self.s_run.synchronize()
 
 
 def stage_heads_forward(heads, x: torch.Tensor) -> torch.Tensor:

@@ -525,3 +525,25 @@ def test_forward_is_cuda_graph_capturable(dev):
         want = ces(x)
     assert torch.equal(yg, want)
     assert not torch.equal(yg, y0)
+
+
+def test_host_pipeline_streams_requests(dev, rand_weights):
+    """CE.host_pipeline: six requests with different inputs through two device slots (copies of neighbouring requests overlap
+    the kernels); every result equals the plain device forward of its own input, bit for bit."""
+    import dagl_b200
+    ce = dagl_b200.CE(in_channels=64)
+    ce.load_state_dict(rand_weights)
+    ce = ce.to(dev).eval()
+    B, H, W = 2, 40, 36
+    gen = torch.Generator().manual_seed(17)
+    xs = [torch.randn(B, 64, H, W, generator=gen).pin_memory() for _ in range(6)]
+    ys = [torch.full((B, 16, H, W), float("nan")).pin_memory() for _ in range(6)]
+    pipe = ce.host_pipeline(B, H, W, depth=2)
+    evs = [pipe.submit(x, y) for x, y in zip(xs, ys)]
+    pipe.drain()
+    assert all(e.query() for e in evs)
+    with torch.no_grad():
+        for x, y in zip(xs, ys):
+            assert torch.equal(y, ce(x.to(dev)).cpu())
+    with pytest.raises(RuntimeError):
+        pipe.submit(xs[0][:, :, :8], ys[0])
