@@ -428,6 +428,7 @@ def main():
             ce(x_dev)
             stops[i].record()
             launches += ce.last_launches
+            launches_per_step = ce.last_launches
         barrier()
         t_wall = time.perf_counter() - t_wall0
         t_epoch1 = time.time()
@@ -508,6 +509,9 @@ def main():
             "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": traffic,
             "peak_source": f"{peaks['source']} bf16 dense burst (MEASURED_PEAKS.json)",
             "kernel": {"tc": "attend_tc2_kernel", "tc4": "attend_tc4_kernel", "simt": "attend_simt_kernel"}.get(impl_used, impl_used), "kernel_ms": k_avg, "kernel_share_of_step": k_avg / ms_per_step,
+            "kernel_note": ("the graph stage = attend_tc4_kernel on the first ~94 % of the keys + attend_tc2_kernel on the rest, launched as its "
+                            "programmatic dependent and running concurrently on the SMs the 4-CTA clusters cannot use; kernel_ms spans both, "
+                            "flops_per_launch is their sum (DAGL_HYBRID=0: the 4-CTA kernel alone)") if (impl_used == "tc4" and launches_per_step == 12) else None,
             "flops_per_launch": B_PER_GPU * FLOPS_ALG, "bytes_per_launch": B_PER_GPU * BYTES_ALG,
             "hbm_gbs_algorithmic": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9,
             "hbm_frac_of_measured": B_PER_GPU * BYTES_ALG / (k_avg * 1e-3) / 1e9 / peaks["hbm_gbs"],

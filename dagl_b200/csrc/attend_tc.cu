@@ -583,8 +583,14 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
                   float sm_scale_log2, int topk,
                   int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][2][Nq]*/,
-                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
-  pdl_prologue();
+                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz,
+                  int t_cut /*> 0: two unequal key splits [0, t_cut) | [t_cut, NT)*/, int split_base, int tail) {
+  // tail != 0: this launch runs NEXT TO the 4-CTA kernel (its programmatic dependent: launched once every CTA of that grid
+  // has started, onto the SMs the 4-CTA clusters cannot use) on the last part of the keys.  Its inputs were complete before
+  // the 4-CTA kernel triggered it, so it never waits (a CTA parked in griddepcontrol.wait would keep its SM from the next
+  // tail cluster); the kernel after it is launched WITHOUT the programmatic attribute, i.e. after both grids.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!tail) asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_BAR);
   uint64_t* q_full = bars + 0;
@@ -601,11 +607,11 @@ attend_tc2_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
 
   const int warp = warp_id_uniform();
   const int tid = threadIdx.x;
-  const int img = blockIdx.z, split = blockIdx.y;
+  const int img = blockIdx.z, split = blockIdx.y + split_base;
   const int qt = qt_base + (blockIdx.x >> 1);
   const int half = (int)cluster_ctarank();                  // == blockIdx.x & 1
-  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
-  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int t_begin = t_cut > 0 ? (split ? t_cut : 0) : (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = t_cut > 0 ? (split ? tg.NT : t_cut) : (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int ntiles = t_end - t_begin;
   const int n_own = (ntiles - half + 1) / 2;                // local tiles j with (j & 1) == half
 #ifdef DAGL_TC_TRACE
@@ -993,9 +999,17 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
                   const float4* __restrict__ thr4 /*per query row: mu partials (x, y), gamma, beta*/,
                   const unsigned* __restrict__ absmax, const unsigned* __restrict__ smax, const unsigned* __restrict__ smax2,
                   float sm_scale_log2, int topk,
-                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][Nq]: summed over the cluster*/,
-                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz) {
-  pdl_prologue();
+                  int nsplit, int qt_base, float* __restrict__ Opart, float* __restrict__ lpart /*[B][nsplit][nparts][Nq]: summed over the cluster*/,
+                  uint32_t* __restrict__ mask_bits, int32_t* __restrict__ nnz,
+                  int t_cut /*> 0: two unequal key splits [0, t_cut) | [t_cut, NT)*/, int nparts, int head) {
+  // head != 0: a 2-CTA tail launch follows as the programmatic dependent and runs concurrently: it must not start before
+  // the kernels in front of this one have completed, so the trigger comes after the wait
+  if (head) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else {
+    pdl_prologue();
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
   uint64_t* q_ready = bars + 0;   // query tile resident in TMEM (128 arrivals)
@@ -1016,8 +1030,8 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   const int img = blockIdx.z, split = blockIdx.y;
   const int qt = qt_base + (blockIdx.x >> 2);
   const int rank = (int)cluster_ctarank();                  // == blockIdx.x & 3
-  const int t_begin = (int)(((long long)split * tg.NT) / nsplit);
-  const int t_end = (int)(((long long)(split + 1) * tg.NT) / nsplit);
+  const int t_begin = t_cut > 0 ? (split ? t_cut : 0) : (int)(((long long)split * tg.NT) / nsplit);
+  const int t_end = t_cut > 0 ? (split ? tg.NT : t_cut) : (int)(((long long)(split + 1) * tg.NT) / nsplit);
   const int ntiles = t_end - t_begin;
   const int n_own = (ntiles - rank + 3) / 4;                // local tiles j with (j & 3) == rank
   const int nslots = rank == 3 ? 4 : 2;                     // theta rows this rank needs
@@ -1515,7 +1529,9 @@ attend_tc4_kernel(Geom g, TcGeom tg, const uint8_t* __restrict__ Qp, const uint8
   cluster_sync_all();
   if (rank == 0 && tid < TC_BM && qt * TC_BM + tid < g.Nq) {
     const float* ls = reinterpret_cast<const float*>(smem + S4_LSUM) + tid;
-    lpart[((size_t)img * nsplit + split) * g.Nq + qt * TC_BM + tid] = ((ls[0] + ls[TC_BM]) + ls[2 * TC_BM]) + ls[3 * TC_BM];
+    float* lp = lpart + ((size_t)img * nsplit + split) * nparts * g.Nq + qt * TC_BM + tid;
+    lp[0] = ((ls[0] + ls[TC_BM]) + ls[2 * TC_BM]) + ls[3 * TC_BM];
+    if (nparts > 1) lp[g.Nq] = 0.f;                         // layout shared with a 2-CTA tail launch (two partials per split)
   }
   if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tbase);
 }
@@ -1734,27 +1750,63 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
                             qt_begin, qt_end, smax, thr4, absmax, sm_scale_log2, topk, smax2, tilemask, (float*)nullptr));
     DAGL_LAUNCH_CHECK();
   }
+  // Hybrid: 4-CTA clusters only fit 33 at a time (GPC sizes), so a launch of <= 32 clusters leaves >= 20 SMs idle.  The last
+  // part of the keys then goes to a 2-CTA launch that runs on those SMs CONCURRENTLY (programmatic dependent launch: it
+  // starts once all CTAs of the 4-CTA grid are running, see the kernels); the cut balances the two by their measured
+  // per-tile rates.  DAGL_HYBRID=0 disables, DAGL_HYBRID=<permille> forces the tail's share of the keys.
+  int t_cut = 0, nsplit_run = w.nsplit, nparts = variant == 4 ? 1 : 2;
+  if (variant == 4 && w.nsplit == 1 && a.mask_bits == nullptr && a.nnz == nullptr && tg.NT >= 64) {
+    const char* hyb_env = getenv("DAGL_HYBRID");                 // read per call: the tests toggle it
+    const int hyb = hyb_env ? atoi(hyb_env) : -1;
+    const int ncl4 = (qt_end - qt_begin) * g.B;
+    const int idle = 148 - 4 * ncl4;
+    const TcWs wfull = tc_ws(g, tg, ranged ? qt_end - qt_begin : 0);
+    if (hyb != 0 && ncl4 <= 33 && idle >= 8 && wfull.nsplit >= 2) {
+      const int slots2 = idle / 2;
+      // measured at 1x64x256x256 (profiles/r2/r2w_hybrid_sweep.log): a 4-CTA cluster takes 0.45 us per key tile, a tail
+      // cluster 1.05 us + ~15 us of start-up, ~10 tail clusters run at a time.  Balance point of
+      //   (NT - x) c4 + o4 = waves2 (x c2 + o2)        [tile units of the 4-CTA kernel]
+      // and 20 % less than that: past the balance point the tail is the critical path and the time climbs steeply, and the
+      // number of SM pairs the 4-CTA clusters leave free depends on the chip's GPC configuration
+      const double c4 = 1.0, c2 = 2.6, o4 = 22.0, o2 = 45.0;
+      const double waves2 = (double)((ncl4 + slots2 - 1) / slots2);
+      double x = 0.8 * ((double)tg.NT * c4 + o4 - waves2 * o2) / (c4 + waves2 * c2);
+      if (hyb > 0) x = (double)tg.NT * hyb / 1000.0;
+      const int xt = (int)x;
+      if (xt >= 16 && xt <= tg.NT / 2) { t_cut = tg.NT - xt; nsplit_run = 2; nparts = 2; }
+    }
+  }
   if (int rc = prof_begin(st)) return rc;
   if (variant == 4) {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL));
+    if (t_cut > 0) grid.y = 1;
     DAGL_CUDA_OK(launch_pdl(attend_tc4_kernel, grid, V4_THREADS, S4_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
-                            sm_scale_log2, topk, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+                            sm_scale_log2, topk, nsplit_run, qt_begin, Opart, lpart, a.mask_bits, a.nnz, t_cut, nparts, t_cut > 0 ? 1 : 0));
+    if (t_cut > 0) {
+      DAGL_LAUNCH_CHECK();
+      DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
+      DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, dim3((qt_end - qt_begin) * 2, 1, g.B), TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp,
+                              tilemask, thr4, absmax, smax, smax2, sm_scale_log2, topk, nsplit_run, qt_begin, Opart, lpart,
+                              a.mask_bits, a.nnz, t_cut, 1, 1));
+    }
   } else {
     DAGL_CUDA_OK(cudaFuncSetAttribute(attend_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_TOTAL));
     DAGL_CUDA_OK(launch_pdl(attend_tc2_kernel, grid, TC2_THREADS, S2_TOTAL, st, g, tg, Qp, Kp, Thp, tilemask, thr4, absmax, smax, smax2,
-                            sm_scale_log2, topk, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz));
+                            sm_scale_log2, topk, w.nsplit, qt_begin, Opart, lpart, a.mask_bits, a.nnz, 0, 0, 0));
   }
   DAGL_LAUNCH_CHECK();
   if (int rc = prof_end(st)) return rc;
   const int q_begin = qt_begin * TC_BM, q_end = qt_end * TC_BM < g.Nq ? qt_end * TC_BM : g.Nq;
-  const int nparts = variant == 4 ? 1 : 2;       // row-sum partials per key split (the 4-CTA kernel reduces over its cluster)
   if (a.rows_out != nullptr) {   // sharded use: hand the merged, normalised rows to the caller (fold happens after the gather)
     const int nq_total = g.B * g.Nq;
-    DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, w.nsplit, nparts, q_begin, q_end, lpart, coef));
+    if (t_cut > 0)      // after a concurrent tail launch: a plain launch (= after BOTH grids), not a programmatic dependent of the tail
+      merge_coef_fixed_kernel<<<(nq_total + 255) / 256, 256, 0, st>>>(g.B, g.Nq, nsplit_run, nparts, q_begin, q_end, lpart, coef);
+    else
+    DAGL_CUDA_OK(launch_pdl(merge_coef_fixed_kernel, (nq_total + 255) / 256, 256, 0, st, g.B, g.Nq, nsplit_run, nparts, q_begin, q_end, lpart, coef));
     DAGL_LAUNCH_CHECK();
-    return launch_merge_rows(g, w.nsplit, q_begin, q_end, Opart, coef, a.rows_out, st);
+    return launch_merge_rows(g, nsplit_run, q_begin, q_end, Opart, coef, a.rows_out, st);
   }
-  return launch_fold_partials(g, w.nsplit, nparts, Opart, lpart, a.y, st);
+  return launch_fold_partials(g, nsplit_run, nparts, Opart, lpart, a.y, st, /*after_concurrent_grids=*/t_cut > 0);
 }
 
 }  // namespace dagl

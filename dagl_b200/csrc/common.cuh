@@ -193,7 +193,8 @@ int launch_rows_fold(const Geom& g, int nsplit, const float* Opart, const float*
 int launch_merge_rows(const Geom& g, int nsplit, int q_begin, int q_end, const float* Opart, const float* coef,
                       float* Omerged, cudaStream_t st);
 int launch_fold_rows(const Geom& g, const float* Omerged, float* y, int shift_major, cudaStream_t st);
-int launch_fold_partials(const Geom& g, int nsplit, int nparts, const float* Opart, const float* lpart, float* y, cudaStream_t st);
+int launch_fold_partials(const Geom& g, int nsplit, int nparts, const float* Opart, const float* lpart, float* y, cudaStream_t st,
+                         bool serialize = false);
 int launch_merge_fold(const Geom& g, int nsplit, const float* Opart, const float* mpart, const float* lpart,
                       float* coef, float* Omerged, float* y, int log2_units, int shift_major, float out_scale,
                       cudaStream_t st);

@@ -113,8 +113,14 @@ fold_partials_kernel(Geom g, int nsplit, int nparts, const float* __restrict__ O
   yo[0] = sum.x * inv; yo[(size_t)g.Nk] = sum.y * inv; yo[2 * (size_t)g.Nk] = sum.z * inv; yo[3 * (size_t)g.Nk] = sum.w * inv;
 }
 
-int launch_fold_partials(const Geom& g, int nsplit, int nparts, const float* Opart, const float* lpart, float* y, cudaStream_t st) {
+// `serialize`: the partials come from two grids that ran concurrently (attend_tc.cu, hybrid launch): a plain launch, which
+// starts after everything in front of it in the stream, instead of a programmatic dependent of the last one only
+int launch_fold_partials(const Geom& g, int nsplit, int nparts, const float* Opart, const float* lpart, float* y, cudaStream_t st,
+                         bool serialize) {
   const int total = g.B * 4 * g.Nk;
+  if (serialize)
+    fold_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(g, nsplit, nparts, Opart, lpart, y);
+  else
   DAGL_CUDA_OK(launch_pdl(fold_partials_kernel, (total + 255) / 256, 256, 0, st, g, nsplit, nparts, Opart, lpart, y));
   DAGL_LAUNCH_CHECK();
   return 0;

@@ -547,3 +547,35 @@ def test_host_pipeline_streams_requests(dev, rand_weights):
             assert torch.equal(y, ce(x.to(dev)).cpu())
     with pytest.raises(RuntimeError):
         pipe.submit(xs[0][:, :, :8], ys[0])
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 256, 256), (1, 64, 248, 248)])
+def test_hybrid_tail_launch(dev, rand_weights, shape):
+    """Single images whose 4-CTA clusters fit one wave unsplit (31 .. 33 query tiles: 248^2 .. 256^2) give the last part of the keys to a 2-CTA launch
+    that runs concurrently on the SMs the clusters cannot use (one more launch: 12).  Same result as the plain launch up to
+    the fp32 order of the two-way partial merge, and within the bar of the query-chunked oracle; the forced shares exercise
+    short and long tails."""
+    import os
+    gen = torch.Generator().manual_seed(29)
+    x = torch.randn(*shape, generator=gen)
+    ce = make_ce(rand_weights, dev, "tc4")
+    yref = O.ce_forward_chunked(rand_weights, x, chunk=256)
+    prev = os.environ.get("DAGL_HYBRID")
+    try:
+        outs = {}
+        for mode in ("0", None, "20", "300"):
+            if mode is None:
+                os.environ.pop("DAGL_HYBRID", None)
+            else:
+                os.environ["DAGL_HYBRID"] = mode
+            with torch.no_grad():
+                outs[mode] = ce(x.to(dev)).cpu()
+            assert ce.last_launches == (11 if mode == "0" else 12), (mode, ce.last_launches)
+            assert rel_err(outs[mode], yref) <= REL_TOL, (mode, rel_err(outs[mode], yref))
+        for mode in (None, "20", "300"):
+            assert rel_err(outs[mode], outs["0"]) <= 1e-5, (mode, rel_err(outs[mode], outs["0"]))
+    finally:
+        if prev is None:
+            os.environ.pop("DAGL_HYBRID", None)
+        else:
+            os.environ["DAGL_HYBRID"] = prev
