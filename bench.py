@@ -304,9 +304,15 @@ def other_configs(ce, dev, flush, peaks):
                 ref = plain(x)
             finally:
                 torch.backends.cudnn.allow_tf32 = prev
+            if not os.environ.get("DAGL_BENCH_NOPOISON"):
+                for _ in range(4):                                                # poison the allocator's free blocks of this size:
+                    torch.empty_like(x).fill_(float("nan"))                      # an output that is not written would show
             y = seq(x)
+            d_async = (y - ref).abs().max() / ref.abs().max()                    # consumed by torch at once, no synchronisation
             rec["impl"] = dagl_b200._lib.lib().dagl_last_impl().decode()
+            torch.cuda.synchronize()
             rec["rel_err_vs_cudnn_fp32"] = float((y - ref).abs().max() / ref.abs().max())
+            rec["rel_err_unsynchronised"] = float(d_async)
         flops = 8 * 2.0 * B * Hh * Ww * 64 * 64 * 9
         rec["tflops_alg"] = flops / (rec["ms"] * 1e-3) / 1e12
         out.append(rec)

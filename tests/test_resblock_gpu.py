@@ -236,3 +236,25 @@ def test_repeated_calls_overwrite_poisoned_outputs(dev):
                 assert rel_err(first[i].cpu(), want) <= CHAIN_TOL
             else:
                 assert torch.equal(y, first[i]), (rep, shape, mode)
+
+
+def test_outputs_are_ordered_before_following_torch_ops(dev):
+    """The chain's kernels are chained by programmatic dependent launch; whatever torch enqueues next on the stream must see
+    the finished output.  200 calls into freshly allocated (NaN-poisoned) outputs, each consumed at once by a torch kernel
+    with no host synchronisation, at a launch-bound and at a longer shape, single-block and four-block chains."""
+    from dagl_b200.resblock import resblocks_forward
+    params = [RB.init_resblock_params(70 + i) for i in range(4)]
+    blocks = make_blocks(params, dev)
+    for shape, nb in (((1, 64, 16, 16), 1), ((1, 64, 64, 64), 4), ((1, 64, 256, 256), 4), ((8, 64, 72, 72), 2)):
+        x = torch.randn(*shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        with torch.no_grad():
+            first = resblocks_forward(blocks[:nb], x).clone()
+            bad = torch.zeros((), device=dev)
+            for i in range(50):
+                for _ in range(3):
+                    torch.empty_like(x).fill_(float("nan"))            # poison the free blocks the next output will get
+                y = resblocks_forward(blocks[:nb], x)
+                d = (y - first).abs().max()                             # consumed immediately, no synchronisation
+                bad = torch.maximum(bad, torch.nan_to_num(d, nan=1e30))
+                del y
+        assert float(bad) == 0.0, (shape, nb, float(bad))

@@ -9,6 +9,7 @@ from oracle import ce_oracle as O
 
 NAMES_TC = ["absmax_img", "pack_b+gamma_beta", "featmap_tc(+G/theta img)", "gather_qpatch", "embed_tc<K>(+tiles)", "kbar",
             "embed_tc<Q>(+tiles,thr)", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
+NAMES_TC_HYBRID = NAMES_TC[:10] + ["attend_tc2 tail (concurrent: its mark = end of both)", "fold_partials"]
 NAMES_STAGE = ["absmax_img", "gamma_beta_heads", "pack_b", "featmap_tc(+G/theta img)", "gather_qpatch", "embed_tc<K>(+tiles)", "kbar",
                "embed_tc<Q>(+tiles,thr)", "rowmax_tc", "rowmax_exact", "attend_tc4", "fold_partials"]
 HEADS = int(os.environ.get("HEADS", "1"))        # > 1: one CES stage call (heads as a grid dimension)
@@ -41,7 +42,7 @@ with torch.no_grad():
         L.dagl_profile_enable(0)
         v = [buf[i] * 1e3 for i in range(n)]
         acc = v if acc is None else [a + b for a, b in zip(acc, v)]
-names = (NAMES_TC if len(acc) == len(NAMES_TC) and HEADS == 1 else NAMES_STAGE if len(acc) == len(NAMES_STAGE) and HEADS > 1 else
+names = (NAMES_TC if len(acc) == len(NAMES_TC) and HEADS == 1 else NAMES_TC_HYBRID if len(acc) == len(NAMES_TC_HYBRID) and HEADS == 1 else NAMES_STAGE if len(acc) == len(NAMES_STAGE) and HEADS > 1 else
          [f"launch {i}" for i in range(len(acc))])
 tot = 0.0
 for nm, t in zip(names, acc):
