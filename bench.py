@@ -257,6 +257,22 @@ def other_configs(ce, dev, flush, peaks):
                     "tflops_alg": flops / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]})
 
     shape_line("cfg1: CE.forward 1x64x64x64", 1, 64, 64, 50)
+    # the same forward replayed from a caller-side CUDA graph (11 dependent launches: the eager number is launch-latency-bound)
+    try:
+        xg1 = torch.randn(1, C_IN, 64, 64, generator=gen).to(dev)
+        with torch.no_grad():
+            side1 = torch.cuda.Stream()
+            side1.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side1):
+                for _ in range(2):
+                    ce(xg1)
+            torch.cuda.current_stream().wait_stream(side1)
+            graph1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph1, stream=side1):
+                ce(xg1)
+        shape_line("cfg1: CE.forward 1x64x64x64, replay of a caller-side CUDA graph", 1, 64, 64, 50, fn=lambda _x: graph1.replay())
+    except Exception as e:                                            # a bench extra, never fatal
+        out.append({"workload": "cfg1: CE.forward 1x64x64x64, CUDA graph", "error": str(e)[:200]})
     shape_line("chop leaves of 256^2: CE.forward 64x64x72x72", 64, 72, 72, 10)
     shape_line("chop leaves of 512^2: CE.forward 256x64x76x76", 256, 76, 76, 5)
     shape_line("cfg3/cfg5 head: CE.forward 1x64x512x512", 1, 512, 512, 5)
