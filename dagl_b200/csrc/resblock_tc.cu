@@ -69,7 +69,7 @@ constexpr int CV_PADK = 3;                           // frame of the packed imag
 //                        loads its three rows).  For narrow images (chop leaves: W = 72 -> 1.6 image rows per tile).
 //   strip = 1            tile (y, c) = pixels (y, 128 c .. 128 c + 127); runs walk down a strip.  For images whose width
 //                        fills the 128-wide strips (W/128 rounded up wastes < 20 %): a third of the L2 -> SM traffic.
-struct CvGeom { int B, H, W, Wp, NkP, ntile, ntile2, NPG, Npix, strip, nstrip, RL, nyb, nst, staged; };
+struct CvGeom { int B, H, W, Wp, NkP, ntile, ntile2, NPG, Npix, strip, nstrip, RL, nyb; };
 static CvGeom cv_geom(int B, int H, int W) {
   CvGeom e;
   e.B = B; e.H = H; e.W = W; e.Npix = H * W;
@@ -82,14 +82,14 @@ static CvGeom cv_geom(int B, int H, int W) {
   e.NPG = ((np > need ? np : need) + 7) & ~7;
   e.nstrip = (W + CV_M - 1) / CV_M;
   e.strip = (10 * W >= 8 * CV_M * e.nstrip && H >= 8) ? 1 : 0;
-  e.RL = 1; e.nyb = H; e.nst = 4; e.staged = 0;      // set per launch (cv_plan)
+  e.RL = 1; e.nyb = H;                               // set per launch (cv_plan)
   return e;
 }
-// per-launch plan: rows per run, ring stages, output staging
+// per-launch plan: rows per run (the ring depth and the output staging follow from the kernel instance: conv64_tc_kernel)
 static void cv_plan(CvGeom& e, bool pair, int workers, int force_flat) {
   if (force_flat) e.strip = 0;
   if (!e.strip) {
-    e.RL = 1; e.nyb = 0; e.nst = pair ? 3 : 4; e.staged = pair ? 1 : 0;
+    e.RL = 1; e.nyb = 0;
     return;
   }
   double best = 1e30;
@@ -101,7 +101,6 @@ static void cv_plan(CvGeom& e, bool pair, int workers, int force_flat) {
     if (cost <= best) { best = cost; e.RL = rl; }
   }
   e.nyb = (e.H + e.RL - 1) / e.RL;
-  e.nst = 4; e.staged = 0;
 }
 static inline size_t cv_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline size_t cv_image_bytes(const CvGeom& e) { return cv_align((size_t)e.B * 2 * e.NPG * CV_REC); }
