@@ -1757,7 +1757,11 @@ int launch_attend_tc(const Geom& g, const AttendArgs& a, const unsigned* absmax_
   int t_cut = 0, nsplit_run = w.nsplit, nparts = variant == 4 ? 1 : 2;
   if (variant == 4 && w.nsplit == 1 && a.mask_bits == nullptr && a.nnz == nullptr && tg.NT >= 64) {
     const char* hyb_env = getenv("DAGL_HYBRID");                 // read per call: the tests toggle it
-    const int hyb = hyb_env ? atoi(hyb_env) : -1;
+    int hyb = hyb_env ? atoi(hyb_env) : -1;
+    // Not inside a stream capture: in a captured graph the fold would depend on the tail node only (a full edge), and the tail
+    // on the 4-CTA node by a programmatic edge it never waits on — "after both grids" is a property of stream order only.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) hyb = 0;
     const int ncl4 = (qt_end - qt_begin) * g.B;
     const int idle = 148 - 4 * ncl4;
     const TcWs wfull = tc_ws(g, tg, ranged ? qt_end - qt_begin : 0);

@@ -579,3 +579,37 @@ def test_hybrid_tail_launch(dev, rand_weights, shape):
             os.environ.pop("DAGL_HYBRID", None)
         else:
             os.environ["DAGL_HYBRID"] = prev
+
+
+def test_hybrid_is_off_under_graph_capture(dev, rand_weights):
+    """'The fold runs after both grids' is a property of stream order; in a captured graph the fold node would depend on the tail
+    node only.  While a stream is being captured the launcher therefore takes the plain path: the replay equals the
+    DAGL_HYBRID=0 eager result bit for bit (and the eager default differs from it in the last bits: two-way partial merge)."""
+    import os
+    ce = make_ce(rand_weights, dev, "tc4")
+    x = torch.randn(1, 64, 256, 256, generator=torch.Generator().manual_seed(31)).to(dev)
+    prev = os.environ.pop("DAGL_HYBRID", None)
+    try:
+        with torch.no_grad():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    y_hybrid = ce(x)
+                assert ce.last_launches == 12
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                yg = ce(x)
+            assert ce.last_launches == 11
+            g.replay()
+            torch.cuda.synchronize()
+            os.environ["DAGL_HYBRID"] = "0"
+            y_plain = ce(x)
+        assert torch.equal(yg, y_plain)
+        assert rel_err(y_hybrid, y_plain) <= 1e-5
+    finally:
+        if prev is None:
+            os.environ.pop("DAGL_HYBRID", None)
+        else:
+            os.environ["DAGL_HYBRID"] = prev
